@@ -1,0 +1,517 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference in-process.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+Two import shims (nerfacc, viser.transforms) are needed and touch nothing on the hot path
+(SURVEY Appendix A).  tinycudann is absent, so every encoder takes the reference's pure-torch
+branch -- exactly the CPU path that BASELINE config 1 names.  Inputs come from tests/golden/synth.py
+(numpy PCG64) so the tests can regenerate them; only OUTPUTS are stored.
+"""
+import importlib.util
+import io
+import sys
+import types
+import warnings
+import zipfile
+from collections import OrderedDict
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+import synth  # noqa: E402
+
+REF = Path("/root/reference")
+na = types.ModuleType("nerfacc"); na.OccGridEstimator = object
+sys.modules["nerfacc"] = na
+v = types.ModuleType("viser"); vt = types.ModuleType("viser.transforms"); v.transforms = vt
+sys.modules["viser"] = v; sys.modules["viser.transforms"] = vt
+sys.path.insert(0, str(REF))
+warnings.filterwarnings("ignore")
+
+from nerfs.scene_box import SceneBox  # noqa: E402
+from nerfs.ray_sampling import get_ray_directions, get_rays, clamp_rays_near_far  # noqa: E402
+from nerfs.ray_rendering import render_rays, stratified_t_vals, volume_render  # noqa: E402
+from models.encodings import HashGridEncoder, SHEncoder  # noqa: E402
+from models.inr.meta_container import MetaContainer  # noqa: E402
+
+torch.set_num_threads(8)
+T = torch.from_numpy
+F32 = np.float32
+
+
+def save(name, **arrs):
+    np.savez_compressed(HERE / name, **{k: np.asarray(v) for k, v in arrs.items()})
+    sz = (HERE / name).stat().st_size
+    print(f"  {name}: {sz / 1024:.1f} KiB, keys={list(arrs)}")
+
+
+# --------------------------------------------------------------------------- stage 1
+def gen_stage1():
+    out = {}
+    H, W, fx, fy, cx, cy = 12, 16, 13.5, 14.25, 8.3, 5.9
+    for cp in (True, False):
+        out[f"dirs_cp{int(cp)}"] = get_ray_directions(H, W, fx, fy, cx, cy, cp, torch.device("cpu")).numpy()
+    box = SceneBox(aabb=T(synth.AABB_GLOBAL))
+    o, d = synth.random_rays_in_box(11, 4096)
+    tmin, tmax = box.ray_aabb_intersect(T(o), T(d))
+    out["aabb_tmin"], out["aabb_tmax"] = tmin.numpy(), tmax.numpy()
+    tmin, tmax = box.ray_aabb_intersect(T(o), T(d), invalid_value=float("inf"))
+    out["aabb_tmin_inf"], out["aabb_tmax_inf"] = tmin.numpy(), tmax.numpy()
+    # get_rays through a synthetic nadir camera
+    cam = synth.nadir_rays(5, 1, H=24, W=32, f=25.0)[0]
+    dirs = get_ray_directions(cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], True, torch.device("cpu"))
+    rays = get_rays(dirs, T(cam["c2w"]), scene_box=box, aabb_invalid_value=float("inf")).view(-1, 8)
+    out["cam_rays"] = rays.numpy()
+    out["cam_dirs"] = dirs.numpy()
+    for tag, ov in (("none", None), ("nn", (None, None)), ("nf", (0.05, 0.4)), ("n", (0.3, None))):
+        r2, valid = clamp_rays_near_far(rays, ov)
+        out[f"clamp_{tag}_rays"], out[f"clamp_{tag}_valid"] = r2.numpy(), valid.numpy()
+    # rays with constant near/far (no box)
+    out["rays_const"] = get_rays(dirs.view(-1, 3), T(cam["c2w"]), near=0.1, far=2.5).numpy()
+    for S in (2, 3, 16, 17, 64, 65, 96, 255, 256):
+        out[f"linspace_{S}"] = torch.linspace(0.0, 1.0, S).numpy()
+    # stratified t: eval + train with captured jitter
+    r2, valid = clamp_rays_near_far(rays, (None, None))
+    rv = r2[valid][:300]
+    for S in (16, 64, 96):
+        out[f"t_eval_{S}"] = stratified_t_vals(rv[:, 6], rv[:, 7], S, randomized=False).numpy()
+        torch.manual_seed(100 + S)
+        out[f"t_train_{S}"] = stratified_t_vals(rv[:, 6], rv[:, 7], S, randomized=True).numpy()
+        torch.manual_seed(100 + S)
+        out[f"jitter_{S}"] = torch.rand(rv.shape[0], S).numpy()
+    out["t_rays"] = rv.numpy()
+    tv = T(out["t_train_64"])
+    pts = rv[:, None, :3] + rv[:, None, 3:6] * tv[..., None]
+    out["pts_64"] = pts.numpy()
+    save("stage1.npz", **out)
+
+
+# --------------------------------------------------------------------------- stage 2
+def hash_inputs(seed, P):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1, (P, 3)).astype(F32)
+    x[:8] = np.float32(1e-6)
+    x[8:16] = np.float32(1.0) - np.float32(1e-6)
+    x[16:24, 0] = np.float32(0.5)      # exact cell boundaries on even resolutions
+    x[24:32] = (rng.integers(0, 16, (8, 3)) / 16.0).astype(F32)
+    return x
+
+
+def ref_indices(enc, x01):
+    L = enc.levels
+    levels = enc.level_resolutions.to(dtype=x01.dtype)
+    scaled = x01[..., None, :] * levels.view(1, L, 1)
+    fl = torch.floor(scaled).to(torch.int64)
+    ce = fl + 1
+    idx = []
+    for cxb in (0, 1):
+        for cyb in (0, 1):
+            for czb in (0, 1):
+                ix = (ce if cxb else fl)[..., 0]
+                iy = (ce if cyb else fl)[..., 1]
+                iz = (ce if czb else fl)[..., 2]
+                idx.append(enc._hash(ix, iy, iz) + enc.level_offsets)
+    return torch.stack(idx, dim=-1)  # (P,L,8) order 000,001,...,111 (x,y,z bits)
+
+
+def gen_hashgrid():
+    out = {}
+    P, L, F, log2T = 2048, 16, 2, 12
+    x = hash_inputs(21, P)
+    sd = synth.make_expert_params(22, L=L, F=F, log2T=log2T)
+    rng = np.random.default_rng(23)
+    dout = rng.standard_normal((P, L * F)).astype(F32)
+    for mode in ("Linear", "Smoothstep", "Nearest"):
+        enc = HashGridEncoder(levels=L, min_res=16, max_res=4096, log2_hashmap_size=log2T,
+                              features_per_level=F, interpolation=mode)
+        assert not enc._use_tcnn
+        with torch.no_grad():
+            enc.hash_table.copy_(T(sd["xyz_encoder.hash_table"]))
+        y = enc(T(x))
+        (y * T(dout)).sum().backward()
+        out[f"feat_{mode}"] = y.detach().numpy()
+        out[f"dtable_{mode}"] = enc.hash_table.grad.numpy()
+        if mode == "Linear":
+            out["res"] = enc.level_resolutions.numpy()
+            out["idx_T12"] = ref_indices(enc, T(x)).numpy().astype(np.int32)
+    for lt in (19, 20):
+        enc = HashGridEncoder(levels=1, log2_hashmap_size=lt)  # tiny table; only the hash matters
+        enc.levels = 16
+        big = HashGridEncoder.__new__(HashGridEncoder)
+        torch.nn.Module.__init__(big)
+        big.levels, big.log2_hashmap_size = 16, lt
+        big.register_buffer("level_resolutions", T(out["res"]))
+        big.register_buffer("level_offsets", torch.arange(16, dtype=torch.int64) * (2 ** lt))
+        big.register_buffer("hash_primes", torch.tensor([1, 2654435761, 805459861], dtype=torch.int64))
+        out[f"idx_T{lt}"] = ref_indices(big, T(x[:512])).numpy().astype(np.int32)
+    # other level configurations (resolutions only)
+    for (Lc, mn, mx) in ((16, 16, 4096), (16, 16, 2048), (8, 16, 512), (4, 16, 4096), (1, 16, 4096)):
+        e = HashGridEncoder(levels=Lc, min_res=mn, max_res=mx, log2_hashmap_size=4)
+        out[f"res_{Lc}_{mn}_{mx}"] = e.level_resolutions.numpy()
+    save("hashgrid.npz", **out)
+
+
+# --------------------------------------------------------------------------- experts / container
+HASH_CONF = dict(levels=16, features_per_level=2, log2_hashmap_size=12, max_res=4096, min_res=16,
+                 interpolation="Linear")
+
+
+def make_container(K, centroids, boxes, margin, use_bg, seed0, hash_conf=HASH_CONF, cluster_2d=True):
+    m = MetaContainer(
+        num_submodules=K, centroids=T(np.asarray(centroids, F32)), aabb=T(synth.AABB_GLOBAL),
+        boundary_margin=margin, cluster_2d=cluster_2d, use_bg_nerf=use_bg,
+        expert_box_list=[SceneBox(aabb=T(np.asarray(b, F32))) for b in boxes],
+        hidden=64, sigma_depth=2, color_depth=2, color_hidden=64, dir_encoding="spherical",
+        use_sigmoid_rgb=True, hash_enc_conf=dict(hash_conf), occ_conf={"use_occ": False})
+    sd = m.state_dict()
+    for k in range(K):
+        p = synth.make_expert_params(seed0 + k, L=hash_conf["levels"], F=hash_conf["features_per_level"],
+                                     log2T=hash_conf["log2_hashmap_size"])
+        for key, val in p.items():
+            sd[f"submodules.{k}.{key}"] = T(val)
+    if use_bg:
+        for key, val in synth.make_bg_params(seed0 + 100).items():
+            sd[key] = T(val)
+    m.load_state_dict(sd)
+    return m
+
+
+def expert_rays(seed, n):
+    cams = synth.nadir_rays(seed, 1, H=16, W=n // 16, f=14.0)
+    cam = cams[0]
+    box = SceneBox(aabb=T(synth.AABB_GLOBAL))
+    dirs = get_ray_directions(cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], True, torch.device("cpu"))
+    rays = get_rays(dirs, T(cam["c2w"]), scene_box=box).view(-1, 8)
+    rays, valid = clamp_rays_near_far(rays, (None, None))
+    assert bool(valid.all())
+    return rays
+
+
+def gen_field():
+    """MetaNGP.forward on world points + grads of a random linear functional."""
+    out = {}
+    m = make_container(1, np.zeros((1, 3)), [synth.AABB_GLOBAL], 1.0, False, 31)
+    ex = m.submodules[0]
+    rng = np.random.default_rng(32)
+    P = 1024
+    lo, hi = synth.AABB_GLOBAL
+    xyz = (lo + rng.uniform(-0.02, 1.02, (P, 3)) * (hi - lo)).astype(F32)  # a few outside -> clamp
+    d = rng.standard_normal((P, 3)).astype(F32)
+    d[:4] *= 1e-3
+    G = rng.standard_normal((P, 4)).astype(F32)
+    x6 = T(np.concatenate([xyz, d], axis=1))
+    y = ex(x6)
+    (y * T(G)).sum().backward()
+    out["xyz"], out["dirs"], out["G"], out["y"] = xyz, d, G, y.detach().numpy()
+    for key in synth.EXPERT_KEYS:
+        out["grad." + key] = dict(ex.named_parameters())[key].grad.numpy()
+    out["grad.xyz_encoder.hash_table"] = ex.xyz_encoder.hash_table.grad.numpy()
+    # intermediate pieces for stage-wise checks
+    with torch.no_grad():
+        x01 = ex._world_to_unit(T(xyz))
+        out["x01"] = x01.numpy()
+        out["enc"] = ex.xyz_encoder(x01).numpy()
+        out["sh"] = ex._enc_dir(T(d)).numpy()
+        dens = ex.density(T(xyz), return_feats=True)
+        out["sigma"], out["geo"] = dens["sigma"].numpy(), dens["geo_feat"].numpy()
+    save("field.npz", **out)
+
+
+def gen_composite():
+    out = {}
+    rng = np.random.default_rng(41)
+    N, S = 256, 48
+    rs = rng.uniform(-0.2, 1.2, (N, S, 4)).astype(F32)
+    rs[..., 3] = (rng.standard_normal((N, S)) * 30).astype(F32)   # mixed sign, large
+    rs[:32, :, 3] = np.abs(rs[:32, :, 3]) * 20                    # opaque early -> tests saturation
+    rs[32:48, :, 3] = -1.0                                         # empty rays
+    near = rng.uniform(0, 0.1, (N, 1)); far = near + rng.uniform(0.2, 0.6, (N, 1))
+    t = np.sort(near + (far - near) * rng.uniform(0, 1, (N, S)), axis=1).astype(F32)
+    t[48:64, 5] = t[48:64, 4]                                      # zero-length intervals -> 1e-4 clamp
+    bg = rng.uniform(0, 1, (N, 3)).astype(F32)
+    gs = [rng.standard_normal(s).astype(F32) for s in ((N, 3), (N,), (N, S), (N,))]
+    for tag, b, scale in (("bg", bg, 1.0), ("nobg", None, 1.0), ("scale", bg, 2.5)):
+        rst = T(rs).requires_grad_(True)
+        bgt = T(b).requires_grad_(True) if b is not None else None
+        o = volume_render(rst, T(t), bg_rgb=bgt, sigma_scale=scale)
+        loss = sum((oi * T(g)).sum() for oi, g in zip(o, gs))
+        loss.backward()
+        for name, oi in zip(("rgb", "depth", "weights", "acc"), o):
+            out[f"{tag}.{name}"] = oi.detach().numpy()
+        out[f"{tag}.d_rgb_sigma"] = rst.grad.numpy()
+        if bgt is not None:
+            out[f"{tag}.d_bg"] = bgt.grad.numpy()
+    out.update(rgb_sigma=rs, t=t, bg=bg, g_rgb=gs[0], g_depth=gs[1], g_weights=gs[2], g_acc=gs[3])
+    save("composite.npz", **out)
+
+
+def grid_centroids_2x4():
+    cams = np.array([[-0.04, -0.9, -0.9], [-0.04, 0.9, 0.9]], F32)
+    spec = importlib.util.spec_from_file_location("cc", REF / "scripts" / "create_clusters.py")
+    return spec, cams
+
+
+def load_cc():
+    for name in ("data.dataset", "data.image_metadata"):
+        pass
+    spec = importlib.util.spec_from_file_location("create_clusters_ref", REF / "scripts" / "create_clusters.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def gen_routing(cc):
+    out = {}
+    rng = np.random.default_rng(51)
+    P = 8192
+    lo, hi = synth.AABB_GLOBAL
+    pts = (lo + rng.uniform(0, 1, (P, 3)) * (hi - lo)).astype(F32)
+    pts[:16] = synth.CENTROIDS_G22[rng.integers(0, 4, 16)]            # exactly on a centroid
+    pts[16:64, 1] = 0.0                                               # on the Voronoi edge
+    pts[64:128, 2] = 0.0
+    cen8 = cc._grid_centroids(T(np.array([[-0.04, -0.9, -0.9], [-0.04, 0.9, 0.9]], F32)), 1, 2, 4, True).numpy().astype(F32)
+    out["pts"], out["cen8"] = pts, cen8
+    for tag, cen in (("g22", synth.CENTROIDS_G22), ("g24", cen8)):
+        K = cen.shape[0]
+        for margin in (1.0, 1.05, 1.1):
+            m = make_container(K, cen, [synth.AABB_GLOBAL] * K, margin, False, 61,
+                               hash_conf=dict(HASH_CONF, levels=1, log2_hashmap_size=4))
+            w, h = m._routing(T(pts))
+            if w is not None:
+                out[f"{tag}.w.{margin}"] = w.numpy()
+            else:
+                out[f"{tag}.hard.{margin}"] = h.numpy().astype(np.int32)
+    m = make_container(4, synth.CENTROIDS_G22 + np.array([[0.1, 0, 0], [0.3, 0, 0], [0.2, 0, 0], [0.0, 0, 0]], F32),
+                       [synth.AABB_GLOBAL] * 4, 1.05, False, 61,
+                       hash_conf=dict(HASH_CONF, levels=1, log2_hashmap_size=4), cluster_2d=False)
+    out["cen3d"] = m.centroids.numpy()
+    out["g22_3d.w.1.05"] = m._routing(T(pts))[0].numpy()
+    save("routing.npz", **out)
+
+
+def read_zip_mask(path):
+    with zipfile.ZipFile(path, "r") as zf:
+        name = zf.namelist()[0]
+        with zf.open(name) as f:
+            return torch.load(io.BytesIO(f.read()), map_location="cpu")
+
+
+def gen_voronoi(cc):
+    """Excerpts of the reference's SHIPPED masks (g22_grid_bm110_ss11) + compute_voronoi_orig."""
+    out = {}
+    root = REF / "data/drz/out/example"
+    mdir = root / "masks/g22_grid_bm110_ss11"
+    params = torch.load(mdir / "params.pt")
+    cents = params["centroids"]
+    out["centroids"] = cents.numpy()
+    out["margin"] = np.float32(params["boundary_margin"])
+    out["ray_samples"] = np.int32(params["ray_samples"])
+    box = SceneBox(aabb=params["aabb_global"])
+    out["aabb"] = params["aabb_global"].numpy()
+    rng = np.random.default_rng(71)
+    for stem in ("000005", "000007"):
+        md = torch.load(root / "train/metadata" / f"{stem}.pt", map_location="cpu")
+        H, W = int(md["H"]), int(md["W"])
+        fx, fy, cx, cy = md["intrinsics"]
+        dirs = get_ray_directions(H, W, fx, fy, cx, cy, True, torch.device("cpu"))
+        rays = get_rays(dirs, md["c2w"], scene_box=box, aabb_max_bound=1e10,
+                        aabb_invalid_value=float("inf")).view(-1, 8)
+        rays, valid = clamp_rays_near_far(rays, (None, None))
+        shipped = torch.stack([read_zip_mask(mdir / str(c) / f"{stem}.pt").view(-1) for c in range(4)], dim=1)
+        # pick pixels: random + every pixel whose membership differs from its right neighbour (edges)
+        sm = shipped.view(H, W, 4)
+        edge = (sm[:, 1:] != sm[:, :-1]).any(-1)
+        edge_idx = torch.nonzero(edge.reshape(-1)).squeeze(1)
+        edge_lin = (edge_idx // (W - 1)) * W + (edge_idx % (W - 1))
+        pick_e = edge_lin[T(rng.choice(len(edge_lin), size=min(3000, len(edge_lin)), replace=False))] if len(edge_lin) else edge_lin
+        pick_r = T(rng.choice(H * W, size=5000, replace=False))
+        pick = torch.unique(torch.cat([pick_e, pick_r]))
+        sub = rays[pick]
+        vor = cc.compute_voronoi_orig(sub, ray_samples=256, ray_chunk_size=32768, sample_chunk_size=2 ** 29,
+                                      centroids=cents, cluster_2d=True, device=torch.device("cpu"),
+                                      boundary_margin=float(params["boundary_margin"]))
+        mine = vor & valid[pick].unsqueeze(1)
+        mism = int((mine != shipped[pick]).sum())
+        print(f"  voronoi {stem}: {len(pick)} px, reference-vs-shipped mismatches = {mism}")
+        assert mism == 0
+        out[f"{stem}.pix"] = pick.numpy().astype(np.int32)
+        out[f"{stem}.rays"] = sub.numpy()
+        out[f"{stem}.valid"] = valid[pick].numpy()
+        out[f"{stem}.shipped"] = shipped[pick].numpy()
+        out[f"{stem}.voronoi_raw"] = vor.numpy()
+        out[f"{stem}.c2w"] = md["c2w"].numpy()
+        out[f"{stem}.intrinsics"] = np.array([float(a) for a in md["intrinsics"]], np.float64)
+        out[f"{stem}.HW"] = np.array([H, W], np.int32)
+    # margin 1.05 and hard rule have no shipped masks: run the reference
+    sub = T(out["000005.rays"][:2048])
+    for margin in (1.0, 1.05):
+        out[f"voronoi_m{margin}"] = cc.compute_voronoi_orig(
+            sub, ray_samples=64, ray_chunk_size=32768, sample_chunk_size=2 ** 29, centroids=cents,
+            cluster_2d=True, device=torch.device("cpu"), boundary_margin=margin).numpy()
+    save("voronoi.npz", **out)
+
+
+def grads_of(model, loss):
+    model.zero_grad(set_to_none=True)
+    loss.backward()
+    return {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+
+def table_digest(g):
+    """Per-level sums / abs-sums plus a fixed strided subsample of a (L*T,F) table gradient."""
+    g = g.numpy()
+    return g[:: 97].copy(), np.array([g.sum(dtype=np.float64), np.abs(g).sum(dtype=np.float64)])
+
+
+def gen_render():
+    """render_rays end to end: one expert (active_module=0) eval + train, fast weights, and a
+    4-expert soft-routed container with the background MLP."""
+    out = {}
+    rays = expert_rays(81, 256)
+    out["rays"] = rays.numpy()
+    S = 32
+    rngG = np.random.default_rng(82)
+    Gr = rngG.standard_normal((rays.shape[0], 3)).astype(F32)
+    Gd = rngG.standard_normal((rays.shape[0],)).astype(F32)
+    m = make_container(1, np.zeros((1, 3)), [synth.AABB_GLOBAL], 1.0, False, 83)
+    for mode in ("eval", "train"):
+        m.train(mode == "train")
+        torch.manual_seed(7)
+        o = render_rays(m, rays, ray_samples=S, active_module=0, chunk=1 << 20)
+        if mode == "train":
+            torch.manual_seed(7)
+            out["jitter"] = torch.rand(rays.shape[0], S).numpy()
+        loss = (o[0] * T(Gr)).sum() + (o[1] * T(Gd)).sum()
+        g = grads_of(m, loss)
+        for name, oi in zip(("rgb", "depth", "weights", "acc"), o):
+            out[f"{mode}.{name}"] = oi.detach().numpy()
+        for key in synth.EXPERT_KEYS:
+            out[f"{mode}.grad.{key}"] = g[f"submodules.0.{key}"].numpy()
+        sub, dig = table_digest(g["submodules.0.xyz_encoder.hash_table"])
+        out[f"{mode}.grad.table_sub"], out[f"{mode}.grad.table_digest"] = sub, dig
+    out["G_rgb"], out["G_depth"] = Gr, Gd
+    # fast weights (params=): with active_module set render_rays hands `params` straight to the
+    # expert (ray_rendering.py:323-325), so keys are expert-relative (meta_core.py:27,196-205)
+    m.eval()
+    fast = OrderedDict((n, (p * 1.25).detach().requires_grad_(True))
+                       for n, p in m.submodules[0].meta_named_parameters())
+    o = render_rays(m, rays, ray_samples=S, params=fast, active_module=0)
+    out["fast.rgb"] = o[0].detach().numpy()
+    gr = torch.autograd.grad((o[0] * T(Gr)).sum(), list(fast.values()))
+    for (n, _), gi in zip(fast.items(), gr):
+        out["fast.grad." + n] = gi.numpy()
+    out["fast.keys"] = np.array(list(fast.keys()))
+    # 4-expert container, soft routing 1.05 and hard routing, background MLP
+    box = SceneBox(aabb=T(synth.AABB_GLOBAL))
+    cam = synth.nadir_rays(84, 1, H=16, W=16, f=7.0)[0]     # wide FOV: crosses all four cells
+    cam["c2w"] = synth.camera_c2w(0.03, -0.02, 0.3)
+    dirs = get_ray_directions(16, 16, cam["fx"], cam["fy"], cam["cx"], cam["cy"], True, torch.device("cpu"))
+    rays4 = get_rays(dirs, T(cam["c2w"]), scene_box=box).view(-1, 8)
+    rays4, valid = clamp_rays_near_far(rays4, (None, None))
+    rays4 = rays4[valid]
+    out["rays4"] = rays4.numpy()
+    G4 = rngG.standard_normal((rays4.shape[0], 3)).astype(F32)
+    out["G4"] = G4
+    for tag, margin in (("soft", 1.05), ("hard", 1.0)):
+        mc = make_container(4, synth.CENTROIDS_G22, synth.EXPERT_BOXES_G22, margin, True, 85)
+        mc.eval()
+        o = render_rays(mc, rays4, ray_samples=S, active_module=None, chunk=1 << 20)
+        g = grads_of(mc, (o[0] * T(G4)).sum())
+        for name, oi in zip(("rgb", "depth", "weights", "acc"), o):
+            out[f"{tag}.{name}"] = oi.detach().numpy()
+        for k in range(4):
+            for key in ("sigma_trunk.0.linear.weight", "color_mlp.2.bias", "sigma_head.weight"):
+                out[f"{tag}.grad.{k}.{key}"] = g[f"submodules.{k}.{key}"].numpy()
+            sub, dig = table_digest(g[f"submodules.{k}.xyz_encoder.hash_table"])
+            out[f"{tag}.grad.{k}.table_sub"], out[f"{tag}.grad.{k}.table_digest"] = sub, dig
+        for key in ("bg_mlp.0.weight", "bg_mlp.2.bias"):
+            out[f"{tag}.grad.{key}"] = g[key].numpy()
+        with torch.no_grad():
+            pts = (rays4[:, None, :3] + rays4[:, None, 3:6] * stratified_t_vals(rays4[:, 6], rays4[:, 7], S, False)[..., None]).reshape(-1, 3)
+            w, h = mc._routing(pts)
+            if w is not None:
+                out[f"{tag}.support"] = (w > 0).numpy()
+            else:
+                out[f"{tag}.assign"] = h.numpy().astype(np.int32)
+    save("render.npz", **out)
+
+
+def gen_train():
+    """Fixed-step Adam training of one expert on an analytic scene; PSNR trajectory."""
+    out = {}
+    steps, N, S = 150, 1024, 32
+    conf = dict(HASH_CONF, log2_hashmap_size=14)
+    m = make_container(1, np.zeros((1, 3)), [synth.AABB_GLOBAL], 1.0, False, 91, hash_conf=conf)
+    # reference init scale for the table (encodings.py:267) so the optimisation is realistic
+    with torch.no_grad():
+        m.submodules[0].xyz_encoder.hash_table.mul_(1e-3 / 0.5)
+    groups = m.get_param_groups()
+    opt = torch.optim.Adam([
+        {"params": groups["encoding"]["params"], "lr": 1e-2},
+        {"params": groups["sigma"]["params"], "lr": 2e-3},
+        {"params": groups["color"]["params"], "lr": 2e-3}], eps=1e-15)
+    cams = synth.nadir_rays(92, 8, H=32, W=32, f=30.0)
+    box = SceneBox(aabb=T(synth.AABB_GLOBAL))
+    all_rays = []
+    for cam in cams:
+        dirs = get_ray_directions(cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], True, torch.device("cpu"))
+        r = get_rays(dirs, T(cam["c2w"]), scene_box=box).view(-1, 8)
+        r, valid = clamp_rays_near_far(r, (None, None))
+        all_rays.append(r[valid])
+    all_rays = torch.cat(all_rays)
+    # analytic target: colour of the ground point hit at x = 0.45 (a smooth function of y,z)
+    tg = (0.45 - all_rays[:, 0]) / all_rays[:, 3]
+    hit = all_rays[:, :3] + all_rays[:, 3:6] * tg[:, None]
+    gt = torch.stack([0.5 + 0.5 * torch.sin(3 * hit[:, 1]), 0.5 + 0.5 * torch.cos(2 * hit[:, 2]),
+                      0.5 + 0.25 * torch.sin(2 * hit[:, 1] + hit[:, 2])], dim=1).clamp(0, 1)
+    out["all_rays"], out["gt"] = all_rays.numpy(), gt.numpy()
+    rng = np.random.default_rng(93)
+    batch_idx = rng.integers(0, all_rays.shape[0], (steps, N))
+    out["batch_idx"] = batch_idx.astype(np.int32)
+    m.train()
+    torch.manual_seed(1234)
+    jit = torch.rand(steps, N, S)
+    out["jitter_seed"] = np.int64(1234)
+    psnr = []
+    import nerfs.ray_rendering as rr
+    for it in range(steps):
+        idx = T(batch_idx[it])
+        rays, tgt = all_rays[idx], gt[idx]
+        # feed the captured jitter: stratified_t_vals draws rand_like(low) -> patch torch.rand_like once
+        orig = torch.rand_like
+        torch.rand_like = lambda x, _j=jit[it]: _j
+        try:
+            rgb, *_ = render_rays(m, rays, ray_samples=S, active_module=0)
+        finally:
+            torch.rand_like = orig
+        loss = torch.nn.functional.mse_loss(rgb, tgt)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        psnr.append(-10.0 * np.log10(float(loss) + 1e-24))
+    out["psnr"] = np.array(psnr, np.float64)
+    m.eval()
+    with torch.no_grad():
+        rgb, *_ = render_rays(m, all_rays[:2048], ray_samples=S, active_module=0)
+        out["final_eval_psnr"] = np.float64(-10.0 * np.log10(float(torch.nn.functional.mse_loss(rgb, gt[:2048])) + 1e-24))
+    print("  train psnr first/last:", psnr[0], psnr[-1], "eval:", out["final_eval_psnr"])
+    save("train.npz", **out)
+
+
+if __name__ == "__main__":
+    which = set(sys.argv[1:])
+    cc = None
+    def want(n):
+        return not which or n in which
+    if want("stage1"): gen_stage1()
+    if want("hashgrid"): gen_hashgrid()
+    if want("field"): gen_field()
+    if want("composite"): gen_composite()
+    if want("routing") or want("voronoi"):
+        cc = load_cc()
+    if want("routing"): gen_routing(cc)
+    if want("voronoi"): gen_voronoi(cc)
+    if want("render"): gen_render()
+    if want("train"): gen_train()

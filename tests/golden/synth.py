@@ -1,0 +1,107 @@
+"""Seeded synthetic inputs shared by tests/golden/make_golden.py (which runs the reference in
+the build container) and by the tests (which run the oracle and the CUDA path).  Only numpy's
+PCG64 is used so the numbers are identical everywhere; nothing here touches torch RNG."""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+
+#: shipped global scene box (reference data/drz/out/example/masks/*/params.pt `aabb_global`)
+AABB_GLOBAL = np.array([[-0.046124, -1.1, -1.1], [0.497646, 1.1, 1.1]], F32)
+#: shipped 2x2 grid centroids (same file, `centroids`), cluster_2d=True
+CENTROIDS_G22 = np.array(
+    [[-1.1642e-10, -0.43409, -0.484345], [-1.1642e-10, -0.43409, 0.484345],
+     [-1.1642e-10, 0.43409, -0.484345], [-1.1642e-10, 0.43409, 0.484345]], F32)
+#: shipped per-expert boxes (scene_boxes.pt mins/maxs) for the 2x2 grid, margin 1.10
+EXPERT_BOXES_G22 = np.array(
+    [[[-0.046124, -1.1, -1.1], [0.497646, 0.062537, 0.06695]],
+     [[-0.046124, -1.1, -0.06695], [0.497646, 0.062537, 1.1]],
+     [[-0.046124, -0.062537, -1.1], [0.497646, 1.1, 0.06695]],
+     [[-0.046124, -0.062537, -0.06695], [0.497646, 1.1, 1.1]]], F32)
+
+EXPERT_KEYS = [
+    "sigma_trunk.0.linear.weight", "sigma_trunk.0.linear.bias",
+    "sigma_trunk.1.linear.weight", "sigma_trunk.1.linear.bias",
+    "sigma_head.weight", "sigma_head.bias", "geo_head.weight", "geo_head.bias",
+    "color_mlp.0.linear.weight", "color_mlp.0.linear.bias",
+    "color_mlp.1.linear.weight", "color_mlp.1.linear.bias",
+    "color_mlp.2.weight", "color_mlp.2.bias",
+]
+
+
+def expert_shapes(E=32, H=64, G=15, C=64):
+    return [(H, E), (H,), (H, H), (H,), (1, H), (1,), (G, H), (G,),
+            (C, G + 16), (C,), (C, C), (C,), (3, C), (3,)]
+
+
+def make_expert_params(seed, L=16, F=2, log2T=12, E=None, H=64, G=15, C=64, table_scale=0.5):
+    """Random-init weights with nn.Linear-like scale, sigma bias -1 (meta_ngp.py:83-84)."""
+    rng = np.random.default_rng(seed)
+    E = L * F if E is None else E
+    sd = {}
+    for key, shp in zip(EXPERT_KEYS, expert_shapes(E, H, G, C)):
+        fan_in = shp[-1] if len(shp) == 2 else None
+        if key.endswith("weight"):
+            bound = 1.0 / np.sqrt(fan_in)
+            last_fan = fan_in
+        else:
+            bound = 1.0 / np.sqrt(last_fan)
+        sd[key] = rng.uniform(-bound, bound, size=shp).astype(F32)
+    sd["sigma_head.bias"][:] = -1.0
+    sd["xyz_encoder.hash_table"] = rng.uniform(-table_scale, table_scale, size=(L << log2T, F)).astype(F32)
+    return sd
+
+
+def expert_weight_list(sd):
+    return [sd[k] for k in EXPERT_KEYS]
+
+
+def make_bg_params(seed, hidden=32):
+    rng = np.random.default_rng(seed)
+    b0, b1 = 1 / np.sqrt(16), 1 / np.sqrt(hidden)
+    return {
+        "bg_mlp.0.weight": rng.uniform(-b0, b0, (hidden, 16)).astype(F32),
+        "bg_mlp.0.bias": rng.uniform(-b0, b0, (hidden,)).astype(F32),
+        "bg_mlp.2.weight": rng.uniform(-b1, b1, (3, hidden)).astype(F32),
+        "bg_mlp.2.bias": rng.uniform(-b1, b1, (3,)).astype(F32),
+    }
+
+
+def camera_c2w(y, z, yaw=0.0, x=-0.04):
+    """Nadir camera (RUB -> world DRB, x = down), SURVEY 8(d)."""
+    cy, sy = np.cos(yaw), np.sin(yaw)
+    R0 = np.array([[0, 0, -1], [1, 0, 0], [0, -1, 0]], np.float64)
+    Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]], np.float64)  # spin about the optical axis
+    R = R0 @ Rz
+    c2w = np.concatenate([R, np.array([[x], [y], [z]])], axis=1)
+    return c2w.astype(F32)
+
+
+def random_rays_in_box(seed, N, aabb=AABB_GLOBAL):
+    """Generic ray soup: origins around the box, mostly pointing inwards, a few degenerate
+    (axis-parallel, zero component, missing the box)."""
+    rng = np.random.default_rng(seed)
+    lo, hi = aabb[0].astype(np.float64), aabb[1].astype(np.float64)
+    ctr, ext = 0.5 * (lo + hi), hi - lo
+    o = ctr + (rng.uniform(-1.2, 1.2, (N, 3)) * ext)
+    tgt = ctr + rng.uniform(-0.5, 0.5, (N, 3)) * ext
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    k = max(1, N // 16)
+    d[:k, 0] = 0.0                       # exactly zero component
+    d[k:2 * k, 1] = 1e-9                 # below eps
+    d[2 * k:3 * k] = np.array([1.0, 0.0, 0.0])
+    d[3 * k:4 * k] *= -1.0               # pointing away
+    return o.astype(F32), d.astype(F32)
+
+
+def nadir_rays(seed, n_views, H=64, W=64, f=60.0):
+    """Camera parameters for n_views synthetic 64x64 nadir views."""
+    rng = np.random.default_rng(seed)
+    cams = []
+    for _ in range(n_views):
+        y, z = rng.uniform(-0.9, 0.9, 2)
+        yaw = rng.uniform(-np.pi, np.pi)
+        cams.append(dict(H=H, W=W, fx=f, fy=f, cx=W / 2.0, cy=H / 2.0, c2w=camera_c2w(y, z, yaw)))
+    return cams
