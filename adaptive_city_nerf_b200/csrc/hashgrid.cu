@@ -1,0 +1,259 @@
+// Stage 2: multiresolution hash-grid encode, forward and atomic-scatter backward.
+//
+// Forward: one thread per point walks all L levels (8 independent gathers per level, levels
+// unrolled so ~32 loads are in flight per thread) and emits the point's full feature row, so
+// every output line is written by one thread.  Indices are bit-exact with the reference's
+// int64 hash; features follow the reference's un-fused lerp order (bit-exact in fp32).
+// Backward: one thread per (point, level), level fastest, so the dL/dout reads are fully
+// coalesced; the 8 corner updates go out as vector red.global.add.v2.f32 (F = 2).
+#include "hashgrid.cuh"
+
+// Where a point's position comes from: an explicit (P,>=3) array, or rays (N,8) + t (N,S), in
+// which case p = o + d*t is formed here (un-fused, nerfs/ray_rendering.py:317) and the
+// reference's (N*S,6) id6 tensor is never materialised.
+struct PosSrc { const float* x; int xs; const float* rays; const float* t; int S; };
+
+__device__ __forceinline__ void load_pos(const PosSrc& s, int64_t p, float& px, float& py, float& pz) {
+    if (s.rays) {
+        const float* ry = s.rays + 8 * (p / s.S);
+        const float t = __ldg(s.t + p);
+        px = __fadd_rn(__ldg(ry + 0), __fmul_rn(__ldg(ry + 3), t));
+        py = __fadd_rn(__ldg(ry + 1), __fmul_rn(__ldg(ry + 4), t));
+        pz = __fadd_rn(__ldg(ry + 2), __fmul_rn(__ldg(ry + 5), t));
+    } else {
+        px = s.x[p * s.xs]; py = s.x[p * s.xs + 1]; pz = s.x[p * s.xs + 2];
+    }
+}
+
+template <int F>
+__device__ __forceinline__ void load_feat(const float* __restrict__ t, uint32_t row, float* f) {
+    if constexpr (F == 2) {
+        float2 v = __ldg(reinterpret_cast<const float2*>(t) + row);
+        f[0] = v.x; f[1] = v.y;
+    } else if constexpr (F == 4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(t) + row);
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < F; ++i) f[i] = __ldg(t + (size_t)row * F + i);
+    }
+}
+
+template <typename T> __device__ __forceinline__ T to_out(float v);
+template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
+
+template <int F, typename OutT>
+__global__ void __launch_bounds__(256) k_hashgrid_fwd(
+    PosSrc pos, int64_t P, const float* __restrict__ box6,
+    const float* __restrict__ table, int L, int log2T, const int32_t* __restrict__ res, int interp,
+    OutT* __restrict__ out, int32_t* __restrict__ idx_out)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float px, py, pz;
+    load_pos(pos, p, px, py, pz);
+    if (box6) {
+        px = world_to_unit1(px, __ldg(box6 + 0), __ldg(box6 + 3));
+        py = world_to_unit1(py, __ldg(box6 + 1), __ldg(box6 + 4));
+        pz = world_to_unit1(pz, __ldg(box6 + 2), __ldg(box6 + 5));
+    }
+    const uint32_t mask = (1u << log2T) - 1u;
+    OutT* orow = out + (size_t)p * L * F;
+#pragma unroll 4
+    for (int l = 0; l < L; ++l) {
+        const float resf = (float)__ldg(res + l);
+        const float* lt = table + ((size_t)l << log2T) * F;
+        float o[F];
+        if (interp == ACN_INTERP_NEAREST) {
+            // models/encodings.py:342-345: torch.round = round half to even
+            uint32_t ix = (uint32_t)(int)rintf(__fmul_rn(px, resf));
+            uint32_t iy = (uint32_t)(int)rintf(__fmul_rn(py, resf));
+            uint32_t iz = (uint32_t)(int)rintf(__fmul_rn(pz, resf));
+            uint32_t row = grid_hash(ix, iy, iz, mask);
+            if (idx_out) idx_out[((size_t)p * L + l) * 8] = (int32_t)(row + ((uint32_t)l << log2T));
+            load_feat<F>(lt, row, o);
+        } else {
+            GridCell g = grid_cell(px, py, pz, resf, interp);
+            float f[8][F];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t row = grid_corner_row(g, c, mask);
+                if (idx_out) idx_out[((size_t)p * L + l) * 8 + c] = (int32_t)(row + ((uint32_t)l << log2T));
+                load_feat<F>(lt, row, f[c]);
+            }
+            float ux = __fsub_rn(1.0f, g.wx), uy = __fsub_rn(1.0f, g.wy), uz = __fsub_rn(1.0f, g.wz);
+#pragma unroll
+            for (int i = 0; i < F; ++i) {
+                float c00 = lerp_rn(f[0][i], f[4][i], g.wx, ux), c01 = lerp_rn(f[1][i], f[5][i], g.wx, ux);
+                float c10 = lerp_rn(f[2][i], f[6][i], g.wx, ux), c11 = lerp_rn(f[3][i], f[7][i], g.wx, ux);
+                float c0 = lerp_rn(c00, c10, g.wy, uy), c1 = lerp_rn(c01, c11, g.wy, uy);
+                o[i] = lerp_rn(c0, c1, g.wz, uz);
+            }
+        }
+        if constexpr (F == 2 && sizeof(OutT) == 4) {
+            reinterpret_cast<float2*>(orow)[l] = make_float2(o[0], o[1]);
+        } else if constexpr (F == 2 && sizeof(OutT) == 2) {
+            reinterpret_cast<__half2*>(orow)[l] = __floats2half2_rn(o[0], o[1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < F; ++i) orow[l * F + i] = to_out<OutT>(o[i]);
+        }
+    }
+}
+
+template <int F>
+__device__ __forceinline__ void scatter_add(float* __restrict__ t, uint32_t row, const float* g, float w) {
+    if constexpr (F == 2) {
+        atomicAdd(reinterpret_cast<float2*>(t) + row, make_float2(g[0] * w, g[1] * w));
+    } else if constexpr (F == 4) {
+        atomicAdd(reinterpret_cast<float4*>(t) + row, make_float4(g[0] * w, g[1] * w, g[2] * w, g[3] * w));
+    } else {
+#pragma unroll
+        for (int i = 0; i < F; ++i) atomicAdd(t + (size_t)row * F + i, g[i] * w);
+    }
+}
+
+template <typename T> __device__ __forceinline__ float from_in(T v);
+template <> __device__ __forceinline__ float from_in<float>(float v) { return v; }
+template <> __device__ __forceinline__ float from_in<__half>(__half v) { return __half2float(v); }
+
+template <int F, typename InT>
+__global__ void __launch_bounds__(256) k_hashgrid_bwd(
+    PosSrc pos, int64_t P, const float* __restrict__ box6, int L, int log2T,
+    const int32_t* __restrict__ res, int interp, const InT* __restrict__ dout, float* __restrict__ dtable)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P * L) return;
+    int64_t p = idx / L;
+    int l = (int)(idx - p * L);
+    float g[F];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < F; ++i) { g[i] = from_in<InT>(dout[idx * F + i]); any |= (g[i] != 0.0f); }
+    if (!any) return;  // zero gradient rows (e.g. fully occluded samples) scatter nothing
+    float px, py, pz;
+    load_pos(pos, p, px, py, pz);
+    if (box6) {
+        px = world_to_unit1(px, __ldg(box6 + 0), __ldg(box6 + 3));
+        py = world_to_unit1(py, __ldg(box6 + 1), __ldg(box6 + 4));
+        pz = world_to_unit1(pz, __ldg(box6 + 2), __ldg(box6 + 5));
+    }
+    const uint32_t mask = (1u << log2T) - 1u;
+    const float resf = (float)__ldg(res + l);
+    float* lt = dtable + ((size_t)l << log2T) * F;
+    if (interp == ACN_INTERP_NEAREST) {
+        uint32_t ix = (uint32_t)(int)rintf(__fmul_rn(px, resf));
+        uint32_t iy = (uint32_t)(int)rintf(__fmul_rn(py, resf));
+        uint32_t iz = (uint32_t)(int)rintf(__fmul_rn(pz, resf));
+        scatter_add<F>(lt, grid_hash(ix, iy, iz, mask), g, 1.0f);
+        return;
+    }
+    GridCell c = grid_cell(px, py, pz, resf, interp);
+    float wx[2] = { 1.0f - c.wx, c.wx }, wy[2] = { 1.0f - c.wy, c.wy }, wz[2] = { 1.0f - c.wz, c.wz };
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float w = wz[k & 1] * wy[(k >> 1) & 1] * wx[(k >> 2) & 1];
+        scatter_add<F>(lt, grid_corner_row(c, k, mask), g, w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+static int check_grid_args(const char* fn, int64_t P, int xs, int L, int F, int log2T, const void* res, int interp) {
+    ACN_REQUIRE(P >= 0 && xs >= 3, ACN_EINVAL, "%s: bad P / x_stride", fn);
+    ACN_REQUIRE(L >= 1 && L <= 64 && res, ACN_EINVAL, "%s: bad level count / res table", fn);
+    ACN_REQUIRE(log2T >= 1 && log2T <= 24, ACN_EUNSUPPORTED, "%s: log2_hashmap_size %d outside [1,24]", fn, log2T);
+    ACN_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8, ACN_EUNSUPPORTED, "%s: features_per_level %d not in {1,2,4,8}", fn, F);
+    ACN_REQUIRE(interp >= 0 && interp <= 2, ACN_EINVAL, "%s: bad interpolation mode", fn);
+    ACN_REQUIRE(((int64_t)L << log2T) <= ((int64_t)1 << 31), ACN_EUNSUPPORTED, "%s: table rows exceed int32", fn);
+    return ACN_OK;
+}
+
+#define DISPATCH_F(F_, CALL)                    \
+    switch (F_) {                               \
+        case 1: { constexpr int FF = 1; CALL; } break; \
+        case 2: { constexpr int FF = 2; CALL; } break; \
+        case 4: { constexpr int FF = 4; CALL; } break; \
+        default: { constexpr int FF = 8; CALL; } break; \
+    }
+
+static int hashgrid_fwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P, const float* box6_or_null,
+                             const float* table, int L, int F, int log2T, const int32_t* res, int interp,
+                             void* out, int out_dtype, int32_t* idx_out_or_null, acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    int rc = check_grid_args(fn, P, pos.rays ? 3 : pos.xs, L, F, log2T, res, interp);
+    if (rc) return rc;
+    ACN_REQUIRE(out_dtype == ACN_F32 || out_dtype == ACN_F16, ACN_EINVAL, "%s: bad out dtype", fn);
+    if (P == 0) return ACN_OK;
+    ACN_REQUIRE((pos.x || (pos.rays && pos.t && pos.S >= 1)) && table && out, ACN_EINVAL, "%s: null buffer", fn);
+    ACN_REQUIRE(((uintptr_t)table & 15) == 0 && ((uintptr_t)out & 7) == 0, ACN_EINVAL, "%s: misaligned table/out", fn);
+    const int block = 256;
+    const int grid = acn_grid_1d(P, block);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == ACN_F32) {
+        DISPATCH_F(F, (k_hashgrid_fwd<FF, float><<<grid, block, 0, st>>>(pos, P, box6_or_null, table, L, log2T, res,
+                                                                        interp, (float*)out, idx_out_or_null)));
+    } else {
+        DISPATCH_F(F, (k_hashgrid_fwd<FF, __half><<<grid, block, 0, st>>>(pos, P, box6_or_null, table, L, log2T, res,
+                                                                         interp, (__half*)out, idx_out_or_null)));
+    }
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
+
+static int hashgrid_bwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P, const float* box6_or_null, int L,
+                             int F, int log2T, const int32_t* res, int interp, const void* dout, int dout_dtype,
+                             float* dtable, acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    int rc = check_grid_args(fn, P, pos.rays ? 3 : pos.xs, L, F, log2T, res, interp);
+    if (rc) return rc;
+    ACN_REQUIRE(dout_dtype == ACN_F32 || dout_dtype == ACN_F16, ACN_EINVAL, "%s: bad dout dtype", fn);
+    if (P == 0) return ACN_OK;
+    ACN_REQUIRE((pos.x || (pos.rays && pos.t && pos.S >= 1)) && dout && dtable, ACN_EINVAL, "%s: null buffer", fn);
+    ACN_REQUIRE(((uintptr_t)dtable & 15) == 0, ACN_EINVAL, "%s: misaligned dtable", fn);
+    const int block = 256;
+    const int grid = acn_grid_1d(P * L, block);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dout_dtype == ACN_F32) {
+        DISPATCH_F(F, (k_hashgrid_bwd<FF, float><<<grid, block, 0, st>>>(pos, P, box6_or_null, L, log2T, res, interp,
+                                                                        (const float*)dout, dtable)));
+    } else {
+        DISPATCH_F(F, (k_hashgrid_bwd<FF, __half><<<grid, block, 0, st>>>(pos, P, box6_or_null, L, log2T, res, interp,
+                                                                         (const __half*)dout, dtable)));
+    }
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
+
+extern "C" int acn_hashgrid_fwd(acn_ctx* ctx, const float* x, int64_t P, int x_stride, const float* box6_or_null,
+                                const float* table, int L, int F, int log2T, const int32_t* res, int interp,
+                                void* out, int out_dtype, int32_t* idx_out_or_null, acn_stream stream) {
+    PosSrc pos{ x, x_stride, nullptr, nullptr, 0 };
+    return hashgrid_fwd_impl(ctx, "acn_hashgrid_fwd", pos, P, box6_or_null, table, L, F, log2T, res, interp, out, out_dtype,
+                             idx_out_or_null, stream);
+}
+
+extern "C" int acn_hashgrid_bwd(acn_ctx* ctx, const float* x, int64_t P, int x_stride, const float* box6_or_null, int L,
+                                int F, int log2T, const int32_t* res, int interp, const void* dout, int dout_dtype,
+                                float* dtable, acn_stream stream) {
+    PosSrc pos{ x, x_stride, nullptr, nullptr, 0 };
+    return hashgrid_bwd_impl(ctx, "acn_hashgrid_bwd", pos, P, box6_or_null, L, F, log2T, res, interp, dout, dout_dtype, dtable, stream);
+}
+
+extern "C" int acn_hashgrid_fwd_rays(acn_ctx* ctx, const float* rays8, const float* t_vals, int64_t N, int S,
+                                     const float* box6_or_null, const float* table, int L, int F, int log2T,
+                                     const int32_t* res, int interp, void* out, int out_dtype, acn_stream stream) {
+    ACN_REQUIRE(N >= 0 && S >= 1, ACN_EINVAL, "acn_hashgrid_fwd_rays: bad N / S");
+    PosSrc pos{ nullptr, 0, rays8, t_vals, S };
+    return hashgrid_fwd_impl(ctx, "acn_hashgrid_fwd_rays", pos, N * S, box6_or_null, table, L, F, log2T, res, interp, out,
+                             out_dtype, nullptr, stream);
+}
+
+extern "C" int acn_hashgrid_bwd_rays(acn_ctx* ctx, const float* rays8, const float* t_vals, int64_t N, int S,
+                                     const float* box6_or_null, int L, int F, int log2T, const int32_t* res, int interp,
+                                     const void* dout, int dout_dtype, float* dtable, acn_stream stream) {
+    ACN_REQUIRE(N >= 0 && S >= 1, ACN_EINVAL, "acn_hashgrid_bwd_rays: bad N / S");
+    PosSrc pos{ nullptr, 0, rays8, t_vals, S };
+    return hashgrid_bwd_impl(ctx, "acn_hashgrid_bwd_rays", pos, N * S, box6_or_null, L, F, log2T, res, interp, dout, dout_dtype,
+                             dtable, stream);
+}

@@ -1,0 +1,402 @@
+"""Operator layer: one thin Python function per C-ABI entry point plus the torch.autograd
+Functions that stitch the kernels into PyTorch's graph.  Python owns all storage; the shims
+make inputs contiguous fp32, allocate outputs with torch.empty and pass raw pointers + the
+current CUDA stream.  Nothing here computes on the CPU."""
+from __future__ import annotations
+
+import ctypes as C_
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import F16, F32, check, ctx, dev_f32, lib, pack_weights, ptr, stream
+
+_NAN = float("nan")
+
+
+def _dt(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float16:
+        return F16
+    raise RuntimeError(f"unsupported dtype {t.dtype}")
+
+
+# ------------------------------------------------------------------------------------------ stage 1
+def ray_directions(H: int, W: int, fx: float, fy: float, cx: float, cy: float, center_pixels: bool,
+                   device: torch.device) -> Tensor:
+    device = torch.device(device)
+    out = torch.empty(H, W, 3, dtype=torch.float32, device=device)
+    check(lib().acn_ray_directions(ctx(device), H, W, fx, fy, cx, cy, int(bool(center_pixels)), ptr(out), stream(device)))
+    return out
+
+
+def aabb_intersect(o: Tensor, d: Tensor, aabb: Tensor, eps=1e-8, max_bound=1e10, invalid=1e10) -> Tuple[Tensor, Tensor]:
+    o, d = dev_f32(o, "origins"), dev_f32(d, "directions")
+    aabb = dev_f32(aabb.to(o.device), "aabb").reshape(6)
+    N = o.shape[0]
+    tmin = torch.empty(N, dtype=torch.float32, device=o.device)
+    tmax = torch.empty_like(tmin)
+    check(lib().acn_aabb_intersect(ctx(o.device), ptr(o), ptr(d), N, o.stride(0) if N else 3, d.stride(0) if N else 3,
+                                   ptr(aabb), eps, max_bound, invalid, ptr(tmin), ptr(tmax), stream(o.device)))
+    return tmin, tmax
+
+
+def get_rays(dirs_cam: Tensor, c2w: Tensor, aabb: Optional[Tensor], near: float, far: float,
+             max_bound: float, invalid: float) -> Tensor:
+    d = dev_f32(dirs_cam, "directions").reshape(-1, 3)
+    c = dev_f32(c2w.to(d.device), "c2w")
+    assert c.shape[-1] == 4 and c.shape[0] in (3, 4), "c2w must be (3,4) or (4,4)"
+    a = dev_f32(aabb.to(d.device), "aabb").reshape(6) if aabb is not None else None
+    N = d.shape[0]
+    rays = torch.empty(N, 8, dtype=torch.float32, device=d.device)
+    check(lib().acn_get_rays(ctx(d.device), ptr(d), N, ptr(c), ptr(a), float(near), float(far), max_bound, invalid,
+                             ptr(rays), stream(d.device)))
+    return rays
+
+
+def clamp_near_far_(rays: Tensor, has_override: bool, n: Optional[float], f: Optional[float], eps: float,
+                    invalid: float) -> Tensor:
+    """In place on `rays` (N,8) contiguous fp32; returns the bool validity mask."""
+    assert rays.is_contiguous() and rays.dtype == torch.float32
+    N = rays.shape[0]
+    valid = torch.empty(N, dtype=torch.uint8, device=rays.device)
+    check(lib().acn_clamp_near_far(ctx(rays.device), ptr(rays), N, int(has_override),
+                                   _NAN if n is None else float(n), _NAN if f is None else float(f),
+                                   eps, invalid, ptr(valid), stream(rays.device)))
+    return valid.bool()
+
+
+_ULIN = {}
+
+
+def u_lin(S: int, device: torch.device) -> Tensor:
+    """torch.linspace(0,1,S) evaluated by the CPU kernel the reference oracle uses (bit-exact
+    bins), cached per (S, device)."""
+    key = (int(S), str(device))
+    t = _ULIN.get(key)
+    if t is None:
+        t = torch.linspace(0.0, 1.0, int(S), device="cpu").to(device)
+        _ULIN[key] = t
+    return t
+
+
+def sample_stratified(rays: Tensor, S: int, jitter: Optional[Tensor]) -> Tensor:
+    rays = dev_f32(rays, "rays")
+    N = rays.shape[0]
+    t = torch.empty(N, S, dtype=torch.float32, device=rays.device)
+    j = dev_f32(jitter, "jitter") if jitter is not None else None
+    check(lib().acn_sample_stratified(ctx(rays.device), ptr(rays), N, S, ptr(u_lin(S, rays.device)), ptr(j), ptr(t),
+                                      stream(rays.device)))
+    return t
+
+
+def points(rays: Tensor, t: Tensor) -> Tensor:
+    rays, t = dev_f32(rays, "rays"), dev_f32(t, "t_vals")
+    N, S = t.shape
+    id6 = torch.empty(N * S, 6, dtype=torch.float32, device=rays.device)
+    check(lib().acn_points(ctx(rays.device), ptr(rays), N, S, ptr(t), ptr(id6), stream(rays.device)))
+    return id6
+
+
+# ------------------------------------------------------------------------------------------ stage 2
+class GridSpec:
+    """Static description of one hash grid (device-resident resolution table)."""
+
+    def __init__(self, L: int, F: int, log2T: int, res: Tensor, interp: int):
+        self.L, self.F, self.log2T, self.res, self.interp = L, F, log2T, res, interp
+
+    @property
+    def rows(self) -> int:
+        return self.L << self.log2T
+
+
+def _grid_res(spec: GridSpec, device) -> Tensor:
+    if spec.res.device != device or spec.res.dtype != torch.int32:
+        spec.res = spec.res.to(device=device, dtype=torch.int32).contiguous()
+    return spec.res
+
+
+def hashgrid_fwd(x: Tensor, table: Tensor, spec: GridSpec, box6: Optional[Tensor] = None,
+                 out_dtype=torch.float32, want_idx: bool = False):
+    """x (P,>=3) fp32 (row stride honoured) -> (P, L*F); optional (P,L,8) int32 table rows."""
+    assert x.dim() == 2 and x.shape[1] >= 3
+    if not x.is_cuda:
+        raise RuntimeError("hashgrid_fwd needs CUDA tensors; there is no CPU path")
+    if x.dtype != torch.float32 or x.stride(1) != 1:
+        x = x.float().contiguous()
+    P = x.shape[0]
+    dev = x.device
+    table = dev_f32(table, "hash_table")
+    out = torch.empty(P, spec.L * spec.F, dtype=out_dtype, device=dev)
+    idx = torch.zeros(P, spec.L, 8, dtype=torch.int32, device=dev) if want_idx else None
+    check(lib().acn_hashgrid_fwd(ctx(dev), ptr(x), P, x.stride(0) if P else 3, ptr(box6), ptr(table), spec.L, spec.F,
+                                 spec.log2T, ptr(_grid_res(spec, dev)), spec.interp, ptr(out), _dt(out), ptr(idx),
+                                 stream(dev)))
+    return (out, idx) if want_idx else out
+
+
+def hashgrid_bwd(x: Tensor, dout: Tensor, spec: GridSpec, box6: Optional[Tensor], dtable: Tensor) -> None:
+    if x.dtype != torch.float32 or x.stride(1) != 1:
+        x = x.float().contiguous()
+    dout = dout.contiguous()
+    P = x.shape[0]
+    dev = x.device
+    check(lib().acn_hashgrid_bwd(ctx(dev), ptr(x), P, x.stride(0) if P else 3, ptr(box6), spec.L, spec.F, spec.log2T,
+                                 ptr(_grid_res(spec, dev)), spec.interp, ptr(dout), _dt(dout), ptr(dtable), stream(dev)))
+
+
+def hashgrid_fwd_rays(rays: Tensor, t: Tensor, table: Tensor, spec: GridSpec, box6: Optional[Tensor], out_dtype) -> Tensor:
+    N, S = t.shape
+    dev = rays.device
+    out = torch.empty(N * S, spec.L * spec.F, dtype=out_dtype, device=dev)
+    check(lib().acn_hashgrid_fwd_rays(ctx(dev), ptr(rays), ptr(t), N, S, ptr(box6), ptr(table), spec.L, spec.F, spec.log2T,
+                                      ptr(_grid_res(spec, dev)), spec.interp, ptr(out), _dt(out), stream(dev)))
+    return out
+
+
+def hashgrid_bwd_rays(rays: Tensor, t: Tensor, dout: Tensor, spec: GridSpec, box6: Optional[Tensor], dtable: Tensor) -> None:
+    N, S = t.shape
+    dev = rays.device
+    dout = dout.contiguous()
+    check(lib().acn_hashgrid_bwd_rays(ctx(dev), ptr(rays), ptr(t), N, S, ptr(box6), spec.L, spec.F, spec.log2T,
+                                      ptr(_grid_res(spec, dev)), spec.interp, ptr(dout), _dt(dout), ptr(dtable), stream(dev)))
+
+
+class HashEncodeFn(torch.autograd.Function):
+    """models/encodings.py:293-381 forward + table gradient (positions carry no gradient, as in
+    the reference pipeline where rays and t are built under no_grad)."""
+
+    @staticmethod
+    def forward(ctx_, x, table, spec, box6):
+        x2 = x.reshape(-1, x.shape[-1])
+        out = hashgrid_fwd(x2, table, spec, box6)
+        ctx_.save_for_backward(x2, box6 if box6 is not None else x2.new_empty(0))
+        ctx_.spec, ctx_.has_box, ctx_.tshape = spec, box6 is not None, table.shape
+        return out.view(*x.shape[:-1], spec.L * spec.F)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx_, g):
+        x2, box6 = ctx_.saved_tensors
+        if ctx_.needs_input_grad[0]:
+            raise NotImplementedError("gradient w.r.t. hash-grid input positions is not implemented (the reference never needs it)")
+        dtable = None
+        if ctx_.needs_input_grad[1]:
+            dtable = torch.zeros(ctx_.tshape, dtype=torch.float32, device=g.device)
+            hashgrid_bwd(x2, g.reshape(x2.shape[0], -1).float(), ctx_.spec, box6 if ctx_.has_box else None, dtable)
+        return None, dtable, None, None
+
+
+# ------------------------------------------------------------------------------------------ stage 3
+def sh16(d: Tensor) -> Tensor:
+    d2 = dev_f32(d, "directions").reshape(-1, 3)
+    out = torch.empty(d2.shape[0], 16, dtype=torch.float32, device=d2.device)
+    check(lib().acn_sh16(ctx(d2.device), ptr(d2), d2.shape[0], 3, ptr(out), stream(d2.device)))
+    return out.view(*d.shape[:-1], 16)
+
+
+def _field_dims(ws: Sequence[Tensor]):
+    H, E = ws[0].shape
+    G = ws[6].shape[0]
+    C = ws[8].shape[0]
+    return int(E), int(H), int(G), int(C)
+
+
+def field_fwd(enc: Tensor, dirs: Tensor, dirs_stride: int, dirs_group: int, ws: Sequence[Tensor], half: bool) -> Tensor:
+    P = enc.shape[0]
+    E, H, G, C = _field_dims(ws)
+    dev = enc.device
+    out = torch.empty(P, 4, dtype=torch.float32, device=dev)
+    st = pack_weights(ws)
+    check(lib().acn_field_fwd(ctx(dev), ptr(enc), _dt(enc), ptr(dirs), dirs_stride, dirs_group, P, E, H, G, C, C_.byref(st),
+                              F16 if half else F32, ptr(out), stream(dev)))
+    return out
+
+
+def field_bwd(enc: Tensor, dirs: Tensor, dirs_stride: int, dirs_group: int, ws: Sequence[Tensor], half: bool,
+              d_rgb_sigma: Tensor, want_enc_grad: bool, need: Sequence[bool]):
+    P = enc.shape[0]
+    E, H, G, C = _field_dims(ws)
+    dev = enc.device
+    grads: List[Optional[Tensor]] = [torch.zeros_like(w, dtype=torch.float32) if n else None for w, n in zip(ws, need)]
+    d_enc = torch.empty(P, E, dtype=enc.dtype, device=dev) if want_enc_grad else None
+    wst, gst = pack_weights(ws), pack_weights(grads)
+    check(lib().acn_field_bwd(ctx(dev), ptr(enc), _dt(enc), ptr(dirs), dirs_stride, dirs_group, P, E, H, G, C,
+                              C_.byref(wst), F16 if half else F32, ptr(d_rgb_sigma), C_.byref(gst),
+                              ptr(d_enc), _dt(enc), stream(dev)))
+    return grads, d_enc
+
+
+class ExpertFieldFn(torch.autograd.Function):
+    """One expert on a batch of points: world->unit, hash encode, density trunk + heads, SH,
+    colour MLP, activations (models/inr/meta_ngp.py:226-241) -> (P,4) [rgb, sigma].
+
+    Positions come either from `x6` (P,>=6: xyz + dir) or from (`rays` (N,8), `t` (N,S)).
+    Differentiable inputs: the hash table and the 14 MLP tensors (module parameters or `params=`
+    fast weights).  The backward recomputes the MLP activations from the saved encoding."""
+
+    @staticmethod
+    def forward(ctx_, x6, rays, t, table, spec, box6, half, *ws):
+        ws = [dev_f32(w, "MLP weight") for w in ws]
+        table_c = dev_f32(table, "hash_table")
+        enc_dtype = torch.float16 if half else torch.float32
+        if rays is not None:
+            rays = dev_f32(rays, "rays")
+            t = dev_f32(t, "t_vals")
+            enc = hashgrid_fwd_rays(rays, t, table_c, spec, box6, enc_dtype)
+            dirs, dstride, dgroup = rays[:, 3:], 8, t.shape[1]
+            pos = (rays, t)
+        else:
+            if x6.dtype != torch.float32 or not x6.is_contiguous():
+                x6 = x6.float().contiguous()
+            enc = hashgrid_fwd(x6, table_c, spec, box6, enc_dtype)
+            dirs, dstride, dgroup = x6[:, 3:], x6.stride(0), 1
+            pos = (x6,)
+        out = field_fwd(enc, dirs, dstride, dgroup, ws, half)
+        ctx_.save_for_backward(enc, *pos, *(t_ for t_ in (box6,) if t_ is not None), *ws)
+        ctx_.meta = (spec, half, len(pos), box6 is not None, dstride, dgroup, table.shape)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx_, g):
+        spec, half, npos, has_box, dstride, dgroup, tshape = ctx_.meta
+        saved = ctx_.saved_tensors
+        enc, pos = saved[0], saved[1:1 + npos]
+        box6 = saved[1 + npos] if has_box else None
+        ws = saved[1 + npos + int(has_box):]
+        need_table = ctx_.needs_input_grad[3]
+        need_w = ctx_.needs_input_grad[7:]
+        dirs = pos[0][:, 3:]
+        g = g.contiguous().float()
+        grads, d_enc = field_bwd(enc, dirs, dstride, dgroup, ws, half, g, need_table, need_w)
+        dtable = None
+        if need_table:
+            dtable = torch.zeros(tshape, dtype=torch.float32, device=g.device)
+            if npos == 2:
+                hashgrid_bwd_rays(pos[0], pos[1], d_enc, spec, box6, dtable)
+            else:
+                hashgrid_bwd(pos[0], d_enc, spec, box6, dtable)
+        return (None, None, None, dtable, None, None, None, *grads)
+
+
+# ------------------------------------------------------------------------------------------ stage 4
+def composite_fwd(rgb_sigma: Tensor, t: Tensor, bg: Optional[Tensor], sigma_scale: float):
+    N, S = t.shape
+    dev = t.device
+    rgb = torch.empty(N, 3, dtype=torch.float32, device=dev)
+    depth = torch.empty(N, dtype=torch.float32, device=dev)
+    weights = torch.empty(N, S, dtype=torch.float32, device=dev)
+    acc = torch.empty(N, dtype=torch.float32, device=dev)
+    check(lib().acn_composite_fwd(ctx(dev), ptr(rgb_sigma), ptr(t), ptr(bg), N, S, float(sigma_scale), ptr(rgb), ptr(depth),
+                                  ptr(weights), ptr(acc), stream(dev)))
+    return rgb, depth, weights, acc
+
+
+class CompositeFn(torch.autograd.Function):
+    """nerfs/ray_rendering.py:114-165 volume_render (raw_rgb = raw_sigma = False)."""
+
+    @staticmethod
+    def forward(ctx_, rgb_sigma, t, bg, sigma_scale):
+        rs = dev_f32(rgb_sigma, "rgb_sigma")
+        t = dev_f32(t, "t_vals")
+        bgc = dev_f32(bg.to(rs.device), "bg_rgb") if bg is not None else None
+        out = composite_fwd(rs, t, bgc, sigma_scale)
+        ctx_.save_for_backward(rs, t, *(b for b in (bgc,) if b is not None))
+        ctx_.sigma_scale, ctx_.has_bg = float(sigma_scale), bgc is not None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx_, g_rgb, g_depth, g_weights, g_acc):
+        saved = ctx_.saved_tensors
+        rs, t = saved[0], saved[1]
+        bg = saved[2] if ctx_.has_bg else None
+        N, S = t.shape
+        dev = t.device
+        c = lambda g: None if g is None else g.contiguous().float()
+        g_rgb, g_depth, g_weights, g_acc = c(g_rgb), c(g_depth), c(g_weights), c(g_acc)
+        d = torch.empty(N, S, 4, dtype=torch.float32, device=dev)
+        need_bg = ctx_.has_bg and ctx_.needs_input_grad[2]
+        d_bg = torch.zeros(N, 3, dtype=torch.float32, device=dev) if need_bg else None
+        check(lib().acn_composite_bwd(ctx(dev), ptr(rs), ptr(t), ptr(bg), N, S, ctx_.sigma_scale, ptr(g_rgb), ptr(g_depth),
+                                      ptr(g_weights), ptr(g_acc), ptr(d), ptr(d_bg), stream(dev)))
+        return d.view_as(rs), None, d_bg, None
+
+
+# ------------------------------------------------------------------------------------------ stage 5
+def route_points(pts: Tensor, centroids: Tensor, dims: int, margin: float, want_counts: bool = False):
+    """-> (weights (P,K) | None, hard (P,) int32 | None, counts (K,) int32 | None)"""
+    if not pts.is_cuda:
+        raise RuntimeError("route_points needs CUDA tensors; there is no CPU path")
+    if pts.dtype != torch.float32 or pts.stride(-1) != 1:
+        pts = pts.float().contiguous()
+    cen = dev_f32(centroids.to(pts.device), "centroids")
+    P, K = pts.shape[0], cen.shape[0]
+    dev = pts.device
+    soft = margin > 1.0
+    w = torch.empty(P, K, dtype=torch.float32, device=dev) if soft else None
+    h = torch.empty(P, dtype=torch.int32, device=dev) if not soft else None
+    counts = torch.zeros(K, dtype=torch.int32, device=dev) if want_counts else None
+    check(lib().acn_route_points(ctx(dev), ptr(pts), P, pts.stride(0) if P else 3, ptr(cen), K, dims, float(margin),
+                                 ptr(w), ptr(h), ptr(counts), stream(dev)))
+    return w, h, counts
+
+
+def route_rays_voronoi(rays: Tensor, S: int, centroids: Tensor, dims: int, margin: float) -> Tensor:
+    rays = dev_f32(rays, "rays")
+    cen = dev_f32(centroids.to(rays.device), "centroids")
+    N, K = rays.shape[0], cen.shape[0]
+    mask = torch.empty(N, K, dtype=torch.uint8, device=rays.device)
+    check(lib().acn_route_rays_voronoi(ctx(rays.device), ptr(rays), N, S, ptr(u_lin(S, rays.device)), ptr(cen), K, dims,
+                                       float(margin), ptr(mask), stream(rays.device)))
+    return mask.bool()
+
+
+def bucket_points(id6: Tensor, weights: Optional[Tensor], hard: Optional[Tensor], K: int, offsets: Tensor, total: int):
+    """-> sel (total,) int32, xd (total,6), w (total,)"""
+    dev = id6.device
+    P = id6.shape[0]
+    sel = torch.empty(total, dtype=torch.int32, device=dev)
+    xd = torch.empty(total, 6, dtype=torch.float32, device=dev)
+    w = torch.empty(total, dtype=torch.float32, device=dev)
+    cursor = torch.zeros(K, dtype=torch.int32, device=dev)
+    check(lib().acn_bucket_points(ctx(dev), ptr(id6), P, ptr(weights), ptr(hard), K, ptr(offsets), ptr(cursor), ptr(sel),
+                                  ptr(xd), ptr(w), stream(dev)))
+    return sel, xd, w
+
+
+class BlendFn(torch.autograd.Function):
+    """out[sel[i]] += y[i] * w[i] (models/inr/meta_container.py:321 index_add_ / :336 index_copy_)
+    for one expert's routed rows; `out` is threaded through so experts accumulate in k order."""
+
+    @staticmethod
+    def forward(ctx_, out, y, w, sel):
+        y = y.contiguous()
+        check(lib().acn_blend_add(ctx(y.device), ptr(y), ptr(w), ptr(sel), y.shape[0], ptr(out), stream(y.device)))
+        ctx_.save_for_backward(w, sel)
+        ctx_.mark_dirty(out)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx_, g):
+        w, sel = ctx_.saved_tensors
+        g = g.contiguous()
+        d_y = torch.empty(sel.shape[0], 4, dtype=torch.float32, device=g.device)
+        check(lib().acn_blend_bwd(ctx(g.device), ptr(g), ptr(w), ptr(sel), sel.shape[0], ptr(d_y), stream(g.device)))
+        return g, d_y, None, None
+
+
+# ------------------------------------------------------------------------------------------ diagnostics
+def debug_umma_gemm(a: Tensor, w: Tensor) -> Tensor:
+    """D = A @ W^T on one tcgen05 tile: A (128,K) fp16, W (N,K) fp16 -> (128,N) fp32."""
+    assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.shape[0] == 128
+    a, w = a.contiguous(), w.contiguous()
+    d = torch.empty(128, w.shape[0], dtype=torch.float32, device=a.device)
+    check(lib().acn_debug_umma_gemm(ctx(a.device), ptr(a), ptr(w), w.shape[0], a.shape[1], ptr(d), stream(a.device)))
+    return d

@@ -1,0 +1,191 @@
+/*
+ * acn_b200.h -- C ABI of libacn_b200.so: the per-ray volumetric rendering hot path of
+ * psklavos1/adaptive-city-nerf as hand-written sm_100a kernels.
+ *
+ * Conventions
+ *   - every entry point returns ACN_OK (0) or a negative ACN_E* code; the message for the
+ *     calling thread is in acn_last_error().  No exception crosses the ABI, nothing exits.
+ *   - all tensor arguments are DEVICE pointers to contiguous row-major arrays unless the
+ *     parameter is documented as "stride"; the caller owns every buffer (Python: torch
+ *     allocator).  The library keeps no state besides the opaque acn_ctx.
+ *   - calls are asynchronous on `stream` (a cudaStream_t); there are no hidden syncs.
+ *   - "reference" citations are file:line in psklavos1/adaptive-city-nerf.
+ */
+#ifndef ACN_B200_H
+#define ACN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define ACN_VERSION 100 /* major*100 + minor */
+
+typedef struct acn_ctx acn_ctx;
+typedef void* acn_stream; /* cudaStream_t */
+
+enum {
+    ACN_OK = 0,
+    ACN_EINVAL = -1,       /* bad argument (null pointer, negative size, ...) */
+    ACN_EUNSUPPORTED = -2, /* shape / dtype outside what the kernels are built for */
+    ACN_ECUDA = -3,        /* CUDA runtime / launch error */
+    ACN_ENODEVICE = -4     /* no sm_100 device */
+};
+
+enum { ACN_INTERP_NEAREST = 0, ACN_INTERP_LINEAR = 1, ACN_INTERP_SMOOTHSTEP = 2 };
+enum { ACN_F32 = 0, ACN_F16 = 1 };
+
+/* ---- context ----------------------------------------------------------------------------- */
+int acn_version(void);
+const char* acn_last_error(void);
+/* One context per device; records SM count / L2 size and opts kernels into large shared memory. */
+int acn_create(int device, acn_ctx** out);
+int acn_destroy(acn_ctx* ctx);
+int acn_device_info(acn_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+
+/* ---- stage 1: camera rays, scene-box clipping, stratified sampling ------------------------- */
+
+/* nerfs/ray_sampling.py:111-136 get_ray_directions -> dirs (H,W,3) */
+int acn_ray_directions(acn_ctx*, int H, int W, float fx, float fy, float cx, float cy,
+                       int center_pixels, float* dirs, acn_stream);
+
+/* nerfs/scene_box.py:45-107 SceneBox.ray_aabb_intersect.  o,d are (N,*) with the given row
+ * strides (in floats); aabb6 = [min xyz, max xyz] on the device. */
+int acn_aabb_intersect(acn_ctx*, const float* o, const float* d, int64_t N, int stride_o,
+                       int stride_d, const float* aabb6, float eps, float max_bound,
+                       float invalid, float* tmin, float* tmax, acn_stream);
+
+/* nerfs/ray_sampling.py:10-24,50-108 _rays_cam_to_world + get_rays + pack_rays -> rays (N,8)
+ * [o, d, near, far].  c2w: device pointer to a row-major (3|4, 4) matrix.  aabb6_or_null == NULL
+ * selects the constant near/far branch. */
+int acn_get_rays(acn_ctx*, const float* dirs_cam, int64_t N, const float* c2w,
+                 const float* aabb6_or_null, float near_c, float far_c, float max_bound,
+                 float invalid, float* rays8, acn_stream);
+
+/* nerfs/ray_sampling.py:139-176 clamp_rays_near_far (in place).  has_override = 0 is the
+ * `near_far_override is None` branch; NaN means "no override" for n / f. */
+int acn_clamp_near_far(acn_ctx*, float* rays8, int64_t N, int has_override, float n_or_nan,
+                       float f_or_nan, float eps, float invalid, uint8_t* valid, acn_stream);
+
+/* nerfs/ray_rendering.py:262-287 stratified_t_vals.  u_lin = torch.linspace(0,1,S) (device);
+ * jitter_or_null = the rand tensor (N,S) in training mode.  Bins are bit-exact w.r.t. the
+ * reference CPU path. */
+int acn_sample_stratified(acn_ctx*, const float* rays8, int64_t N, int S, const float* u_lin,
+                          const float* jitter_or_null, float* t_vals, acn_stream);
+
+/* nerfs/ray_rendering.py:317-319 -> id6 (N*S,6) = [o + d*t, d] */
+int acn_points(acn_ctx*, const float* rays8, int64_t N, int S, const float* t_vals, float* id6,
+               acn_stream);
+
+/* ---- stage 2: multiresolution hash grid (models/encodings.py:160-381, torch branch) --------- */
+
+/* x: (P,>=3) with row stride x_stride floats.  box6_or_null = [min xyz, extent xyz] (device):
+ * when given, x is in world coordinates and models/inr/meta_ngp.py:155-158 _world_to_unit is
+ * applied first.  table: (L*2^log2T, F) fp32.  res: (L) int32 on the device.
+ * out: (P, L*F) fp32 or fp16.  idx_out_or_null: (P,L,8) int32 table rows (parity checks). */
+int acn_hashgrid_fwd(acn_ctx*, const float* x, int64_t P, int x_stride, const float* box6_or_null,
+                     const float* table, int L, int F, int log2T, const int32_t* res, int interp,
+                     void* out, int out_dtype, int32_t* idx_out_or_null, acn_stream);
+
+/* Autograd of the above w.r.t. the table: dtable (L*2^log2T, F) fp32 is ACCUMULATED into. */
+int acn_hashgrid_bwd(acn_ctx*, const float* x, int64_t P, int x_stride, const float* box6_or_null,
+                     int L, int F, int log2T, const int32_t* res, int interp, const void* dout,
+                     int dout_dtype, float* dtable, acn_stream);
+
+/* Same, with the points formed on the fly from rays (N,8) and t_vals (N,S): p = o + d*t
+ * (nerfs/ray_rendering.py:317); the reference's (N*S,6) id6 tensor is never materialised.
+ * out / dout are (N*S, L*F). */
+int acn_hashgrid_fwd_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
+                          const float* box6_or_null, const float* table, int L, int F, int log2T,
+                          const int32_t* res, int interp, void* out, int out_dtype, acn_stream);
+int acn_hashgrid_bwd_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
+                          const float* box6_or_null, int L, int F, int log2T, const int32_t* res,
+                          int interp, const void* dout, int dout_dtype, float* dtable, acn_stream);
+
+/* ---- stage 3: field MLPs (models/inr/meta_ngp.py:171-241, metamodule.py:129-192) ------------ */
+
+/* Device pointers, fp32, nn.Linear layout (out,in), in this order:
+ *  0 sigma_trunk.0.linear.weight (H,E)   1 .bias (H)     2 sigma_trunk.1.linear.weight (H,H)  3 .bias
+ *  4 sigma_head.weight (1,H)  5 .bias    6 geo_head.weight (G,H)  7 .bias
+ *  8 color_mlp.0.linear.weight (C,G+16)  9 .bias         10 color_mlp.1.linear.weight (C,C)  11 .bias
+ * 12 color_mlp.2.weight (3,C) 13 .bias
+ * These may be the module's own parameters or `params=` fast weights. */
+typedef struct { const float* p[14]; } acn_field_weights;
+typedef struct { float* p[14]; } acn_field_grads; /* accumulated into; entries may be NULL */
+
+/* models/encodings.py:27-81,133-151 SH degree 3 (16 comps) after the expert's double normalise */
+int acn_sh16(acn_ctx*, const float* dirs, int64_t P, int stride, float* out, acn_stream);
+
+/* enc (P,E) fp32|fp16.  Point p reads its direction at dirs[(p / dirs_group) * dirs_stride]:
+ * (P,6) id6 rows -> dirs = id6 + 3, stride 6, group 1; rays (N,8) -> dirs = rays + 3, stride 8,
+ * group S.  precision ACN_F32: SIMT fp32 math.  ACN_F16: tcgen05 tensor cores, fp16
+ * operands / fp32 accumulate (the reference's autocast path).  -> rgb_sigma (P,4) fp32. */
+int acn_field_fwd(acn_ctx*, const void* enc, int enc_dtype, const float* dirs, int dirs_stride,
+                  int dirs_group, int64_t P, int E, int H, int G, int C,
+                  const acn_field_weights* w, int precision, float* rgb_sigma, acn_stream);
+
+/* d_rgb_sigma (P,4) -> weight grads (accumulated) and d_enc (P,E) (NULL to skip). */
+int acn_field_bwd(acn_ctx*, const void* enc, int enc_dtype, const float* dirs, int dirs_stride,
+                  int dirs_group, int64_t P, int E, int H, int G, int C,
+                  const acn_field_weights* w, int precision, const float* d_rgb_sigma,
+                  const acn_field_grads* g, void* d_enc_or_null, int d_enc_dtype, acn_stream);
+
+/* ---- stage 4: alpha compositing (nerfs/ray_rendering.py:114-165 volume_render) -------------- */
+int acn_composite_fwd(acn_ctx*, const float* rgb_sigma, const float* t_vals,
+                      const float* bg_or_null, int64_t N, int S, float sigma_scale, float* rgb,
+                      float* depth, float* weights, float* acc, acn_stream);
+
+/* Incoming grads may each be NULL (= zero).  d_bg_or_null (N,3) is written when bg is given. */
+int acn_composite_bwd(acn_ctx*, const float* rgb_sigma, const float* t_vals,
+                      const float* bg_or_null, int64_t N, int S, float sigma_scale,
+                      const float* g_rgb, const float* g_depth, const float* g_weights,
+                      const float* g_acc, float* d_rgb_sigma, float* d_bg_or_null, acn_stream);
+
+/* ---- stage 5: Voronoi routing --------------------------------------------------------------- */
+
+/* models/inr/meta_container.py:97-134 _routing.  dims = 2 (cluster_2d: columns y,z) or 3.
+ * margin > 1: weights (P,K) fp32; else hard (P) int32.  counts_or_null (K) int32 is ADDED to:
+ * number of points with w_k > 0 (or assigned to k). */
+int acn_route_points(acn_ctx*, const float* pts, int64_t P, int stride, const float* centroids,
+                     int K, int dims, float margin, float* weights_or_null,
+                     int32_t* hard_or_null, int32_t* counts_or_null, acn_stream);
+
+/* scripts/create_clusters.py:559-634 compute_voronoi_orig: mask (N,K) uint8. */
+int acn_route_rays_voronoi(acn_ctx*, const float* rays8, int64_t N, int S, const float* u_lin,
+                           const float* centroids, int K, int dims, float margin, uint8_t* mask,
+                           acn_stream);
+
+/* Device-side dispatch for meta_container.py:306-337 (replaces nonzero/index_select and its
+ * K host syncs).  For expert k, the points with weight > 0 (or hard == k) are written, in
+ * point order, to sel[offsets[k] .. offsets[k]+counts[k]) where offsets = exclusive scan of
+ * counts.  `cursor` (K) int32 must be zero on entry.  xd_out (sum counts, 6) receives the
+ * gathered [xyz,dir] rows and w_out (sum counts) the blend weight (1 for hard routing). */
+int acn_bucket_points(acn_ctx*, const float* id6, int64_t P, const float* weights_or_null,
+                      const int32_t* hard_or_null, int K, const int32_t* offsets, int32_t* cursor,
+                      int32_t* sel, float* xd_out, float* w_out, acn_stream);
+
+/* out[sel[i]] += y[i] * w[i]  (index_add_, meta_container.py:321) over M routed rows of 4. */
+int acn_blend_add(acn_ctx*, const float* y, const float* w, const int32_t* sel, int64_t M,
+                  float* out, acn_stream);
+/* d_y[i] = d_out[sel[i]] * w[i] */
+int acn_blend_bwd(acn_ctx*, const float* d_out, const float* w, const int32_t* sel, int64_t M,
+                  float* d_y, acn_stream);
+
+/* ---- diagnostics ---------------------------------------------------------------------------- */
+/* One tcgen05 tile GEMM  D(128,N) = A(128,K) * W(N,K)^T  (fp16 in, fp32 out); validates the
+ * shared-memory / instruction descriptors the fused MLP kernels are built on.  N in
+ * {16,32,64}, K in {16,32,64}. */
+int acn_debug_umma_gemm(acn_ctx*, const void* a_f16, const void* w_f16, int N, int K, float* d,
+                        acn_stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACN_B200_H */

@@ -1,0 +1,369 @@
+"""GPU parity tests, stage by stage: CUDA kernels (through the C ABI) vs the CPU oracle on the same
+seeded inputs and vs the committed golden fixtures generated from the reference.
+
+Bars (BASELINE north star): bit-exact for hash indices, sample bins, near/far, validity masks and
+expert assignment; float tolerance (stated per test) for features, colours, depths, gradients."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from helpers import F32, assert_bitexact, cu, npy, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from adaptive_city_nerf_b200 import ops as o
+    return o
+
+
+# ----------------------------------------------------------------------------- stage 1
+def test_ray_directions(ops, golden):
+    g = golden("stage1")
+    from adaptive_city_nerf_b200.nerfs.ray_sampling import get_ray_directions
+    for cp in (True, False):
+        d = get_ray_directions(12, 16, 13.5, 14.25, 8.3, 5.9, cp, torch.device("cuda"))
+        np.testing.assert_allclose(npy(d), g[f"dirs_cp{int(cp)}"], atol=2e-7, rtol=0)   # fp32 tolerance: 2 ulp
+
+
+def test_aabb_intersect_bitexact(ops, golden, orc):
+    from adaptive_city_nerf_b200.nerfs.scene_box import SceneBox
+    g = golden("stage1")
+    o, d = synth.random_rays_in_box(11, 4096)
+    box = SceneBox(cu(synth.AABB_GLOBAL))
+    tmin, tmax = box.ray_aabb_intersect(cu(o), cu(d))
+    assert_bitexact(npy(tmin), g["aabb_tmin"], "tmin vs reference")
+    assert_bitexact(npy(tmax), g["aabb_tmax"], "tmax vs reference")
+    tmin, tmax = box.ray_aabb_intersect(cu(o), cu(d), invalid_value=float("inf"))
+    assert_bitexact(npy(tmin), g["aabb_tmin_inf"], "tmin inf")
+    # a different seed against the oracle
+    o, d = synth.random_rays_in_box(12, 100_003)
+    tmin, tmax = box.ray_aabb_intersect(cu(o), cu(d))
+    omin, omax = orc.aabb_intersect(o, d, synth.AABB_GLOBAL)
+    assert_bitexact(npy(tmin), omin, "tmin vs oracle")
+    assert_bitexact(npy(tmax), omax, "tmax vs oracle")
+    e0, e1 = box.ray_aabb_intersect(cu(o[:0]), cu(d[:0]))     # empty input
+    assert e0.shape == (0,) and e1.shape == (0,)
+
+
+def test_get_rays_and_clamp(ops, golden):
+    from adaptive_city_nerf_b200.nerfs.ray_sampling import get_rays, clamp_rays_near_far
+    from adaptive_city_nerf_b200.nerfs.scene_box import SceneBox
+    g = golden("stage1")
+    cam = synth.nadir_rays(5, 1, H=24, W=32, f=25.0)[0]
+    box = SceneBox(cu(synth.AABB_GLOBAL))
+    dirs = cu(g["cam_dirs"])
+    rays = get_rays(dirs, cu(cam["c2w"]), scene_box=box, aabb_invalid_value=float("inf"))
+    assert rays.shape == (24, 32, 8)
+    rays = rays.view(-1, 8)
+    ref = g["cam_rays"]
+    np.testing.assert_allclose(npy(rays)[:, :6], ref[:, :6], atol=1e-6, rtol=0)
+    # fed the reference's own o,d the clip is bit-exact
+    tmin, tmax = box.ray_aabb_intersect(cu(ref[:, :3]), cu(ref[:, 3:6]), invalid_value=float("inf"))
+    assert_bitexact(npy(tmin), ref[:, 6], "near")
+    assert_bitexact(npy(tmax), ref[:, 7], "far")
+    for tag, ov in (("none", None), ("nn", (None, None)), ("nf", (0.05, 0.4)), ("n", (0.3, None))):
+        r2, valid = clamp_rays_near_far(cu(ref), ov)
+        assert (npy(valid).astype(bool) == g[f"clamp_{tag}_valid"]).all(), tag
+        assert_bitexact(npy(r2), g[f"clamp_{tag}_rays"], f"clamp {tag}")
+    rc = get_rays(dirs.view(-1, 3), cu(cam["c2w"]), near=0.1, far=2.5)
+    np.testing.assert_allclose(npy(rc), g["rays_const"], atol=1e-6, rtol=0)
+    with pytest.raises(ValueError):
+        get_rays(dirs.view(-1, 3), cu(cam["c2w"]))
+
+
+@pytest.mark.parametrize("S", [16, 64, 96])
+def test_sample_bins_bitexact(ops, golden, S):
+    from adaptive_city_nerf_b200.nerfs.ray_rendering import stratified_t_vals
+    g = golden("stage1")
+    rays = cu(g["t_rays"])
+    t = stratified_t_vals(rays[:, 6], rays[:, 7], S, randomized=False)
+    assert_bitexact(npy(t), g[f"t_eval_{S}"], "eval bins")
+    t = stratified_t_vals(rays[:, 6], rays[:, 7], S, randomized=True, jitter=cu(g[f"jitter_{S}"]))
+    assert_bitexact(npy(t), g[f"t_train_{S}"], "train bins (shared jitter)")
+
+
+def test_sample_bins_odd_S_vs_oracle(ops, orc, golden):
+    rays = golden("stage1")["t_rays"]
+    for S in (2, 3, 17, 65, 255):
+        jit = np.random.default_rng(S).uniform(0, 1, (rays.shape[0], S)).astype(F32)
+        assert_bitexact(npy(ops.sample_stratified(cu(rays), S, None)), orc.stratified_t(rays, S), f"S={S} eval")
+        assert_bitexact(npy(ops.sample_stratified(cu(rays), S, cu(jit))), orc.stratified_t(rays, S, jit), f"S={S} train")
+
+
+def test_points_bitexact(ops, golden):
+    g = golden("stage1")
+    id6 = ops.points(cu(g["t_rays"]), cu(g["t_train_64"]))
+    assert_bitexact(npy(id6)[:, :3].reshape(-1, 64, 3), g["pts_64"], "pts")
+    assert_bitexact(npy(id6)[:, 3:].reshape(-1, 64, 3)[:, 0], g["t_rays"][:, 3:6], "dirs")
+
+
+# ----------------------------------------------------------------------------- stage 2
+def _hash_inputs():
+    rng = np.random.default_rng(21)
+    x = rng.uniform(0, 1, (2048, 3)).astype(F32)
+    x[:8] = np.float32(1e-6)
+    x[8:16] = np.float32(1.0) - np.float32(1e-6)
+    x[16:24, 0] = np.float32(0.5)
+    x[24:32] = (rng.integers(0, 16, (8, 3)) / 16.0).astype(F32)
+    return x
+
+
+def _encoder(log2T, mode="Linear", table=None, L=16, F=2):
+    from adaptive_city_nerf_b200.models.encodings import HashGridEncoder
+    enc = HashGridEncoder(levels=L, min_res=16, max_res=4096, log2_hashmap_size=log2T, features_per_level=F,
+                          interpolation=mode).cuda()
+    if table is not None:
+        with torch.no_grad():
+            enc.hash_table.copy_(cu(table))
+    return enc
+
+
+@pytest.mark.parametrize("log2T", [12, 19, 20])
+def test_hash_indices_bitexact(golden, log2T):
+    g = golden("hashgrid")
+    x = _hash_inputs()
+    n = 2048 if log2T == 12 else 512
+    enc = _encoder(log2T)
+    idx = enc.hash_indices(cu(x[:n]))
+    assert (npy(idx).astype(np.int64) == g[f"idx_T{log2T}"]).all()
+
+
+@pytest.mark.parametrize("mode", ["Linear", "Smoothstep", "Nearest"])
+def test_hashgrid_features_and_grad(golden, mode):
+    g = golden("hashgrid")
+    x = _hash_inputs()
+    sd = synth.make_expert_params(22, log2T=12)
+    enc = _encoder(12, mode, sd["xyz_encoder.hash_table"])
+    y = enc(cu(x))
+    assert y.shape == (2048, 32) and y.dtype == torch.float32
+    assert_bitexact(npy(y), g[f"feat_{mode}"], f"features {mode}")     # same op order as the reference -> same bits
+    dout = np.random.default_rng(23).standard_normal((2048, 32)).astype(F32)
+    (y * cu(dout)).sum().backward()
+    # atomics reorder the fp32 sums: tolerance 2e-5 abs on O(1)-magnitude sums of <= 2048 terms
+    np.testing.assert_allclose(npy(enc.hash_table.grad), g[f"dtable_{mode}"], atol=2e-5, rtol=1e-5)
+
+
+def test_hashgrid_shapes_and_edge_cases(orc):
+    enc = _encoder(10)
+    assert enc(torch.rand(0, 3, device="cuda")).shape == (0, 32)                # empty
+    y = enc(torch.rand(3, 5, 3, device="cuda"))
+    assert y.shape == (3, 5, 32)                                                # leading dims kept
+    # features_per_level 1/4/8 and fewer levels against the oracle
+    for F_, L_ in ((1, 4), (4, 8), (8, 2)):
+        rng = np.random.default_rng(F_)
+        tab = rng.uniform(-1, 1, (L_ << 10, F_)).astype(F32)
+        e = _encoder(10, "Linear", tab, L=L_, F=F_)
+        x = rng.uniform(0, 1, (777, 3)).astype(F32)
+        res = npy(e.level_resolutions).astype(np.int32)
+        assert_bitexact(npy(e(cu(x))), orc.hashgrid_fwd(x, tab, L_, F_, 10, res), f"F={F_}")
+    # positions outside [0,1] (negative floors) hash like the reference's int64 arithmetic
+    x = np.random.default_rng(9).uniform(-2, 3, (999, 3)).astype(F32)
+    e = _encoder(12)
+    res = npy(e.level_resolutions).astype(np.int32)
+    _, idx = orc.hashgrid_fwd(x, np.zeros((16 << 12, 2), F32), 16, 2, 12, res, want_idx=True)
+    assert (npy(e.hash_indices(cu(x))).astype(np.int64) == idx).all()
+
+
+def test_hashgrid_full_size_properties():
+    """BASELINE-size table (T=2^19, 64 MiB): linearity in the table and partition of unity."""
+    enc = _encoder(19)
+    x = torch.rand(1 << 18, 3, device="cuda")
+    with torch.no_grad():
+        enc.hash_table.fill_(1.0)
+        y1 = enc(x)
+        assert (y1 - 1.0).abs().max() < 2e-6          # trilinear weights sum to one
+        enc.hash_table.copy_(torch.randn_like(enc.hash_table))
+        a = enc(x)
+        enc.hash_table.mul_(2.0)
+        assert torch.equal(enc(x), 2.0 * a)           # exact linearity under power-of-two scaling
+    idx = enc.hash_indices(x[:4096])
+    lvl = torch.arange(16, device="cuda").view(1, 16, 1)
+    assert ((idx >> 19) == lvl).all()                 # every level stays inside its own table slice
+
+
+# ----------------------------------------------------------------------------- stage 3
+def _field_inputs(golden):
+    g = golden("field")
+    sd = synth.make_expert_params(31, log2T=12)
+    return g, sd, synth.expert_weight_list(sd)
+
+
+def test_sh16(ops, golden):
+    g = golden("field")
+    np.testing.assert_allclose(npy(ops.sh16(cu(g["dirs"]))), g["sh"], atol=2e-6, rtol=0)
+
+
+def test_field_fp32_forward_backward(ops, golden, orc):
+    g, sd, ws = _field_inputs(golden)
+    wt = [cu(w).requires_grad_(True) for w in ws]
+    enc = cu(g["enc"])
+    dirs = cu(g["dirs"])
+    y = ops.field_fwd(enc, dirs, 3, 1, wt, half=False)
+    np.testing.assert_allclose(npy(y)[:, :3], g["y"][:, :3], atol=1e-5, rtol=0)     # fp32 path: 1e-5 abs on rgb
+    np.testing.assert_allclose(npy(y)[:, 3], g["y"][:, 3], atol=0, rtol=1e-4)       # sigma spans decades: relative
+    grads, d_enc = ops.field_bwd(enc, dirs, 3, 1, wt, False, cu(g["G"]), True, [True] * 14)
+    for key, gr in zip(synth.EXPERT_KEYS, grads):
+        assert rel_err(npy(gr), g["grad." + key]) < 1e-4, key
+    ogr, o_denc = orc.field_bwd(g["enc"], g["dirs"], ws, g["G"])
+    assert rel_err(npy(d_enc), o_denc) < 1e-4
+    # ragged sizes: tails of the 64-point tiles
+    for P in (1, 63, 65, 200):
+        y2 = ops.field_fwd(enc[:P].contiguous(), dirs[:P].contiguous(), 3, 1, wt, half=False)
+        np.testing.assert_allclose(npy(y2), npy(y)[:P], atol=1e-6, rtol=1e-6)
+
+
+def test_expert_forward_autograd_fp32(golden):
+    """MetaNGP.forward through autograd: all 14 MLP tensors + the hash table (reference grads)."""
+    from helpers import make_container
+    g = golden("field")
+    m = make_container(1, np.zeros((1, 3)), [synth.AABB_GLOBAL], 1.0, False, 31)
+    ex = m.submodules[0]
+    x6 = cu(np.concatenate([g["xyz"], g["dirs"]], axis=1))
+    y = ex(x6)
+    np.testing.assert_allclose(npy(y)[:, :3], g["y"][:, :3], atol=1e-5, rtol=0)
+    (y * cu(g["G"])).sum().backward()
+    named = dict(ex.named_parameters())
+    for key in synth.EXPERT_KEYS:
+        assert rel_err(npy(named[key].grad), g["grad." + key]) < 1e-4, key
+    assert rel_err(npy(ex.xyz_encoder.hash_table.grad), g["grad.xyz_encoder.hash_table"]) < 1e-4
+    # split API agrees with the fused kernels
+    with torch.no_grad():
+        dens = ex.density(cu(g["xyz"]), return_feats=True)
+        np.testing.assert_allclose(npy(dens["sigma"]), g["sigma"], rtol=1e-4, atol=0)
+        np.testing.assert_allclose(npy(dens["geo_feat"]), g["geo"], atol=2e-5, rtol=1e-4)
+        rgb = ex.color(cu(g["dirs"]), dens["geo_feat"])
+        np.testing.assert_allclose(npy(rgb), g["y"][:, :3], atol=1e-5, rtol=0)
+
+
+# ----------------------------------------------------------------------------- stage 4
+@pytest.mark.parametrize("tag,scale", [("bg", 1.0), ("nobg", 1.0), ("scale", 2.5)])
+def test_composite(golden, tag, scale):
+    from adaptive_city_nerf_b200.nerfs.ray_rendering import volume_render
+    g = golden("composite")
+    rs = cu(g["rgb_sigma"]).requires_grad_(True)
+    bg = None if tag == "nobg" else cu(g["bg"]).requires_grad_(True)
+    rgb, dep, w, acc = volume_render(rs, cu(g["t"]), bg_rgb=bg, sigma_scale=scale)
+    # fp32 compositing; scan order differs from the reference's sequential cumprod: 2e-6 abs
+    np.testing.assert_allclose(npy(w), g[f"{tag}.weights"], atol=2e-6, rtol=1e-5)
+    np.testing.assert_allclose(npy(rgb), g[f"{tag}.rgb"], atol=3e-6, rtol=0)
+    np.testing.assert_allclose(npy(dep), g[f"{tag}.depth"], atol=3e-6, rtol=0)
+    np.testing.assert_allclose(npy(acc), g[f"{tag}.acc"], atol=3e-6, rtol=0)
+    loss = (rgb * cu(g["g_rgb"])).sum() + (dep * cu(g["g_depth"])).sum() + (w * cu(g["g_weights"])).sum() + (acc * cu(g["g_acc"])).sum()
+    loss.backward()
+    ref = g[f"{tag}.d_rgb_sigma"]
+    d = npy(rs.grad)
+    np.testing.assert_allclose(d[..., :3], ref[..., :3], atol=3e-6, rtol=1e-5)
+    err = np.abs(d[..., 3] - ref[..., 3])
+    assert (err <= 2e-5 + 2e-4 * np.abs(ref[..., 3])).all(), err.max()
+    if bg is not None:
+        np.testing.assert_allclose(npy(bg.grad), g[f"{tag}.d_bg"], atol=3e-6, rtol=0)
+
+
+def test_composite_long_rays_and_properties(orc):
+    """S not a multiple of 32, S = 256, early termination, and weights summing to acc."""
+    from adaptive_city_nerf_b200.nerfs.ray_rendering import volume_render
+    rng = np.random.default_rng(5)
+    for S in (2, 31, 33, 100, 256):
+        N = 257
+        rs = rng.uniform(0, 1, (N, S, 4)).astype(F32)
+        rs[..., 3] = rng.uniform(0, 400 if S > 64 else 20, (N, S))          # dense -> saturates -> early exit
+        t = np.sort(rng.uniform(0, 1, (N, S)), axis=1).astype(F32)
+        bg = rng.uniform(0, 1, (N, 3)).astype(F32)
+        rgb, dep, w, acc = volume_render(cu(rs), cu(t), bg_rgb=cu(bg))
+        o = orc.composite_fwd(rs, t, bg)
+        np.testing.assert_allclose(npy(rgb), o[0], atol=3e-6, rtol=0)
+        np.testing.assert_allclose(npy(w), o[2], atol=2e-6, rtol=1e-5)
+        np.testing.assert_allclose(npy(w).sum(1), npy(acc), atol=2e-6)
+        assert (npy(acc) <= 1.0 + 1e-6).all()
+    z = volume_render(torch.rand(0, 8, 4, device="cuda"), torch.rand(0, 8, device="cuda"))
+    assert z[0].shape == (0, 3) and z[2].shape == (0, 8)
+
+
+# ----------------------------------------------------------------------------- stage 5
+@pytest.mark.parametrize("tag", ["g22", "g24"])
+def test_point_routing(ops, golden, tag):
+    g = golden("routing")
+    cen = synth.CENTROIDS_G22 if tag == "g22" else g["cen8"]
+    pts = cu(g["pts"])
+    _, hard, counts = ops.route_points(pts, cu(cen), 2, 1.0, want_counts=True)
+    assert (npy(hard).astype(np.int64) == g[f"{tag}.hard.1.0"]).all()                  # bit-exact assignment
+    assert (npy(counts) == np.bincount(g[f"{tag}.hard.1.0"], minlength=cen.shape[0])).all()
+    for margin in (1.05, 1.1):
+        w, _, counts = ops.route_points(pts, cu(cen), 2, margin, want_counts=True)
+        ref = g[f"{tag}.w.{margin}"]
+        assert ((npy(w) > 0) == (ref > 0)).all(), "support set"                        # bit-exact support
+        np.testing.assert_allclose(npy(w), ref, atol=1.2e-7, rtol=0)                   # FP weights: <= 2 ulp
+        assert (npy(counts) == (ref > 0).sum(0)).all()
+
+
+def test_point_routing_vs_oracle_large(ops, orc):
+    rng = np.random.default_rng(77)
+    lo, hi = synth.AABB_GLOBAL
+    pts = (lo + rng.uniform(0, 1, (300_001, 3)) * (hi - lo)).astype(F32)
+    for margin in (1.0, 1.05):
+        w, h, _ = ops.route_points(cu(pts), cu(synth.CENTROIDS_G22), 2, margin)
+        ow, oh = orc.route_points(pts, synth.CENTROIDS_G22, margin)
+        if margin == 1.0:
+            assert (npy(h) == oh).all()
+        else:
+            assert_bitexact(npy(w), ow, "soft weights vs oracle")      # same op order as the C oracle
+    # 3-D clustering (tolerance-only in the reference too)
+    w, _, _ = ops.route_points(cu(pts[:5000]), cu(synth.CENTROIDS_G22), 3, 1.05)
+    ow, _ = orc.route_points(pts[:5000], synth.CENTROIDS_G22, 1.05, cluster_2d=False)
+    assert_bitexact(npy(w), ow, "3-D weights vs oracle")
+
+
+@pytest.mark.parametrize("stem", ["000005", "000007"])
+def test_voronoi_masks_vs_shipped(ops, golden, stem):
+    """The reference's own golden vectors: excerpts of data/drz/out/example/masks/g22_grid_bm110_ss11."""
+    from adaptive_city_nerf_b200.nerfs.ray_sampling import clamp_rays_near_far
+    g = golden("voronoi")
+    rays = cu(g[f"{stem}.rays"])
+    mask = ops.route_rays_voronoi(rays, int(g["ray_samples"]), cu(g["centroids"]), 2, float(g["margin"]))
+    assert (npy(mask).astype(bool) == g[f"{stem}.voronoi_raw"]).all()
+    _, valid = clamp_rays_near_far(rays, (None, None))
+    assert ((npy(mask).astype(bool) & npy(valid).astype(bool)[:, None]) == g[f"{stem}.shipped"]).all()
+
+
+def test_voronoi_other_margins_and_k8(ops, golden, orc):
+    g = golden("voronoi")
+    rays = g["000005.rays"][:2048]
+    for margin in (1.0, 1.05):
+        mask = ops.route_rays_voronoi(cu(rays), 64, cu(g["centroids"]), 2, margin)
+        assert (npy(mask).astype(bool) == g[f"voronoi_m{margin}"]).all(), margin
+    cen8 = golden("routing")["cen8"]
+    fin = np.isfinite(rays[:, 6])
+    mask = ops.route_rays_voronoi(cu(rays), 256, cu(cen8), 2, 1.05)
+    assert (npy(mask).astype(bool)[fin] == orc.route_rays_voronoi(rays, 256, cen8, 1.05)[fin]).all()
+
+
+def test_bucket_and_blend(ops, orc):
+    rng = np.random.default_rng(3)
+    lo, hi = synth.AABB_GLOBAL
+    P = 10_007
+    id6 = np.concatenate([(lo + rng.uniform(0, 1, (P, 3)) * (hi - lo)), rng.standard_normal((P, 3))], 1).astype(F32)
+    for margin in (1.0, 1.1):
+        w, h, counts = ops.route_points(cu(id6), cu(synth.CENTROIDS_G22), 2, margin, want_counts=True)
+        cnt = npy(counts).astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int32)
+        sel, xd, ws = ops.bucket_points(cu(id6), w, h, 4, cu(off), int(cnt.sum()))
+        sel_n, xd_n, ws_n = npy(sel).astype(np.int64), npy(xd), npy(ws)
+        wn = npy(w) if w is not None else np.eye(4, dtype=F32)[npy(h).astype(np.int64)]
+        for k in range(4):
+            s = sel_n[off[k]:off[k] + cnt[k]]
+            assert sorted(s.tolist()) == np.nonzero(wn[:, k] > 0)[0].tolist()       # same set as nonzero()
+            assert (xd_n[off[k]:off[k] + cnt[k]] == id6[s]).all()
+            assert (ws_n[off[k]:off[k] + cnt[k]] == wn[s, k]).all()
+        y = rng.standard_normal((int(cnt.sum()), 4)).astype(F32)
+        out = torch.zeros(P, 4, device="cuda")
+        for k in range(4):
+            sl = slice(int(off[k]), int(off[k] + cnt[k]))
+            out = ops.BlendFn.apply(out, cu(y[sl]), ws[sl], sel[sl])
+        ref = np.zeros((P, 4), F32)
+        for k in range(4):
+            sl = slice(int(off[k]), int(off[k] + cnt[k]))
+            np.add.at(ref, sel_n[sl], y[sl] * ws_n[sl, None])
+        np.testing.assert_allclose(npy(out), ref, atol=1e-6)
