@@ -61,7 +61,51 @@ def _parse_header(path: Path):
 SIGNATURES = _parse_header(HEADER)
 
 
-def lib() -> C.CDLL:
+class _Profile:
+    """Optional per-kernel CUDA-event timing + launch counting (bench.py turns it on).  Events are
+    recorded on torch's current stream, which is the stream every kernel is launched on."""
+    enabled = False
+    events: dict = {}
+    launches = 0
+
+    @classmethod
+    def start(cls):
+        cls.enabled, cls.events, cls.launches = True, {}, 0
+
+    @classmethod
+    def stop(cls):
+        """-> {kernel: (n_launches, total_ms)}; call after torch.cuda.synchronize()."""
+        cls.enabled = False
+        return {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in cls.events.items()}
+
+
+_NOT_KERNELS = {"acn_version", "acn_last_error", "acn_create", "acn_destroy", "acn_device_info"}
+
+
+class _Bound:
+    """Namespace of the bound entry points; kernel launches go through the profiling shim."""
+
+
+def _wrap(name, fn):
+    if name in _NOT_KERNELS:
+        return fn
+
+    def call(*args):
+        if not _Profile.enabled:
+            return fn(*args)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        _Profile.events.setdefault(name, []).append((s, e))
+        _Profile.launches += 1
+        return rc
+
+    call.argtypes = fn.argtypes
+    return call
+
+
+def lib():
     """Load the shared library (once).  Raises if it has not been built."""
     global _lib
     if _lib is None:
@@ -72,11 +116,13 @@ def lib() -> C.CDLL:
                         f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(nvcc, sm_100a).  adaptive_city_nerf_b200 has no CPU or PyTorch fallback.")
                 l = C.CDLL(str(LIB_PATH))
+                ns = _Bound()
                 for name, argtypes in SIGNATURES.items():
                     fn = getattr(l, name)
                     fn.argtypes = argtypes
                     fn.restype = C.c_char_p if name == "acn_last_error" else c_int
-                _lib = l
+                    setattr(ns, name, _wrap(name, fn))
+                _lib = ns
     return _lib
 
 

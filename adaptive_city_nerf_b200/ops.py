@@ -223,11 +223,13 @@ def field_bwd(enc: Tensor, dirs: Tensor, dirs_stride: int, dirs_group: int, ws: 
     E, H, G, C = _field_dims(ws)
     dev = enc.device
     grads: List[Optional[Tensor]] = [torch.zeros_like(w, dtype=torch.float32) if n else None for w, n in zip(ws, need)]
-    d_enc = torch.empty(P, E, dtype=enc.dtype, device=dev) if want_enc_grad else None
+    # d_enc stays fp32 even for an fp16 encoding: per-sample gradients of a mean loss over 2^18 rays are
+    # ~1e-9 and would flush to zero in fp16 (the reference needs GradScaler for the same reason)
+    d_enc = torch.empty(P, E, dtype=torch.float32, device=dev) if want_enc_grad else None
     wst, gst = pack_weights(ws), pack_weights(grads)
     check(lib().acn_field_bwd(ctx(dev), ptr(enc), _dt(enc), ptr(dirs), dirs_stride, dirs_group, P, E, H, G, C,
                               C_.byref(wst), F16 if half else F32, ptr(d_rgb_sigma), C_.byref(gst),
-                              ptr(d_enc), _dt(enc), stream(dev)))
+                              ptr(d_enc), F32, stream(dev)))
     return grads, d_enc
 
 

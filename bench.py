@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native rendering hot path (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU arm (oracle port, host cores)
+
+Workload (BASELINE.json configs[1]): ONE Instant-NGP expert (16-level hash grid, T = 2^19, F = 2,
+64-wide MLPs), 2^18 rays x 64 samples per batch, one TRAINING step = render_rays (train mode,
+stratified jitter, fp16 tcgen05 MLP under autocast) + MSE + backward (table + 14 MLP tensors) +
+fused Adam step.  Synthetic rays: 64 nadir 64x64 pinhole views inside the shipped scene box
+(SURVEY 8d); random-init weights (reference init).  Metric: train rays/s (whole job).
+
+N > 1 (torchrun): single-expert data parallel -- every rank renders its own 2^18-ray batch (weak
+scaling) and the hash-table + MLP gradients are all-reduced over NCCL before the optimizer step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "tests" / "golden"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+N_VIEWS, VIEW_HW, SAMPLES, LOG2T = 64, 64, 64, 19
+N_RAYS = N_VIEWS * VIEW_HW * VIEW_HW          # 2^18
+CPU_SAMPLE_RAYS = 4096                         # BASELINE configs[0] shape for the CPU arms
+
+# algorithmic work per sample
+ENC_FWD_BYTES = 16 * 8 * 2 * 4 + 64            # 1024 B gathered (fp32 table) + 64 B fp16 row written
+ENC_BWD_BYTES = 2 * 1024 + 128                 # read-modify-write of the same 1024 B + 128 B fp32 dL/denc read
+FIELD_FWD_FLOP = 26880
+FIELD_BWD_FLOP = 2 * 26880                     # dgrad + wgrad (the recompute is not counted)
+COMPOSITE_BYTES = 24
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return dict(hbm=float(d["hbm_gbs"]), tensor=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tensor=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_workload(n_rays: int, seed: int = 0):
+    import synth
+    from oracle import oracle as orc
+    cams = synth.nadir_rays(seed, max(1, n_rays // (VIEW_HW * VIEW_HW)), H=VIEW_HW, W=VIEW_HW, f=60.0)
+    rays = []
+    for cam in cams:
+        d = orc.ray_directions(cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], True).reshape(-1, 3)
+        rays.append(orc.get_rays(d, cam["c2w"], aabb=synth.AABB_GLOBAL))
+    rays = np.concatenate(rays)[:n_rays]
+    rays, valid = orc.clamp_near_far(rays, (None, None))
+    assert valid.all()
+    rng = np.random.default_rng(seed + 1)
+    gt = rng.uniform(0, 1, (rays.shape[0], 3)).astype(np.float32)
+    sd = synth.make_expert_params(seed + 2, log2T=LOG2T, table_scale=1e-3)
+    return rays, gt, sd
+
+
+def cpu_step(orc, rays, gt, sd, jitter):
+    """One fwd+bwd of the hot path on the host (oracle port of the reference's torch path)."""
+    import synth
+    lo, hi = synth.AABB_GLOBAL
+    ws = synth.expert_weight_list(sd)
+    res = orc.level_resolutions()
+    N = rays.shape[0]
+    bg = np.ones((N, 3), np.float32)
+    rgb, dep, w, acc, aux = orc.render_expert(rays, SAMPLES, ws, sd["xyz_encoder.hash_table"], lo, hi - lo, 16, 2, LOG2T,
+                                              res, jitter=jitter, bg=bg)
+    g_rgb = (2.0 / rgb.size) * (rgb - gt)
+    d_rs, _ = orc.composite_bwd(aux["rgb_sigma"].reshape(N, SAMPLES, 4), aux["t"], bg, g_rgb)
+    grads, d_enc = orc.field_bwd(aux["enc"], aux["dirs"], ws, d_rs.reshape(-1, 4))
+    dt = orc.hashgrid_bwd(aux["x01"], d_enc, 16, 2, LOG2T, res)
+    return float(((rgb - gt) ** 2).mean()), dt
+
+
+def time_cpu(steps: int, warmup: int):
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    orc.set_threads(cores)
+    orc.lib()
+    rays, gt, sd = cpu_workload(CPU_SAMPLE_RAYS)
+    jit = np.random.default_rng(5).uniform(0, 1, (rays.shape[0], SAMPLES)).astype(np.float32)
+    for _ in range(warmup):
+        cpu_step(orc, rays, gt, sd, jit)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_step(orc, rays, gt, sd, jit)
+        ts.append(time.perf_counter() - t0)
+    return rays.shape[0], ts, cores
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port: the reference is
+    pure Python/torch and cannot travel to the GPU box) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, ts, cores = time_cpu(args.steps, max(1, min(args.warmup, 2)))
+    total = sum(ts)
+    val = n * len(ts) / total
+    sample = f"{n} rays x {SAMPLES} samples fwd+bwd per step (configs[0] shape; T=2^{LOG2T}), no optimizer"
+    print(json.dumps({
+        "impl": "reference", "metric": "train rays/s", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"single Instant-NGP expert (L16 F2 T=2^{LOG2T}, 64-wide MLPs), training step; CPU arm on a "
+                               f"{n}-ray sample", "rays_per_step": n, "samples_per_ray": SAMPLES},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def gpu_workload(dev, seed: int):
+    import torch
+    import synth
+    from adaptive_city_nerf_b200.nerfs.ray_sampling import clamp_rays_near_far, get_ray_directions, get_rays
+    from adaptive_city_nerf_b200.nerfs.scene_box import SceneBox
+    box = SceneBox(torch.from_numpy(synth.AABB_GLOBAL).to(dev))
+    dirs = get_ray_directions(VIEW_HW, VIEW_HW, 60.0, 60.0, VIEW_HW / 2, VIEW_HW / 2, True, dev)
+    rays = []
+    for cam in synth.nadir_rays(seed, N_VIEWS, H=VIEW_HW, W=VIEW_HW, f=60.0):
+        rays.append(get_rays(dirs, torch.from_numpy(cam["c2w"]).to(dev), scene_box=box).view(-1, 8))
+    rays = torch.cat(rays)
+    rays, valid = clamp_rays_near_far(rays, (None, None))
+    assert bool(valid.all()) and rays.shape[0] == N_RAYS
+    gen = torch.Generator(device="cpu").manual_seed(seed + 1)
+    gt = torch.rand(N_RAYS, 3, generator=gen)
+    return rays, gt.to(dev), box
+
+
+def make_model(dev, box):
+    import torch
+    import synth
+    from adaptive_city_nerf_b200.models.inr import MetaContainer
+    torch.manual_seed(0)
+    conf = dict(levels=16, features_per_level=2, log2_hashmap_size=LOG2T, max_res=4096, min_res=16, interpolation="Linear")
+    m = MetaContainer(num_submodules=1, centroids=torch.zeros(1, 3), aabb=torch.from_numpy(synth.AABB_GLOBAL),
+                      boundary_margin=1.0, use_bg_nerf=False, expert_box_list=[box], hidden=64, sigma_depth=2,
+                      color_depth=2, color_hidden=64, dir_encoding="spherical", hash_enc_conf=conf,
+                      occ_conf={"use_occ": False}).to(dev)
+    m.train()
+    return m
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from adaptive_city_nerf_b200 import _lib
+    from adaptive_city_nerf_b200.nerfs.ray_rendering import render_rays
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a B200; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    rays, gt, box = gpu_workload(dev, seed=100 + rank)
+    model = make_model(dev, box)
+    groups = model.get_param_groups()
+    opt = torch.optim.Adam([{"params": groups["encoding"]["params"], "lr": 1e-2},
+                            {"params": groups["sigma"]["params"], "lr": 2e-3},
+                            {"params": groups["color"]["params"], "lr": 2e-3}], eps=1e-15, fused=True)
+    params = [p for g in opt.param_groups for p in g["params"]]
+    mlp_params = [p for p in params if p.numel() < (1 << 20)]
+    table = [p for p in params if p.numel() >= (1 << 20)]
+
+    def step(r, g):
+        with torch.autocast("cuda", dtype=torch.float16):
+            rgb, _, _, _ = render_rays(model, r, ray_samples=SAMPLES, active_module=0, chunk=1 << 30)
+        loss = torch.nn.functional.mse_loss(rgb, g)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            for t in table:
+                dist.all_reduce(t.grad)
+            flat = torch.cat([p.grad.reshape(-1) for p in mlp_params])
+            dist.all_reduce(flat)
+            off = 0
+            for p in mlp_params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            for p in params:
+                p.grad.div_(world)
+        opt.step()
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(rays, gt)
+    # ---- device-resident throughput (`value`) with per-kernel events ----
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        _lib._Profile.start()
+        e0.record()
+        for _ in range(args.steps):
+            step(rays, gt)
+        e1.record()
+        sync()
+    prof = _lib._Profile.stop()
+    launches = _lib._Profile.launches
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    # ---- end to end through the public API with HOST buffers ----
+    rays_h = rays.cpu().pin_memory()
+    gt_h = gt.cpu().pin_memory()
+    for _ in range(2):
+        float(step(rays_h.to(dev, non_blocking=True), gt_h.to(dev, non_blocking=True)))
+    sync()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(rays_h.to(dev, non_blocking=True), gt_h.to(dev, non_blocking=True))
+        loss_val = float(loss)                      # D2H read of the step's result
+    e1.record()
+    sync()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t)
+
+    if rank == 0:
+        pk = peaks()
+        P = N_RAYS * SAMPLES
+        work = {  # kernel -> (bound, algorithmic units per launch, unit scale)
+            "acn_hashgrid_fwd_rays": ("hbm", ENC_FWD_BYTES * P), "acn_hashgrid_bwd_rays": ("hbm", ENC_BWD_BYTES * P),
+            "acn_field_fwd": ("tensor", FIELD_FWD_FLOP * P), "acn_field_bwd": ("tensor", FIELD_BWD_FLOP * P),
+            "acn_composite_fwd": ("hbm", COMPOSITE_BYTES * P), "acn_composite_bwd": ("hbm", (COMPOSITE_BYTES + 20) * P),
+        }
+        kernels = {}
+        for k, (n, tot) in prof.items():
+            avg = tot / max(n, 1)
+            ent = {"launches": n, "avg_ms": round(avg, 4), "share": round(tot / ms, 4)}
+            if k in work and avg > 0:
+                bound, units = work[k]
+                ach = units / (avg * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+                ent.update(bound=bound, achieved=round(ach, 2), frac=round(ach / pk[bound], 4),
+                           unit="GB/s" if bound == "hbm" else "TFLOP/s")
+            kernels[k] = ent
+        top = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches"])
+        tk = kernels[top]
+        roof = {"kernel": top, "bound": tk["bound"], "achieved": tk["achieved"], "peak": pk[tk["bound"]], "unit": tk["unit"],
+                "frac": tk["frac"], "traffic": None, "peak_source": pk["src"], "avg_ms": tk["avg_ms"]}
+        n_cpu, ts, cores = time_cpu(steps=2, warmup=1) if world == 1 else (0, [], 0)
+        out = {
+            "metric": "train rays/s", "value": world * N_RAYS * args.steps / (ms * 1e-3), "unit": "rays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"single Instant-NGP expert (L16 F2 T=2^{LOG2T}, 64-wide MLPs), 2^18 rays/batch x {SAMPLES} "
+                                   "samples, training step = render_rays fwd + MSE + bwd + fused Adam (configs[1])",
+                       "rays_per_step_per_gpu": N_RAYS, "samples_per_ray": SAMPLES, "parallelism": f"dp{world}",
+                       "l2": "inputs > L2: 64 MiB table + 1 GiB fp16 encodings + 2 GiB fp32 dL/denc per step"},
+            "samples_per_s": world * N_RAYS * SAMPLES * args.steps / (ms * 1e-3),
+            "e2e": {"value": world * N_RAYS * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
+                    "h2d_bytes_per_step": int(rays_h.numel() * 4 + gt_h.numel() * 4), "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps, "last_loss": loss_val},
+            "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "kernels": kernels,
+        }
+        if ts:
+            out["cpu_baseline"] = {"value": n_cpu / min(ts), "unit": "rays/s", "cores": cores, "kind": "port",
+                                   "sample": f"{n_cpu} rays x {SAMPLES} samples fwd+bwd (configs[0] shape, T=2^{LOG2T}), "
+                                             "best of 2, no optimizer"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,6 +16,7 @@
  * fuses (torch.lerp, the cdist matmul form) -- those spots call fmaf() explicitly.
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -382,16 +383,27 @@ typedef struct {
 
 /* y = W x + b over `in` inputs; half=1 emulates torch autocast(fp16): inputs and weights are
  * rounded to fp16, products accumulate in fp32, the GEMM result is rounded to fp16, and the
- * fp32 bias is then added in fp32 (models/metamodule/metamodule.py:150-155 under autocast). */
-static inline void orc_linear(const float* W, const float* b, const float* x, int in, int out,
-                              int half, float* y)
+ * fp32 bias is then added in fp32 (models/metamodule/metamodule.py:150-155 under autocast).
+ * The loop nest is input-major so the compiler can vectorise across outputs WITHOUT changing
+ * any output's summation order (i ascending), i.e. results are identical to the naive nest. */
+static inline void orc_linear(const float* restrict W, const float* restrict b, const float* restrict x,
+                              int in, int out, int half, float* restrict y)
 {
-    for (int o = 0; o < out; ++o) {
-        float acc = 0.0f;
-        if (half) { for (int i = 0; i < in; ++i) acc += f16r(W[o * in + i]) * f16r(x[i]); acc = f16r(acc); }
-        else { for (int i = 0; i < in; ++i) acc += W[o * in + i] * x[i]; }
-        y[o] = acc + b[o];
+    for (int o = 0; o < out; ++o) y[o] = 0.0f;
+    if (half) {
+        for (int i = 0; i < in; ++i) {
+            float xi = f16r(x[i]);
+            for (int o = 0; o < out; ++o) y[o] += f16r(W[o * in + i]) * xi;
+        }
+        for (int o = 0; o < out; ++o) y[o] = f16r(y[o]);
+    } else {
+        for (int i = 0; i < in; ++i) {
+            float xi = x[i];
+#pragma omp simd
+            for (int o = 0; o < out; ++o) y[o] += W[o * in + i] * xi;
+        }
     }
+    for (int o = 0; o < out; ++o) y[o] = y[o] + b[o];
 }
 
 /* models/trunc_exp.py:32-61: exp(clamp(x, -88.722839111, 88.722839111)). */
@@ -444,14 +456,14 @@ typedef struct {
 
 /* Backward of orc_field_fwd (fp32 math): d rgb_sigma (P,4) -> weight grads (+=) and d enc (P,E).
  * sigmoid' = y(1-y); trunc_exp' = exp(clamped x) (models/trunc_exp.py:52-57); ReLU' = (h>0). */
-ORC_API void orc_field_bwd(const float* enc, const float* dirs, int64_t P, int E, int H, int G,
-                           int C, const orc_field_weights* w, const float* d_rgb_sigma,
-                           orc_field_grads* g, float* d_enc)
+static void orc_field_bwd_range(const float* enc, const float* dirs, int64_t p0, int64_t p1, int E, int H, int G,
+                                int C, const orc_field_weights* w, const float* d_rgb_sigma,
+                                orc_field_grads* g, float* d_enc)
 {
     const int stride = 2 * H + 1 + G + 16 + 2 * C + 3;
     float* act = (float*)malloc(sizeof(float) * (size_t)stride);
     float rs[4];
-    for (int64_t p = 0; p < P; ++p) {
+    for (int64_t p = p0; p < p1; ++p) {
         orc_field_fwd(enc + (size_t)p * E, dirs + 3 * p, 1, E, H, G, C, w, 0, rs, act);
         const float *h1 = act, *h2 = act + H, *cin = act + 2 * H + 1, *c1 = cin + G + 16, *c2 = c1 + C;
         const float* x = enc + (size_t)p * E;
@@ -463,17 +475,20 @@ ORC_API void orc_field_bwd(const float* enc, const float* dirs, int64_t P, int E
         for (int i = 0; i < C; ++i) d_c2[i] = 0.0f;
         for (int o = 0; o < 3; ++o) {
             g->b_c2[o] += d_rr[o];
+            _Pragma("omp simd")
             for (int i = 0; i < C; ++i) { g->w_c2[o * C + i] += d_rr[o] * c2[i]; d_c2[i] += d_rr[o] * w->w_c2[o * C + i]; }
         }
         for (int i = 0; i < C; ++i) { if (!(c2[i] > 0.0f)) d_c2[i] = 0.0f; d_c1[i] = 0.0f; }
         for (int o = 0; o < C; ++o) {
             g->b_c1[o] += d_c2[o];
+            _Pragma("omp simd")
             for (int i = 0; i < C; ++i) { g->w_c1[o * C + i] += d_c2[o] * c1[i]; d_c1[i] += d_c2[o] * w->w_c1[o * C + i]; }
         }
         for (int i = 0; i < C; ++i) if (!(c1[i] > 0.0f)) d_c1[i] = 0.0f;
         for (int i = 0; i < G + 16; ++i) d_cin[i] = 0.0f;
         for (int o = 0; o < C; ++o) {
             g->b_c0[o] += d_c1[o];
+            _Pragma("omp simd")
             for (int i = 0; i < G + 16; ++i) { g->w_c0[o * (G + 16) + i] += d_c1[o] * cin[i]; d_cin[i] += d_c1[o] * w->w_c0[o * (G + 16) + i]; }
         }
         /* heads */
@@ -482,12 +497,14 @@ ORC_API void orc_field_bwd(const float* enc, const float* dirs, int64_t P, int E
         for (int i = 0; i < H; ++i) { g->w_sig[i] += d_sg * h2[i]; d_h2[i] += d_sg * w->w_sig[i]; }
         for (int o = 0; o < G; ++o) {
             g->b_geo[o] += d_cin[o];
+            _Pragma("omp simd")
             for (int i = 0; i < H; ++i) { g->w_geo[o * H + i] += d_cin[o] * h2[i]; d_h2[i] += d_cin[o] * w->w_geo[o * H + i]; }
         }
         /* trunk */
         for (int i = 0; i < H; ++i) { if (!(h2[i] > 0.0f)) d_h2[i] = 0.0f; d_h1[i] = 0.0f; }
         for (int o = 0; o < H; ++o) {
             g->b_t1[o] += d_h2[o];
+            _Pragma("omp simd")
             for (int i = 0; i < H; ++i) { g->w_t1[o * H + i] += d_h2[o] * h1[i]; d_h1[i] += d_h2[o] * w->w_t1[o * H + i]; }
         }
         for (int i = 0; i < H; ++i) if (!(h1[i] > 0.0f)) d_h1[i] = 0.0f;
@@ -499,6 +516,35 @@ ORC_API void orc_field_bwd(const float* enc, const float* dirs, int64_t P, int E
         }
     }
     free(act);
+}
+
+/* Points are split over OpenMP threads with private gradient buffers (used by the CPU baseline). */
+ORC_API void orc_field_bwd(const float* enc, const float* dirs, int64_t P, int E, int H, int G,
+                           int C, const orc_field_weights* w, const float* d_rgb_sigma,
+                           orc_field_grads* g, float* d_enc)
+{
+    /* sizes of the 14 tensors, in struct order */
+    const size_t sz[14] = { (size_t)H * E, (size_t)H, (size_t)H * H, (size_t)H, (size_t)H, 1, (size_t)G * H, (size_t)G,
+                            (size_t)C * (G + 16), (size_t)C, (size_t)C * C, (size_t)C, (size_t)3 * C, 3 };
+    size_t total = 0;
+    for (int i = 0; i < 14; ++i) total += sz[i];
+    float** gp = (float**)g;
+#pragma omp parallel
+    {
+        int nt = omp_get_num_threads(), id = omp_get_thread_num();
+        int64_t p0 = P * id / nt, p1 = P * (id + 1) / nt;
+        float* buf = (float*)calloc(total, sizeof(float));
+        orc_field_grads loc;
+        float** lp = (float**)&loc;
+        size_t off = 0;
+        for (int i = 0; i < 14; ++i) { lp[i] = buf + off; off += sz[i]; }
+        orc_field_bwd_range(enc, dirs, p0, p1, E, H, G, C, w, d_rgb_sigma, &loc, d_enc);
+#pragma omp critical
+        {
+            for (int i = 0; i < 14; ++i) for (size_t j = 0; j < sz[i]; ++j) gp[i][j] += lp[i][j];
+        }
+        free(buf);
+    }
 }
 
 /* models/inr/meta_container.py:347-382 background_color: SH16(normalize(d)) -> Linear(16,Hb)
