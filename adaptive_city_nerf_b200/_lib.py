@@ -50,6 +50,8 @@ def _parse_header(path: Path):
                     types.append(c_i64)
                 elif a.startswith("float"):
                     types.append(c_f)
+                elif a.startswith("uint32_t"):
+                    types.append(C.c_uint32)
                 elif a.startswith("int"):
                     types.append(c_int)
                 else:

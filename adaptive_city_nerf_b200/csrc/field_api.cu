@@ -59,8 +59,11 @@ extern "C" int acn_field_bwd(acn_ctx* ctx, const void* enc, int enc_dtype, const
     ACN_REQUIRE(d_enc_dtype == ACN_F32 || d_enc_dtype == ACN_F16, ACN_EINVAL, "acn_field_bwd: bad d_enc dtype");
     if (P == 0) return ACN_OK;
     ACN_REQUIRE(d_rgb_sigma && ((uintptr_t)d_rgb_sigma & 15) == 0, ACN_EINVAL, "acn_field_bwd: d_rgb_sigma null or misaligned");
-    // Round 1: both precisions take the fp32 SIMT backward (gradients of the fp16 forward to
-    // within fp16 rounding); the tcgen05 backward is the next kernel on the list.
+    if (precision == ACN_F16) {
+        ACN_REQUIRE(d_enc_dtype == ACN_F32, ACN_EUNSUPPORTED, "acn_field_bwd(f16): d_enc must be fp32");
+        return acn_field_bwd_tc(ctx, enc, enc_dtype, dirs, dirs_stride, dirs_group, P, E, H, G, C, w, d_rgb_sigma, g,
+                                (float*)d_enc_or_null, (cudaStream_t)stream);
+    }
     return acn_field_bwd_fp32(ctx, enc, enc_dtype, dirs, dirs_stride, dirs_group, P, E, H, G, C, w, d_rgb_sigma, g,
                               d_enc_or_null, d_enc_dtype, (cudaStream_t)stream);
 }

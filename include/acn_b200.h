@@ -182,6 +182,14 @@ int acn_blend_bwd(acn_ctx*, const float* d_out, const float* w, const int32_t* s
 int acn_debug_umma_gemm(acn_ctx*, const void* a_f16, const void* w_f16, int N, int K, float* d,
                         acn_stream);
 
+/* Raw harness: stages two 16-bit matrices as canonical tiles and issues `ksteps` MMAs with
+ * host-supplied descriptors, then dumps TMEM lanes 0..127 x ncols.  Used by tools/umma_probe.py to
+ * establish MN-major / mixed-dtype / M=64 layouts on hardware. */
+int acn_debug_umma_raw(acn_ctx*, const void* a16, int rows_a, int cols_a, const void* b16, int rows_b,
+                       int cols_b, uint32_t idesc, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step,
+                       uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, int ksteps, int ncols, float* out,
+                       acn_stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

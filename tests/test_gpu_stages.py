@@ -367,3 +367,33 @@ def test_bucket_and_blend(ops, orc):
             sl = slice(int(off[k]), int(off[k] + cnt[k]))
             np.add.at(ref, sel_n[sl], y[sl] * ws_n[sl, None])
         np.testing.assert_allclose(npy(out), ref, atol=1e-6)
+
+
+def test_hashgrid_bwd_march_vs_generic(ops):
+    """The ray-marching scatter (run-length aggregation, rotated start) must equal the generic
+    per-(point,level) scatter: same sums, different order -> fp32 tolerance."""
+    from adaptive_city_nerf_b200.nerfs.ray_sampling import get_rays, get_ray_directions
+    from adaptive_city_nerf_b200.nerfs.scene_box import SceneBox
+    box = SceneBox(cu(synth.AABB_GLOBAL))
+    cam = synth.nadir_rays(17, 1, H=48, W=33, f=25.0)[0]
+    dirs = get_ray_directions(48, 33, cam["fx"], cam["fy"], cam["cx"], cam["cy"], True, torch.device("cuda"))
+    rays = get_rays(dirs, cu(cam["c2w"]), scene_box=box).view(-1, 8)
+    for S, log2T, mode in ((64, 14, 1), (37, 12, 2), (2, 10, 1)):
+        N = rays.shape[0]
+        t = ops.sample_stratified(rays, S, torch.rand(N, S, device="cuda"))
+        enc = _encoder(log2T)
+        spec = ops.GridSpec(16, 2, log2T, enc.level_resolutions.clone(), mode)
+        box6 = torch.cat([box.min, box.extent]).contiguous()
+        gen = torch.Generator(device="cuda").manual_seed(S)
+        dout = torch.randn(N * S, 32, device="cuda", generator=gen)
+        dout[::7] = 0.0                                     # zero rows are skipped
+        a = torch.zeros(16 << log2T, 2, device="cuda")
+        b = torch.zeros_like(a)
+        ops.hashgrid_bwd_rays(rays, t, dout, spec, box6, a)                       # march kernel
+        ops.hashgrid_bwd(ops.points(rays, t), dout, spec, box6, b)                # generic kernel
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 2e-5 * scale + 1e-6, (S, log2T, mode)
+        # fp16 dL/denc input
+        a16 = torch.zeros_like(a)
+        ops.hashgrid_bwd_rays(rays, t, dout.half(), spec, box6, a16)
+        assert float((a16 - b).abs().max()) <= 2e-3 * scale

@@ -57,3 +57,41 @@ def test_field_fp16_many_tiles_matches_fp32():
     y32 = ops.field_fwd(enc, dirs, 3, 1, wt, half=False)
     assert (y16[:, :3] - y32[:, :3]).abs().max() < 4e-3
     assert ((y16[:, 3] - y32[:, 3]).abs() / (y32[:, 3].abs() + 1e-3)).max() < 2e-2
+
+
+def _rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+@pytest.mark.parametrize("P", [1, 128, 129, 1000, 300_007])
+def test_field_bf16_backward_matches_fp32(P):
+    """tcgen05 backward (bf16 operands, fp32 accumulate, TMEM-resident weight gradients) vs the fp32
+    SIMT backward on the same inputs.  Bar: relative L2 <= 1e-2 per tensor."""
+    from adaptive_city_nerf_b200 import ops
+    sd = synth.make_expert_params(5, log2T=4)
+    wt = [cu(w) for w in synth.expert_weight_list(sd)]
+    gen = torch.Generator(device="cuda").manual_seed(P)
+    enc = (torch.rand(P, 32, device="cuda", generator=gen) - 0.5).half()
+    dirs = torch.randn(P, 3, device="cuda", generator=gen)
+    # realistic magnitudes: gradients of a mean loss are tiny (this is what rules fp16 gradient tiles out)
+    dy = torch.randn(P, 4, device="cuda", generator=gen) * 1e-7
+    dy[::5] = 0.0
+    g32, de32 = ops.field_bwd(enc, dirs, 3, 1, wt, False, dy, True, [True] * 14)
+    g16, de16 = ops.field_bwd(enc, dirs, 3, 1, wt, True, dy, True, [True] * 14)
+    for key, a, b in zip(synth.EXPERT_KEYS, g16, g32):
+        assert torch.isfinite(a).all(), key
+        assert _rel_l2(a, b) < 1e-2, (key, _rel_l2(a, b))
+    assert _rel_l2(de16, de32) < 1e-2
+    # skipping the input gradient (inner-loop steps) must not change the weight gradients
+    g16b, none = ops.field_bwd(enc, dirs, 3, 1, wt, True, dy, False, [True] * 14)
+    assert none is None
+    for a, b in zip(g16b, g16):
+        assert _rel_l2(a, b) < 1e-5
+    # only some gradients requested
+    need = [i % 2 == 0 for i in range(14)]
+    g16c, _ = ops.field_bwd(enc, dirs, 3, 1, wt, True, dy, False, need)
+    assert all((x is None) == (not n) for x, n in zip(g16c, need))
+    for a, b, n in zip(g16c, g16, need):
+        if n:
+            assert _rel_l2(a, b) < 1e-5
