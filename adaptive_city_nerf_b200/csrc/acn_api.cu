@@ -11,6 +11,12 @@ void acn_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+unsigned int* acn_scratch_word(acn_ctx* ctx) {
+    if (!ctx || !ctx->scratch) return nullptr;
+    unsigned int i = __atomic_fetch_add(&ctx->scratch_next, 1u, __ATOMIC_RELAXED);
+    return ctx->scratch + (i % ACN_SCRATCH_WORDS);
+}
+
 extern "C" int acn_version(void) { return ACN_VERSION; }
 
 extern "C" const char* acn_last_error(void) { return g_err; }
@@ -33,12 +39,27 @@ extern "C" int acn_create(int device, acn_ctx** out) {
     c->cc_minor = p.minor;
     c->l2_bytes = p.l2CacheSize;
     c->max_smem_optin = (int)p.sharedMemPerBlockOptin;
+    c->scratch = nullptr;
+    c->scratch_next = 0;
+    {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaError_t es = cudaSetDevice(device);
+        if (es == cudaSuccess) es = cudaMalloc((void**)&c->scratch, ACN_SCRATCH_WORDS * sizeof(unsigned int));
+        if (prev >= 0 && prev != device) cudaSetDevice(prev);
+        if (es != cudaSuccess) {
+            delete c;
+            acn_set_error("acn_create: scratch allocation failed: %s", cudaGetErrorString(es));
+            return ACN_ECUDA;
+        }
+    }
     *out = c;
     return ACN_OK;
 }
 
 extern "C" int acn_destroy(acn_ctx* ctx) {
     ACN_CHECK_CTX(ctx);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     delete ctx;
     return ACN_OK;
 }

@@ -13,7 +13,14 @@ struct acn_ctx {
     int cc_major, cc_minor;
     int64_t l2_bytes;
     int max_smem_optin;
+    unsigned int* scratch;      // ACN_SCRATCH_WORDS device words (loss-scale reductions), ring-allocated
+    unsigned int scratch_next;  // ring cursor (atomic)
 };
+constexpr int ACN_SCRATCH_WORDS = 256;
+
+// One device word of context scratch; consecutive calls (possibly on different streams / host threads)
+// get different words, so they never share one while in flight.
+unsigned int* acn_scratch_word(acn_ctx* ctx);
 
 void acn_set_error(const char* fmt, ...);
 

@@ -1,0 +1,841 @@
+// Stage 3 under autocast(fp16): the expert's field MLPs on tcgen05 tensor cores, forward and backward.
+//
+// Reference numerics: models/metamodule/metamodule.py:150-155 under torch.autocast -- fp16 GEMM operands,
+// fp32 accumulation, the GEMM result rounded to fp16 before the bias add + ReLU.
+//
+// Both kernels are persistent (one CTA per SM).  Tiles are 128 points (MMA M = 128); a point owns row r of
+// every activation tile in shared memory (canonical no-swizzle UMMA layout, umma.cuh) and lane r of a TMEM
+// accumulator window.  All six weight matrices stay resident in shared memory as B operands.  The layers of a
+// tile are serially dependent (MMA -> epilogue -> MMA ...), so the tensor pipe is kept busy by running several
+// tiles per SM out of phase, with no __syncthreads and no dedicated issuer thread in the steady state:
+//
+//   forward   4 warpgroups x 2 tiles.  Each warpgroup (128 threads, thread = row) ping-pongs two tiles: while
+//             the tensor core runs tile A's layer, the same threads run tile B's epilogue.  After an epilogue
+//             the warpgroup meets on a named barrier and ONE elected lane of its first warp issues the next
+//             layer's tcgen05.mma's and commits to that tile's mbarrier.  (A single issuer thread serving all
+//             tiles was measured at ~1200 cycles per layer step -- see tools/field_trace.py -- and was the
+//             bottleneck; per-warpgroup issue from warp-uniform code with elect.sync is ~10x cheaper.)
+//   backward  2 slots x 1 tile (the six activation tiles of a tile take 88 KB), 256 threads per slot: two
+//             threads per row, each owning 32 of a layer's 64 columns, to halve the epilogue latency on the
+//             critical path.  Per layer the issuer launches dgrad FIRST and commits it separately, then wgrad
+//             and bgrad: the epilogue starts on the dgrad result while the weight-gradient MMAs still run and
+//             only its in-place stores wait for them.
+//
+// Backward (autograd of the forward): recomputes the tile's forward with the SAME instructions as the
+// forward kernel (bit-identical activations, hence the ReLU masks the forward used), then walks the layers
+// in reverse: wgrad (contraction over the tile's 128 points, both operands viewed MN-major, accumulator
+// PERSISTENT in TMEM across every tile the CTA processes), bgrad (G^T 1 against a constant ones tile) and
+// dgrad; the epilogue masks with [act > 0] and overwrites the dead activation tile with the gradient tile.
+// Gradient tiles are fp16 carrying one global power-of-two scale (max|dL/dy| * 2^k in [2^9, 2^10)) measured
+// by a max-reduction over dL/dy before the launch -- the job GradScaler does for the reference -- and divided
+// out of d_enc and the weight gradients in fp32.  After its last tile the CTA adds its TMEM-resident weight
+// gradients to global memory (one atomicAdd per weight per CTA).
+//
+// Operand-layout facts were established on hardware with tools/umma_probe.py (profiles/): for a canonical
+// tile with row-group stride RG the K-major view is (lbo=128, sbo=RG, +256 B per K step), the MN-major view
+// is (lbo=RG, sbo=128, +2*RG per K step); an M=128 MMA whose MN-major A tile has only 64 (or 16) columns
+// reads on into the following shared memory and leaves garbage in TMEM lanes >= 64 (16), which are never read.
+#include "field_common.cuh"
+#include "field_internal.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using umma::lds128;
+using umma::sts128;
+
+constexpr int TM = 128;                 // points per tile = MMA M
+constexpr uint32_t HALF2_ONE = 0x3C003C00u;
+
+struct Tile { uint32_t a; uint32_t rg; };   // shared-space byte address + row-group stride (= cols/8 * 128 B)
+__device__ __forceinline__ Tile mk_tile(uint32_t addr, int cols) { return Tile{ addr, (uint32_t)(cols / 8) * 128u }; }
+
+__device__ __forceinline__ uint64_t desc_k(const Tile& t, int ks) { return umma::make_desc(t.a + ks * 256, 128, t.rg); }
+__device__ __forceinline__ uint64_t desc_mn(const Tile& t, int ks) { return umma::make_desc(t.a + ks * 2 * t.rg, t.rg, 128); }
+__device__ __forceinline__ uint32_t chunk_addr(const Tile& t, int r, int c) { return t.a + umma::chunk_off(r, c, t.rg); }
+
+// ---- small PTX helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// relu(a * b + c) on packed halves, single rounding
+__device__ __forceinline__ uint32_t hfma2_relu(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// g * [act > 0] on packed halves
+__device__ __forceinline__ uint32_t hmask2(uint32_t g, uint32_t act) {
+    uint32_t m, d;
+    asm("set.gt.f16x2.f16x2 %0, %1, %2;" : "=r"(m) : "r"(act), "r"(0u));
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(g), "r"(m));
+    return d;
+}
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// MUFU-based activations: relative error ~2^-22, far inside the fp16 operand rounding of this path
+__device__ __forceinline__ float sigmoid_fast(float x) { return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float trunc_exp_fast(float x) { return fast_ex2(1.4426950408889634f * fminf(fmaxf(x, -88.722839111f), 88.722839111f)); }
+
+// models/inr/meta_ngp.py:166-169 + models/encodings.py:141 (d / max(|d|, 1e-9), twice), then the SH basis.
+// The results feed fp16 GEMM operands, so the two normalisations use rsqrt.approx instead of sqrt + divide.
+__device__ __forceinline__ void sh16_fast(float x, float y, float z, float* sh) {
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+        const float inv = fminf(fast_rsqrt(x * x + y * y + z * z), 1e9f);
+        x *= inv; y *= inv; z *= inv;
+    }
+    sh16_poly(x, y, z, sh);
+}
+
+// TMEM -> registers, 32 consecutive columns of this thread's lane
+__device__ __forceinline__ void ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint4 pack8(const float* v) {
+    return make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+}
+
+// ---- shared-memory map of the weights (byte offsets from the weight block) ------------------------------
+// B-operand tiles, rows = output unit: t0 (64,E) t1 (64,64) hd (16,64) c0 (64,32) c1 (64,64) c2 (16,64);
+// hidden biases as packed halves (128 B each), head / output biases fp32 (64 B each).
+struct WMap { uint32_t t0, t1, hd, c0, c1, c2, bh_t0, bh_t1, bh_c0, bh_c1, b_hd, b_c2, end; };
+__host__ __device__ constexpr WMap wmap(int E) {
+    WMap m{};
+    uint32_t o = 0;
+    m.t0 = o; o += 64 * E * 2;
+    m.t1 = o; o += 64 * 64 * 2;
+    m.hd = o; o += 16 * 64 * 2;
+    m.c0 = o; o += 64 * 32 * 2;
+    m.c1 = o; o += 64 * 64 * 2;
+    m.c2 = o; o += 16 * 64 * 2;
+    m.bh_t0 = o; o += 128; m.bh_t1 = o; o += 128; m.bh_c0 = o; o += 128; m.bh_c1 = o; o += 128;
+    m.b_hd = o; o += 64; m.b_c2 = o; o += 64;
+    m.end = o;
+    return m;
+}
+
+// Colour-MLP input columns are permuted so that the SH block sits at a fixed position whatever G is:
+// A-tile column k' < 16 is SH component k', column 16 + j is geo feature j (j < G), the rest is zero.
+// The reference order is [geo(G), sh(16)] (models/inr/meta_ngp.py:186), so tile column k' reads source
+// column G + k' (k' < 16) or k' - 16.
+__device__ __forceinline__ int cin_src_col(int kp, int G) { return kp < 16 ? G + kp : (kp - 16 < G ? kp - 16 : -1); }
+
+template <int E>
+__device__ void stage_weights(const acn_field_weights& w, int G, uint32_t wb) {
+    constexpr WMap m = wmap(E);
+    auto stage = [&](uint32_t addr, int rows, int K, auto elem) {
+        const Tile t = mk_tile(addr, K);
+        for (int idx = threadIdx.x; idx < rows * (K / 8); idx += blockDim.x) {
+            const int n = idx / (K / 8), c = idx - n * (K / 8);
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = elem(n, c * 8 + j);
+            sts128(chunk_addr(t, n, c), pack8(v));
+        }
+    };
+    stage(wb + m.t0, 64, E, [&](int n, int k) { return __ldg(w.p[0] + (size_t)n * E + k); });
+    stage(wb + m.t1, 64, 64, [&](int n, int k) { return __ldg(w.p[2] + n * 64 + k); });
+    stage(wb + m.hd, 16, 64, [&](int n, int k) { return n < G ? __ldg(w.p[6] + n * 64 + k) : (n == 15 ? __ldg(w.p[4] + k) : 0.0f); });
+    stage(wb + m.c0, 64, 32, [&](int n, int k) { const int sc = cin_src_col(k, G); return sc >= 0 ? __ldg(w.p[8] + n * (G + 16) + sc) : 0.0f; });
+    stage(wb + m.c1, 64, 64, [&](int n, int k) { return __ldg(w.p[10] + n * 64 + k); });
+    stage(wb + m.c2, 16, 64, [&](int n, int k) { return n < 3 ? __ldg(w.p[12] + n * 64 + k) : 0.0f; });
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+        umma::sts_u32(wb + m.bh_t0 + 4 * i, pack_h2(__ldg(w.p[1] + 2 * i), __ldg(w.p[1] + 2 * i + 1)));
+        umma::sts_u32(wb + m.bh_t1 + 4 * i, pack_h2(__ldg(w.p[3] + 2 * i), __ldg(w.p[3] + 2 * i + 1)));
+        umma::sts_u32(wb + m.bh_c0 + 4 * i, pack_h2(__ldg(w.p[9] + 2 * i), __ldg(w.p[9] + 2 * i + 1)));
+        umma::sts_u32(wb + m.bh_c1 + 4 * i, pack_h2(__ldg(w.p[11] + 2 * i), __ldg(w.p[11] + 2 * i + 1)));
+    }
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) {
+        umma::sts_f32(wb + m.b_hd + 4 * i, i < G ? __ldg(w.p[7] + i) : (i == 15 ? __ldg(w.p[5]) : 0.0f));
+        umma::sts_f32(wb + m.b_c2 + 4 * i, i < 3 ? __ldg(w.p[13] + i) : 0.0f);
+    }
+}
+
+// ---- MMA issue (one elected lane, warp-uniform operands) ---------------------------------------------------
+__device__ __forceinline__ void mma_fwd(uint32_t d, const Tile& a, const Tile& w, int N, int K) {
+    const uint32_t id = umma::make_idesc_f16(128, N, false, false);
+    for (int ks = 0; ks < K / 16; ++ks) umma::mma_f16_ss(d, desc_k(a, ks), desc_k(w, ks), id, ks > 0);
+}
+// acc += A^T B over the tile's 128 points: A, B canonical tiles whose ROWS are points (both MN-major views)
+__device__ __forceinline__ void mma_over_points(uint32_t acc, const Tile& a, const Tile& b, int N) {
+    const uint32_t id = umma::make_idesc_f16(128, N, true, true);
+#pragma unroll
+    for (int ks = 0; ks < TM / 16; ++ks) umma::mma_f16_ss(acc, desc_mn(a, ks), desc_mn(b, ks), id, true);
+}
+// D = G W: G (128, Kout) K-major, W tile (Kout rows, N cols) viewed MN-major
+__device__ __forceinline__ void mma_dgrad(uint32_t d, const Tile& g, const Tile& w, int N, int Kout) {
+    const uint32_t id = umma::make_idesc_f16(128, N, false, true);
+    for (int ks = 0; ks < Kout / 16; ++ks) umma::mma_f16_ss(d, desc_k(g, ks), desc_mn(w, ks), id, ks > 0);
+}
+
+// Every thread of a group: my shared-memory writes are visible to the tensor core, my TMEM reads are ordered
+// before whatever the group's issuer launches next; then meet.
+__device__ __forceinline__ void group_sync(uint32_t bar_id, uint32_t nthreads) {
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    umma::bar_sync(bar_id, nthreads);
+}
+__device__ __forceinline__ void wait_done(uint32_t bar_addr, uint32_t& phase) {
+    umma::mbar_wait_a(bar_addr, phase);
+    phase ^= 1u;
+    umma::fence_after_sync();
+}
+
+// ---- epilogue pieces (thread = row) ------------------------------------------------------------------------
+// 32 accumulator columns [col0, col0+32) -> fp16 -> + bias, ReLU (packed halves) -> chunks col0/8.. of `dst`
+__device__ __forceinline__ void epi_hidden32(uint32_t tmem_d, int col0, uint32_t bias_addr, const Tile& dst, int row) {
+    float v[32];
+    ld32(tmem_d + col0, v);
+    uint4 b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) b[q] = lds128(bias_addr + col0 * 2 + q * 16);
+    umma::wait_ld();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = hfma2_relu(pack_h2(v[8 * q + 0], v[8 * q + 1]), HALF2_ONE, b[q].x);
+        o.y = hfma2_relu(pack_h2(v[8 * q + 2], v[8 * q + 3]), HALF2_ONE, b[q].y);
+        o.z = hfma2_relu(pack_h2(v[8 * q + 4], v[8 * q + 5]), HALF2_ONE, b[q].z);
+        o.w = hfma2_relu(pack_h2(v[8 * q + 6], v[8 * q + 7]), HALF2_ONE, b[q].w);
+        sts128(chunk_addr(dst, row, col0 / 8 + q), o);
+    }
+}
+// heads, geo part: accumulator columns 0..G-1 = geo, 15 = raw sigma -> cin chunks 2,3 ([geo(G) | 0]);
+// returns raw sigma (bias added)
+__device__ __forceinline__ float epi_heads_geo(uint32_t tmem_d, uint32_t b_hd_addr, int G, const Tile& cin, int row) {
+    float v[16];
+    umma::ld16(tmem_d, v);
+    float b[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 u = lds128(b_hd_addr + 16 * q);
+        b[4 * q] = __uint_as_float(u.x); b[4 * q + 1] = __uint_as_float(u.y); b[4 * q + 2] = __uint_as_float(u.z); b[4 * q + 3] = __uint_as_float(u.w);
+    }
+    umma::wait_ld();
+    const float sig_raw = v[15] + b[15];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = j < G ? v[j] + b[j] : 0.0f;
+    sts128(chunk_addr(cin, row, 2), pack8(v));
+    sts128(chunk_addr(cin, row, 3), pack8(v + 8));
+    return sig_raw;
+}
+// heads, direction part: SH(dir) -> cin chunks 0,1
+__device__ __forceinline__ void epi_heads_sh(const float* dir3, const Tile& cin, int row) {
+    float sh[16];
+    sh16_fast(dir3[0], dir3[1], dir3[2], sh);
+    sts128(chunk_addr(cin, row, 0), pack8(sh));
+    sts128(chunk_addr(cin, row, 1), pack8(sh + 8));
+}
+__device__ __forceinline__ void load_b_c2(uint32_t addr, float* b3) {
+    const uint4 u = lds128(addr);
+    b3[0] = __uint_as_float(u.x); b3[1] = __uint_as_float(u.y); b3[2] = __uint_as_float(u.z);
+}
+
+// Optional timeline for tools/field_trace.py: row 0 of warpgroup 0 in CTA 0 logs (SM clock << 8 | tag).
+struct Tracer {
+    long long* buf; int n, cap;
+    __device__ __forceinline__ void operator()(int tag) {
+        if (buf && n < cap) { buf[n++] = (clock64() << 8) | (long long)(tag & 0xff); }
+    }
+};
+constexpr int TRACE_CAP = 1024;
+
+// ======================================================================================================
+// forward: FWG warpgroups x 2 tiles
+// ======================================================================================================
+constexpr int FWG = 4;
+constexpr uint32_t FWD_TMEM_COLS = 512;          // FWG * 2 windows of 64 columns
+template <int E> struct FwdMap {
+    static constexpr uint32_t w = 0;
+    static constexpr uint32_t a = (wmap(E).end + 1023u) & ~1023u;           // FWG*2 A tiles of 16 KB
+    static constexpr uint32_t bars = a + FWG * 2 * 16384u;                   // FWG*2 mbarriers
+    static constexpr uint32_t tmem_ptr = bars + FWG * 2 * 8u;
+    static constexpr uint32_t bytes = tmem_ptr + 16u;
+};
+
+template <int E>
+__global__ void __launch_bounds__(FWG * 128, 1) k_field_fwd_mma(
+    const __half* __restrict__ enc, const float* __restrict__ dirs, int dstride, int dgroup, int64_t P, int G,
+    acn_field_weights w, float4* __restrict__ rgb_sigma, long long* __restrict__ trace)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    using M = FwdMap<E>;
+    constexpr WMap wm = wmap(E);
+    constexpr int EC = E / 8;
+    const uint32_t sb = umma::smem_u32(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    stage_weights<E>(w, G, sb + M::w);
+    if (tid == 0) {
+        for (int i = 0; i < FWG * 2; ++i) umma::mbar_init_a(sb + M::bars + 8 * i, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(reinterpret_cast<uint32_t*>(smem_raw + M::tmem_ptr), FWD_TMEM_COLS);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + M::tmem_ptr);
+
+    const int wg = warp >> 2, row = tid & (TM - 1);
+    const bool issuer_warp = (warp & 3) == 0;
+    const uint32_t bar_id = 1 + wg;
+    const Tile A0 = mk_tile(sb + M::a + (uint32_t)(wg * 2) * 16384u, 64), A1 = mk_tile(A0.a + 16384u, 64);
+    const uint32_t done0 = sb + M::bars + 8u * (wg * 2), done1 = done0 + 8u;
+    const uint32_t d0 = tmem_base + (uint32_t)(wg * 2) * 64u, d1 = d0 + 64u;                 // accumulator windows
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const Tile Wt0 = mk_tile(sb + wm.t0, E), Wt1 = mk_tile(sb + wm.t1, 64), Whd = mk_tile(sb + wm.hd, 64),
+               Wc0 = mk_tile(sb + wm.c0, 32), Wc1 = mk_tile(sb + wm.c1, 64), Wc2 = mk_tile(sb + wm.c2, 64);
+    const uint32_t bh_t0 = sb + wm.bh_t0, bh_t1 = sb + wm.bh_t1, bh_c0 = sb + wm.bh_c0, bh_c1 = sb + wm.bh_c1;
+
+    const int64_t ntiles = (P + TM - 1) / TM;
+    const int64_t npairs = (ntiles + 1) / 2;
+    const int64_t pair_stride = (int64_t)gridDim.x * FWG;
+    Tracer tr{ (trace && blockIdx.x == 0 && tid == 0) ? trace : nullptr, 0, TRACE_CAP };
+
+    // one elected lane of the warpgroup's first warp issues a layer and commits it to `done`
+    auto issue = [&](int step, const Tile& A, uint32_t d, uint32_t done) {
+        if (issuer_warp) {
+            if (umma::elect_one()) {
+                umma::fence_after_sync();
+                switch (step) {
+                    case 0: mma_fwd(d, A, Wt0, 64, E); break;
+                    case 1: mma_fwd(d, A, Wt1, 64, 64); break;
+                    case 2: mma_fwd(d, A, Whd, 16, 64); break;
+                    case 3: mma_fwd(d, A, Wc0, 64, 32); break;
+                    case 4: mma_fwd(d, A, Wc1, 64, 64); break;
+                    default: mma_fwd(d, A, Wc2, 16, 64); break;
+                }
+                umma::commit_a(done);
+            }
+            __syncwarp();
+        }
+    };
+    auto load_inputs = [&](int64_t tile, uint4* q, float* dir) {
+        const int64_t p = tile * TM + row;
+        const bool on = tile < ntiles && p < P;
+#pragma unroll
+        for (int c = 0; c < EC; ++c) q[c] = on ? __ldg(reinterpret_cast<const uint4*>(enc + p * E) + c) : make_uint4(0u, 0u, 0u, 0u);
+        dir[0] = 0.f; dir[1] = 0.f; dir[2] = 1.f;
+        if (on) { const float* dp = dir_of(dirs, dstride, dgroup, p); dir[0] = __ldg(dp); dir[1] = __ldg(dp + 1); dir[2] = __ldg(dp + 2); }
+    };
+
+    uint32_t ph0 = 0, ph1 = 0;
+    uint4 q0[EC], q1[EC];
+    float dir0[3], dir1[3];
+    int64_t pair = (int64_t)blockIdx.x * FWG + wg;
+    load_inputs(2 * pair, q0, dir0);
+    load_inputs(2 * pair + 1, q1, dir1);
+
+    for (; pair < npairs; pair += pair_stride) {
+        const int64_t p0 = (2 * pair) * TM + row, p1 = p0 + TM;
+        float cdir0[3] = { dir0[0], dir0[1], dir0[2] }, cdir1[3] = { dir1[0], dir1[1], dir1[2] };
+        tr(1);
+        // ---- stage both tiles' encoding rows, launch layer 1 of each ----
+#pragma unroll
+        for (int c = 0; c < EC; ++c) sts128(chunk_addr(A0, row, c), q0[c]);
+        group_sync(bar_id, 128); issue(0, A0, d0, done0);
+#pragma unroll
+        for (int c = 0; c < EC; ++c) sts128(chunk_addr(A1, row, c), q1[c]);
+        group_sync(bar_id, 128); issue(0, A1, d1, done1);
+        tr(2);
+        // prefetch the next pair's inputs; they land while this pair's layers run
+        load_inputs(2 * (pair + pair_stride), q0, dir0);
+        load_inputs(2 * (pair + pair_stride) + 1, q1, dir1);
+        // ---- trunk layer 1 -> 2 ----
+        wait_done(done0, ph0); tr(3);
+        epi_hidden32(d0 + lane_off, 0, bh_t0, A0, row); epi_hidden32(d0 + lane_off, 32, bh_t0, A0, row); tr(4);
+        group_sync(bar_id, 128); tr(5); issue(1, A0, d0, done0); tr(6);
+        wait_done(done1, ph1); tr(7);
+        epi_hidden32(d1 + lane_off, 0, bh_t0, A1, row); epi_hidden32(d1 + lane_off, 32, bh_t0, A1, row);
+        group_sync(bar_id, 128); issue(1, A1, d1, done1);
+        // ---- trunk layer 2 -> heads ----
+        wait_done(done0, ph0); tr(8);
+        epi_hidden32(d0 + lane_off, 0, bh_t1, A0, row); epi_hidden32(d0 + lane_off, 32, bh_t1, A0, row);
+        group_sync(bar_id, 128); issue(2, A0, d0, done0);
+        wait_done(done1, ph1);
+        epi_hidden32(d1 + lane_off, 0, bh_t1, A1, row); epi_hidden32(d1 + lane_off, 32, bh_t1, A1, row);
+        group_sync(bar_id, 128); issue(2, A1, d1, done1);
+        // ---- heads -> colour layer 1 ----
+        wait_done(done0, ph0); tr(9);
+        epi_heads_sh(cdir0, A0, row);
+        const float sigma0 = trunc_exp_fast(epi_heads_geo(d0 + lane_off, sb + wm.b_hd, G, A0, row));
+        group_sync(bar_id, 128); issue(3, A0, d0, done0);
+        wait_done(done1, ph1);
+        epi_heads_sh(cdir1, A1, row);
+        const float sigma1 = trunc_exp_fast(epi_heads_geo(d1 + lane_off, sb + wm.b_hd, G, A1, row));
+        group_sync(bar_id, 128); issue(3, A1, d1, done1);
+        // ---- colour layer 1 -> 2 ----
+        wait_done(done0, ph0); tr(10);
+        epi_hidden32(d0 + lane_off, 0, bh_c0, A0, row); epi_hidden32(d0 + lane_off, 32, bh_c0, A0, row);
+        group_sync(bar_id, 128); issue(4, A0, d0, done0);
+        wait_done(done1, ph1);
+        epi_hidden32(d1 + lane_off, 0, bh_c0, A1, row); epi_hidden32(d1 + lane_off, 32, bh_c0, A1, row);
+        group_sync(bar_id, 128); issue(4, A1, d1, done1);
+        // ---- colour layer 2 -> out ----
+        wait_done(done0, ph0); tr(11);
+        epi_hidden32(d0 + lane_off, 0, bh_c1, A0, row); epi_hidden32(d0 + lane_off, 32, bh_c1, A0, row);
+        group_sync(bar_id, 128); issue(5, A0, d0, done0);
+        wait_done(done1, ph1);
+        epi_hidden32(d1 + lane_off, 0, bh_c1, A1, row); epi_hidden32(d1 + lane_off, 32, bh_c1, A1, row);
+        group_sync(bar_id, 128); issue(5, A1, d1, done1);
+        // ---- outputs ----
+        float bc2[3];
+        load_b_c2(sb + wm.b_c2, bc2);
+        wait_done(done0, ph0); tr(12);
+        {
+            float v[16];
+            umma::ld16(d0 + lane_off, v);
+            umma::wait_ld();
+            if (p0 < P) rgb_sigma[p0] = make_float4(sigmoid_fast(v[0] + bc2[0]), sigmoid_fast(v[1] + bc2[1]), sigmoid_fast(v[2] + bc2[2]), sigma0);
+        }
+        wait_done(done1, ph1);
+        {
+            float v[16];
+            umma::ld16(d1 + lane_off, v);
+            umma::wait_ld();
+            if (p1 < P) rgb_sigma[p1] = make_float4(sigmoid_fast(v[0] + bc2[0]), sigmoid_fast(v[1] + bc2[1]), sigmoid_fast(v[2] + bc2[2]), sigma1);
+        }
+        tr(13);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_base, FWD_TMEM_COLS);
+}
+
+// ======================================================================================================
+// backward: 2 slots x 1 tile, 256 threads per slot (two threads per row)
+// ======================================================================================================
+constexpr int BNS = 2;
+// TMEM columns: per-slot D windows, then the persistent weight / bias gradient accumulators
+constexpr uint32_t COL_ACC0 = 128;
+constexpr uint32_t COL_WC1 = 128, COL_WT1 = 192, COL_WC0 = 256, COL_WT0 = 288, COL_WC2T = 352, COL_WHDT = 368;
+constexpr uint32_t COL_BC2 = 384, COL_BC1 = 400, COL_BC0 = 416, COL_BHD = 432, COL_BT1 = 448, COL_BT0 = 464;
+constexpr uint32_t COL_ACC1 = 480;
+constexpr uint32_t BWD_TMEM_COLS = 512;
+
+// per-slot tiles (byte offsets inside the slot block).  Activation / gradient tiles first: MN-major M=128 views
+// of 64- and 16-column tiles read up to 2 KB past the tile into whatever follows, which must be mapped.
+template <int E> struct SlotMap {
+    static constexpr uint32_t drr = 0, ghd = 4096, c2 = 8192, c1 = c2 + 16384, h2 = c1 + 16384, h1 = h2 + 16384;
+    static constexpr uint32_t xe = h1 + 16384, cin = xe + TM * E * 2, bytes = cin + TM * 32 * 2;
+};
+template <int E> struct BwdMap {
+    static constexpr uint32_t slots = 0;
+    static constexpr uint32_t ones = BNS * SlotMap<E>::bytes;
+    static constexpr uint32_t w = ones + 4096;
+    static constexpr uint32_t bars = (w + wmap(E).end + 127u) & ~127u;     // per slot: done_d, done_w
+    static constexpr uint32_t tmem_ptr = bars + BNS * 2 * 8u;
+    static constexpr uint32_t bytes = tmem_ptr + 16u;
+};
+
+// power-of-two loss scale from max |dL/dy|: max * scale in [2^9, 2^10)
+__device__ __forceinline__ float grad_scale_from_max(float mx) {
+    if (!(mx > 0.0f) || !(mx < 3.0e38f)) return 1.0f;
+    int e;
+    frexpf(mx, &e);                       // mx = m * 2^e, m in [0.5, 1)
+    e = 10 - e;
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    return ldexpf(1.0f, e);
+}
+
+__global__ void __launch_bounds__(256) k_absmax(const float4* __restrict__ x, int64_t n4, unsigned int* __restrict__ out) {
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = ld_stream_f4(x + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));   // fmaxf drops NaNs
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
+}
+
+// backward epilogue, part 1: 32 columns of D -> fp16 -> * [act > 0] in registers (the act tile is only read)
+__device__ __forceinline__ void epi_mask32_load(uint32_t tmem_d, int col0, const Tile& act, int row, uint4* o) {
+    float v[32];
+    ld32(tmem_d + col0, v);
+    uint4 a[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[q] = lds128(chunk_addr(act, row, col0 / 8 + q));
+    umma::wait_ld();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        o[q].x = hmask2(pack_h2(v[8 * q + 0], v[8 * q + 1]), a[q].x);
+        o[q].y = hmask2(pack_h2(v[8 * q + 2], v[8 * q + 3]), a[q].y);
+        o[q].z = hmask2(pack_h2(v[8 * q + 4], v[8 * q + 5]), a[q].z);
+        o[q].w = hmask2(pack_h2(v[8 * q + 6], v[8 * q + 7]), a[q].w);
+    }
+}
+// part 2 (after the weight-gradient MMAs that read the act tile have completed): overwrite it in place
+__device__ __forceinline__ void epi_mask32_store(const Tile& act, int row, int col0, const uint4* o) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sts128(chunk_addr(act, row, col0 / 8 + q), o[q]);
+}
+
+template <int E>
+__global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
+    const __half* __restrict__ enc, const float* __restrict__ dirs, int dstride, int dgroup, int64_t P, int G,
+    acn_field_weights w, const float4* __restrict__ d_rgb_sigma, const unsigned int* __restrict__ absmax_bits,
+    acn_field_grads g, float* __restrict__ d_enc)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    using M = BwdMap<E>;
+    using SM = SlotMap<E>;
+    constexpr WMap wm = wmap(E);
+    constexpr int EC = E / 8;            // 16-byte chunks per encoding row
+    constexpr int ECH = (EC + 1) / 2;    // ... handled by one of the row's two threads
+    const uint32_t sb = umma::smem_u32(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    stage_weights<E>(w, G, sb + M::w);
+    for (int r = tid; r < TM; r += blockDim.x) {
+        const uint4 one = make_uint4(HALF2_ONE, HALF2_ONE, HALF2_ONE, HALF2_ONE);
+        const Tile ones = mk_tile(sb + M::ones, 16);
+        sts128(chunk_addr(ones, r, 0), one);
+        sts128(chunk_addr(ones, r, 1), one);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < BNS * 2; ++i) umma::mbar_init_a(sb + M::bars + 8 * i, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(reinterpret_cast<uint32_t*>(smem_raw + M::tmem_ptr), BWD_TMEM_COLS);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + M::tmem_ptr);
+    if (warp < 4) {   // zero the persistent accumulators (lanes 32*warp.., every accumulator column)
+        for (uint32_t c = COL_ACC0; c < COL_ACC1; c += 16) umma::st16_zero(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+        umma::wait_st();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+
+    const int slot = warp >> 3;                    // 8 warps per slot
+    const int hcol = (warp >> 2) & 1;              // which half of a row's columns this thread owns
+    const int row = (warp & 3) * 32 + lane;
+    const bool issuer_warp = (warp & 7) == 0;
+    const uint32_t bar_id = 1 + slot;
+    const uint32_t sbase = sb + M::slots + (uint32_t)slot * SM::bytes;
+    const Tile Txe = mk_tile(sbase + SM::xe, E), Th1 = mk_tile(sbase + SM::h1, 64), Th2 = mk_tile(sbase + SM::h2, 64),
+               Tcin = mk_tile(sbase + SM::cin, 32), Tc1 = mk_tile(sbase + SM::c1, 64), Tc2 = mk_tile(sbase + SM::c2, 64),
+               Tdrr = mk_tile(sbase + SM::drr, 16), Tghd = mk_tile(sbase + SM::ghd, 16), Tones = mk_tile(sb + M::ones, 16);
+    const Tile Wt0 = mk_tile(sb + M::w + wm.t0, E), Wt1 = mk_tile(sb + M::w + wm.t1, 64), Whd = mk_tile(sb + M::w + wm.hd, 64),
+               Wc0 = mk_tile(sb + M::w + wm.c0, 32), Wc1 = mk_tile(sb + M::w + wm.c1, 64), Wc2 = mk_tile(sb + M::w + wm.c2, 64);
+    const uint32_t wb = sb + M::w;
+    const uint32_t done_d = sb + M::bars + 16u * slot, done_w = done_d + 8u;
+    const uint32_t dwin = tmem_base + (uint32_t)slot * 64u;
+    const uint32_t tmem_d = dwin + ((uint32_t)((warp & 3) * 32) << 16);
+    const int col0 = hcol * 32;
+
+    const int64_t ntiles = (P + TM - 1) / TM;
+    const int64_t tile_stride = (int64_t)gridDim.x * BNS;
+    const float scale = grad_scale_from_max(__uint_as_float(__ldg(absmax_bits)));
+    const float inv_scale = 1.0f / scale;
+    const bool want_denc = d_enc != nullptr;
+
+    auto issue = [&](int step) {
+        if (issuer_warp) {
+            if (umma::elect_one()) {
+                umma::fence_after_sync();
+                switch (step) {
+                    case 0: mma_fwd(dwin, Txe, Wt0, 64, E); break;
+                    case 1: mma_fwd(dwin, Th1, Wt1, 64, 64); break;
+                    case 2: mma_fwd(dwin, Th2, Whd, 16, 64); break;
+                    case 3: mma_fwd(dwin, Tcin, Wc0, 64, 32); break;
+                    case 4: mma_fwd(dwin, Tc1, Wc1, 64, 64); break;
+                    case 5: mma_fwd(dwin, Tc2, Wc2, 16, 64); break;
+                    case 6:   // colour out: D = drr W_c2 ; dW^T (in x out) = c2^T drr ; db = drr^T 1
+                        mma_dgrad(dwin, Tdrr, Wc2, 64, 16); umma::commit_a(done_d);
+                        mma_over_points(tmem_base + COL_WC2T, Tc2, Tdrr, 16);
+                        mma_over_points(tmem_base + COL_BC2, Tdrr, Tones, 16);
+                        break;
+                    case 7:   // colour layer 2: g lives in the c2 tile now; dW (out x in) = g^T c1
+                        mma_dgrad(dwin, Tc2, Wc1, 64, 64); umma::commit_a(done_d);
+                        mma_over_points(tmem_base + COL_WC1, Tc2, Tc1, 64);
+                        mma_over_points(tmem_base + COL_BC1, Tc2, Tones, 16);
+                        break;
+                    case 8:   // colour layer 1
+                        mma_dgrad(dwin, Tc1, Wc0, 32, 64); umma::commit_a(done_d);
+                        mma_over_points(tmem_base + COL_WC0, Tc1, Tcin, 32);
+                        mma_over_points(tmem_base + COL_BC0, Tc1, Tones, 16);
+                        break;
+                    case 9:   // heads: dW^T (in x out) = h2^T ghd
+                        mma_dgrad(dwin, Tghd, Whd, 64, 16); umma::commit_a(done_d);
+                        mma_over_points(tmem_base + COL_WHDT, Th2, Tghd, 16);
+                        mma_over_points(tmem_base + COL_BHD, Tghd, Tones, 16);
+                        break;
+                    case 10:  // trunk layer 2
+                        mma_dgrad(dwin, Th2, Wt1, 64, 64); umma::commit_a(done_d);
+                        mma_over_points(tmem_base + COL_WT1, Th2, Th1, 64);
+                        mma_over_points(tmem_base + COL_BT1, Th2, Tones, 16);
+                        break;
+                    default:  // trunk layer 1 (+ optional d enc)
+                        if (want_denc) mma_dgrad(dwin, Th1, Wt0, E, 64);
+                        umma::commit_a(done_d);
+                        mma_over_points(tmem_base + COL_WT0, Th1, Txe, E);
+                        mma_over_points(tmem_base + COL_BT0, Th1, Tones, 16);
+                        break;
+                }
+                umma::commit_a(step < 6 ? done_d : done_w);
+            }
+            __syncwarp();
+        }
+    };
+    // this thread's share of a tile's inputs: its encoding chunks (c = hcol, hcol+2, ..), dir (hcol 1), dy (hcol 0)
+    auto load_inputs = [&](int64_t tile, uint4* q, float* dir, float4& dy) {
+        const int64_t p = tile * TM + row;
+        const bool on = tile < ntiles && p < P;
+#pragma unroll
+        for (int j = 0; j < ECH; ++j) {
+            const int c = 2 * j + hcol;
+            q[j] = (on && c < EC) ? __ldg(reinterpret_cast<const uint4*>(enc + p * E) + c) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        dir[0] = 0.f; dir[1] = 0.f; dir[2] = 1.f;
+        dy = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) {
+            if (hcol) { const float* dp = dir_of(dirs, dstride, dgroup, p); dir[0] = __ldg(dp); dir[1] = __ldg(dp + 1); dir[2] = __ldg(dp + 2); }
+            else dy = __ldg(d_rgb_sigma + p);
+        }
+    };
+
+    uint32_t ph_d = 0, ph_w = 0;
+    uint4 encq[ECH];
+    float dir[3];
+    float4 dy;
+    int64_t tile = (int64_t)blockIdx.x * BNS + slot;
+    load_inputs(tile, encq, dir, dy);
+
+    for (; tile < ntiles; tile += tile_stride) {
+        const int64_t p = tile * TM + row;
+        const bool on = p < P;
+        // ---------------- forward recompute (same arithmetic as k_field_fwd_mma) ----------------
+#pragma unroll
+        for (int j = 0; j < ECH; ++j) if (2 * j + hcol < EC) sts128(chunk_addr(Txe, row, 2 * j + hcol), encq[j]);
+        group_sync(bar_id, 256); issue(0);
+        const float cdir[3] = { dir[0], dir[1], dir[2] };
+        const float4 cdy = dy;
+        load_inputs(tile + tile_stride, encq, dir, dy);        // prefetch: lands while this tile runs
+        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, wb + wm.bh_t0, Th1, row); group_sync(bar_id, 256); issue(1);
+        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, wb + wm.bh_t1, Th2, row); group_sync(bar_id, 256); issue(2);
+        wait_done(done_d, ph_d);
+        float sig_raw = 0.0f;
+        if (hcol) epi_heads_sh(cdir, Tcin, row);
+        else sig_raw = epi_heads_geo(tmem_d, wb + wm.b_hd, G, Tcin, row);
+        group_sync(bar_id, 256); issue(3);
+        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, wb + wm.bh_c0, Tc1, row); group_sync(bar_id, 256); issue(4);
+        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, wb + wm.bh_c1, Tc2, row); group_sync(bar_id, 256); issue(5);
+        wait_done(done_d, ph_d);
+        float d_sig = 0.0f;
+        if (!hcol) {   // output gradients (scaled): d rgb_raw = dy * y (1 - y); d sigma_raw = dy * exp(clamp(sigma_raw))
+            float v[16], drr[16], bc2[3];
+            umma::ld16(tmem_d, v);
+            load_b_c2(wb + wm.b_c2, bc2);
+            umma::wait_ld();
+            const float y0 = sigmoid_fast(v[0] + bc2[0]), y1 = sigmoid_fast(v[1] + bc2[1]), y2 = sigmoid_fast(v[2] + bc2[2]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) drr[j] = 0.0f;
+            drr[0] = cdy.x * scale * y0 * (1.0f - y0); drr[1] = cdy.y * scale * y1 * (1.0f - y1); drr[2] = cdy.z * scale * y2 * (1.0f - y2);
+            d_sig = cdy.w * scale * trunc_exp_fast(sig_raw);
+            sts128(chunk_addr(Tdrr, row, 0), pack8(drr));
+            sts128(chunk_addr(Tdrr, row, 1), pack8(drr + 8));
+        }
+        group_sync(bar_id, 256); issue(6);
+        // ---------------- backward ----------------
+        uint4 o[4];
+        wait_done(done_d, ph_d); epi_mask32_load(tmem_d, col0, Tc2, row, o); wait_done(done_w, ph_w); epi_mask32_store(Tc2, row, col0, o);
+        group_sync(bar_id, 256); issue(7);
+        wait_done(done_d, ph_d); epi_mask32_load(tmem_d, col0, Tc1, row, o); wait_done(done_w, ph_w); epi_mask32_store(Tc1, row, col0, o);
+        group_sync(bar_id, 256); issue(8);
+        wait_done(done_d, ph_d);
+        if (!hcol) {   // d cin = [d sh | d geo | 0] -> heads gradient row [d geo | 0 | d sigma_raw @15]
+            float v[16];
+            umma::ld16(tmem_d + 16, v);
+            umma::wait_ld();
+#pragma unroll
+            for (int j = 0; j < 15; ++j) v[j] = j < G ? v[j] : 0.0f;
+            v[15] = d_sig;
+            sts128(chunk_addr(Tghd, row, 0), pack8(v));
+            sts128(chunk_addr(Tghd, row, 1), pack8(v + 8));
+        }
+        wait_done(done_w, ph_w);
+        group_sync(bar_id, 256); issue(9);
+        wait_done(done_d, ph_d); epi_mask32_load(tmem_d, col0, Th2, row, o); wait_done(done_w, ph_w); epi_mask32_store(Th2, row, col0, o);
+        group_sync(bar_id, 256); issue(10);
+        wait_done(done_d, ph_d); epi_mask32_load(tmem_d, col0, Th1, row, o); wait_done(done_w, ph_w); epi_mask32_store(Th1, row, col0, o);
+        group_sync(bar_id, 256); issue(11);
+        wait_done(done_d, ph_d);
+        if (want_denc) {   // 16-column groups of d_enc alternate between the row's two threads
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c0 = 16 * (2 * j + hcol);
+                if (c0 < E) {
+                    float v[16];
+                    umma::ld16(tmem_d + c0, v);
+                    umma::wait_ld();
+                    if (on) {
+                        float4* dst = reinterpret_cast<float4*>(d_enc + p * E + c0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            dst[k] = make_float4(v[4 * k] * inv_scale, v[4 * k + 1] * inv_scale, v[4 * k + 2] * inv_scale, v[4 * k + 3] * inv_scale);
+                    }
+                }
+            }
+        }
+        wait_done(done_w, ph_w);     // the xe / h1 tiles are free again only now
+    }
+
+    // ---------------- add the TMEM-resident weight gradients to global memory ----------------
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    if (warp < 4) {
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int t = tid;     // TMEM lane
+        // accumulator(lane t, column n) -> dst[n * ld_col] for n < nvalid (dst null: skip)
+        auto flush = [&](uint32_t col, int ncols, float* dst, int ld_col, int nvalid) {
+            for (int q = 0; q < ncols / 16; ++q) {
+                float v[16];
+                umma::ld16(tmem_row + col + q * 16, v);     // warp-collective: every lane loads
+                umma::wait_ld();
+                if (dst) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = q * 16 + j;
+                        if (n < nvalid && v[j] != 0.0f) atomicAdd(dst + (size_t)n * ld_col, v[j] * inv_scale);
+                    }
+                }
+            }
+        };
+        auto at = [&](float* base, bool valid, int off) { return (base && valid) ? base + off : (float*)nullptr; };
+        const int CIN = G + 16;
+        // dW (out x in) accumulators: lane = output unit, column = input unit
+        flush(COL_WC1, 64, at(g.p[10], t < 64, t * 64), 1, 64);
+        flush(COL_WT1, 64, at(g.p[2], t < 64, t * 64), 1, 64);
+        flush(COL_WT0, 64, at(g.p[0], t < 64, t * E), 1, E);
+        // colour layer 1: tile column k' is source column cin_src_col(k'): SH block, then geo block
+        flush(COL_WC0, 16, at(g.p[8], t < 64, t * CIN + G), 1, 16);
+        flush(COL_WC0 + 16, 16, at(g.p[8], t < 64, t * CIN), 1, G);
+        // dW^T (in x out) accumulators: lane = input unit, column = output unit
+        flush(COL_WC2T, 16, at(g.p[12], t < 64, t), 64, 3);
+        {
+            float v[16];
+            umma::ld16(tmem_row + COL_WHDT, v);
+            umma::wait_ld();
+            if (t < 64) {
+#pragma unroll
+                for (int j = 0; j < 15; ++j) if (g.p[6] && j < G && v[j] != 0.0f) atomicAdd(g.p[6] + j * 64 + t, v[j] * inv_scale);
+                if (g.p[4] && v[15] != 0.0f) atomicAdd(g.p[4] + t, v[15] * inv_scale);
+            }
+        }
+        // bias gradients: every column of a G^T 1 accumulator holds the same sum; take column 0
+        flush(COL_BC2, 16, at(g.p[13], t < 3, t), 1, 1);
+        flush(COL_BC1, 16, at(g.p[11], t < 64, t), 1, 1);
+        flush(COL_BC0, 16, at(g.p[9], t < 64, t), 1, 1);
+        flush(COL_BHD, 16, t == 15 ? g.p[5] : at(g.p[7], t < G, t), 1, 1);
+        flush(COL_BT1, 16, at(g.p[3], t < 64, t), 1, 1);
+        flush(COL_BT0, 16, at(g.p[1], t < 64, t), 1, 1);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_base, BWD_TMEM_COLS);
+}
+
+int check_dims(const char* fn, int enc_dtype, int E, int H, int G, int C, const void* enc) {
+    ACN_REQUIRE(enc_dtype == ACN_F16, ACN_EUNSUPPORTED, "%s(f16): the tensor-core path takes fp16 encodings (cast in the caller)", fn);
+    ACN_REQUIRE(H == 64 && C == 64, ACN_EUNSUPPORTED, "%s(f16): hidden widths must be 64 (got H=%d, C=%d)", fn, H, C);
+    ACN_REQUIRE(E == 16 || E == 32 || E == 48 || E == 64, ACN_EUNSUPPORTED, "%s(f16): encoding width %d not in {16,32,48,64}", fn, E);
+    ACN_REQUIRE(G >= 1 && G <= 15, ACN_EUNSUPPORTED, "%s(f16): geo_feat_dim %d outside [1,15]", fn, G);
+    ACN_REQUIRE(((uintptr_t)enc & 15) == 0, ACN_EINVAL, "%s(f16): enc must be 16-byte aligned", fn);
+    return ACN_OK;
+}
+
+long long* g_field_trace = nullptr;   // set by acn_debug_field_trace for the following forward launches
+
+template <int E>
+int launch_fwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride, int dirs_group, int64_t P, int G,
+               const acn_field_weights* w, float* rgb_sigma, cudaStream_t st) {
+    constexpr uint32_t smem = FwdMap<E>::bytes;
+    ACN_REQUIRE((int)smem <= ctx->max_smem_optin, ACN_EUNSUPPORTED, "acn_field_fwd(f16): needs %u B shared memory", smem);
+    const int64_t npairs = ((P + TM - 1) / TM + 1) / 2;
+    int64_t grid = (npairs + FWG - 1) / FWG;
+    if (grid > ctx->sm_count) grid = ctx->sm_count;
+    ACN_CUDA(cudaFuncSetAttribute(k_field_fwd_mma<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_field_fwd_mma<E><<<(int)grid, FWG * 128, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
+                                                            (float4*)rgb_sigma, g_field_trace);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
+
+template <int E>
+int launch_bwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride, int dirs_group, int64_t P, int G,
+               const acn_field_weights* w, const float* d_rgb_sigma, const unsigned int* absmax, const acn_field_grads* g,
+               float* d_enc, cudaStream_t st) {
+    constexpr uint32_t smem = BwdMap<E>::bytes;
+    ACN_REQUIRE((int)smem <= ctx->max_smem_optin, ACN_EUNSUPPORTED, "acn_field_bwd(f16): needs %u B shared memory", smem);
+    const int64_t ntiles = (P + TM - 1) / TM;
+    int64_t grid = (ntiles + BNS - 1) / BNS;
+    if (grid > ctx->sm_count) grid = ctx->sm_count;
+    ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_field_bwd_mma<E><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
+                                                            (const float4*)d_rgb_sigma, absmax, *g, d_enc);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
+
+}  // namespace
+
+extern "C" int acn_debug_field_trace(acn_ctx* ctx, long long* trace_or_null) {
+    ACN_CHECK_CTX(ctx);
+    g_field_trace = trace_or_null;
+    return ACN_OK;
+}
+
+int acn_field_fwd_tc(acn_ctx* ctx, const void* enc, int enc_dtype, const float* dirs, int dirs_stride, int dirs_group,
+                     int64_t P, int E, int H, int G, int C, const acn_field_weights* w, float* rgb_sigma, cudaStream_t st) {
+    int rc = check_dims("acn_field_fwd", enc_dtype, E, H, G, C, enc);
+    if (rc) return rc;
+    switch (E) {
+        case 16: return launch_fwd<16>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, rgb_sigma, st);
+        case 32: return launch_fwd<32>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, rgb_sigma, st);
+        case 48: return launch_fwd<48>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, rgb_sigma, st);
+        default: return launch_fwd<64>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, rgb_sigma, st);
+    }
+}
+
+int acn_field_bwd_tc(acn_ctx* ctx, const void* enc, int enc_dtype, const float* dirs, int dirs_stride, int dirs_group,
+                     int64_t P, int E, int H, int G, int C, const acn_field_weights* w, const float* d_rgb_sigma,
+                     const acn_field_grads* g, float* d_enc, cudaStream_t st) {
+    int rc = check_dims("acn_field_bwd", enc_dtype, E, H, G, C, enc);
+    if (rc) return rc;
+    ACN_REQUIRE(((uintptr_t)d_enc & 15) == 0, ACN_EINVAL, "acn_field_bwd(f16): d_enc must be 16-byte aligned");
+    // loss scale: max |dL/dy| over the batch -> one word of context scratch (a ring, so calls in flight on
+    // different streams do not share a word)
+    unsigned int* slot = acn_scratch_word(ctx);
+    ACN_REQUIRE(slot != nullptr, ACN_ECUDA, "acn_field_bwd(f16): no context scratch");
+    ACN_CUDA(cudaMemsetAsync(slot, 0, sizeof(unsigned int), st));
+    k_absmax<<<acn_grid_1d(P, 256 * 8, (int64_t)ctx->sm_count * 8), 256, 0, st>>>((const float4*)d_rgb_sigma, P, slot);
+    ACN_CHECK_LAUNCH();
+    switch (E) {
+        case 16: return launch_bwd<16>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, st);
+        case 32: return launch_bwd<32>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, st);
+        case 48: return launch_bwd<48>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, st);
+        default: return launch_bwd<64>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, st);
+    }
+}

@@ -1,0 +1,89 @@
+// Diagnostics: one tcgen05 tile GEMM D(128,N) = A(128,K) * W(N,K)^T (fp16 in, fp32 out) that validates, on real
+// hardware, the shared-memory / instruction descriptors and the barrier protocol the fused field-MLP kernels
+// (field_mma.cu) are built on.  Not on any product path.
+#include "field_common.cuh"
+#include "field_internal.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int TM = 128;           // points per tile = MMA M
+constexpr uint32_t A_SBO = 1024;  // A tile: 8 K-chunks of 128 B per 8-row group (K up to 64)
+constexpr uint32_t TMEM_COLS = 64;
+
+// Issue one layer: D(128 x N) = A(128 x K) * W(N x K)^T, K a multiple of 16.  Single thread.
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, const uint8_t* a_tile, const uint8_t* w_tile, int N, int K, uint64_t* bar) {
+    const uint32_t idesc = umma::make_idesc_f16(128, N);
+    const uint32_t a_addr = umma::smem_u32(a_tile), w_addr = umma::smem_u32(w_tile);
+    const uint32_t w_sbo = (uint32_t)(K / 8) * 128u;
+    for (int ks = 0; ks < K / 16; ++ks) {
+        uint64_t da = umma::make_desc(a_addr + ks * 256, 128, A_SBO);
+        uint64_t db = umma::make_desc(w_addr + ks * 256, 128, w_sbo);
+        umma::mma_f16_ss(tmem_d, da, db, idesc, ks > 0);
+    }
+    umma::commit(bar);
+}
+
+// all threads: publish smem writes to the async proxy, order TMEM reads, then let thread 0 issue
+__device__ __forceinline__ void run_layer(uint32_t tmem_d, const uint8_t* a_tile, const uint8_t* w_tile, int N, int K,
+                                          uint64_t* bar, uint32_t& phase) {
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        umma::fence_after_sync();
+        issue_layer(tmem_d, a_tile, w_tile, N, K, bar);
+    }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1u;
+    umma::fence_after_sync();
+}
+
+// D(128,N) = A(128,K) * W(N,K)^T on one CTA: validates the descriptors on real hardware.
+__global__ void __launch_bounds__(TM) k_debug_umma(const __half* __restrict__ a, const __half* __restrict__ w, int N, int K,
+                                                   float* __restrict__ d)
+{
+    __shared__ __align__(128) uint8_t a_tile[TM * 64 * 2];
+    __shared__ __align__(128) uint8_t w_tile[64 * 64 * 2];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_ptr;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int c = 0; c < K / 8; ++c)
+        *reinterpret_cast<uint4*>(a_tile + umma::chunk_off(tid, c, A_SBO)) = *reinterpret_cast<const uint4*>(a + (size_t)tid * K + c * 8);
+    const uint32_t w_sbo = (uint32_t)(K / 8) * 128u;
+    for (int idx = tid; idx < N * (K / 8); idx += TM) {
+        int n = idx / (K / 8), c = idx - n * (K / 8);
+        *reinterpret_cast<uint4*>(w_tile + umma::chunk_off(n, c, w_sbo)) = *reinterpret_cast<const uint4*>(w + (size_t)n * K + c * 8);
+    }
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_mbar_init(); }
+    if (warp == 0) umma::tmem_alloc(&tmem_ptr, TMEM_COLS);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = tmem_ptr;
+    uint32_t phase = 0;
+    run_layer(tmem_base, a_tile, w_tile, N, K, &bar, phase);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int q = 0; q < N / 16; ++q) {
+        float v[16];
+        umma::ld16(tmem_row + q * 16, v);
+        umma::wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) d[(size_t)tid * N + q * 16 + j] = v[j];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace
+
+extern "C" int acn_debug_umma_gemm(acn_ctx* ctx, const void* a_f16, const void* w_f16, int N, int K, float* d, acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    ACN_REQUIRE(a_f16 && w_f16 && d, ACN_EINVAL, "acn_debug_umma_gemm: null buffer");
+    ACN_REQUIRE((N == 16 || N == 32 || N == 64) && (K == 16 || K == 32 || K == 64), ACN_EUNSUPPORTED,
+                "acn_debug_umma_gemm: N,K must be in {16,32,64}");
+    k_debug_umma<<<1, TM, 0, (cudaStream_t)stream>>>((const __half*)a_f16, (const __half*)w_f16, N, K, d);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}

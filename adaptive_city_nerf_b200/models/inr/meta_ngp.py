@@ -9,7 +9,7 @@ state_dicts and MAML-style callers work unchanged:
 
 `forward` -- the call the renderer makes for every sample -- runs as two kernels: hash encode
 (csrc/hashgrid.cu) and the fused trunk + heads + SH + colour MLP (csrc/field_fp32.cu, or the
-tcgen05 kernel csrc/field_tc.cu under torch.autocast(float16), which is how the reference selects
+tcgen05 kernel csrc/field_mma.cu under torch.autocast(float16), which is how the reference selects
 its fp16 path).  The occupancy-grid renderer (nerfacc, default off, partly broken upstream --
 SURVEY note A) is out of scope: `use_occ=True` raises."""
 from __future__ import annotations

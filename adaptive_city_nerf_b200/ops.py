@@ -210,6 +210,9 @@ def field_fwd(enc: Tensor, dirs: Tensor, dirs_stride: int, dirs_group: int, ws: 
     P = enc.shape[0]
     E, H, G, C = _field_dims(ws)
     dev = enc.device
+    if half and enc.dtype != torch.float16:
+        enc = enc.half()                       # the tensor-core kernels take fp16 encodings
+    enc = enc.contiguous()
     out = torch.empty(P, 4, dtype=torch.float32, device=dev)
     st = pack_weights(ws)
     check(lib().acn_field_fwd(ctx(dev), ptr(enc), _dt(enc), ptr(dirs), dirs_stride, dirs_group, P, E, H, G, C, C_.byref(st),
@@ -222,6 +225,9 @@ def field_bwd(enc: Tensor, dirs: Tensor, dirs_stride: int, dirs_group: int, ws: 
     P = enc.shape[0]
     E, H, G, C = _field_dims(ws)
     dev = enc.device
+    if half and enc.dtype != torch.float16:
+        enc = enc.half()
+    enc = enc.contiguous()
     grads: List[Optional[Tensor]] = [torch.zeros_like(w, dtype=torch.float32) if n else None for w, n in zip(ws, need)]
     # d_enc stays fp32 even for an fp16 encoding: per-sample gradients of a mean loss over 2^18 rays are
     # ~1e-9 and would flush to zero in fp16 (the reference needs GradScaler for the same reason)
@@ -402,3 +408,11 @@ def debug_umma_gemm(a: Tensor, w: Tensor) -> Tensor:
     d = torch.empty(128, w.shape[0], dtype=torch.float32, device=a.device)
     check(lib().acn_debug_umma_gemm(ctx(a.device), ptr(a), ptr(w), w.shape[0], a.shape[1], ptr(d), stream(a.device)))
     return d
+
+
+def debug_field_trace(buf: Optional[Tensor]) -> None:
+    """Arm (int64 CUDA tensor of 1024 words) or disarm (None) the forward-MLP timeline (acn_debug_field_trace)."""
+    dev = buf.device if buf is not None else torch.device("cuda", torch.cuda.current_device())
+    if buf is not None:
+        assert buf.dtype == torch.int64 and buf.numel() >= 1024 and buf.is_contiguous()
+    check(lib().acn_debug_field_trace(ctx(dev), ptr(buf)))

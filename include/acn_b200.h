@@ -190,6 +190,11 @@ int acn_debug_umma_raw(acn_ctx*, const void* a16, int rows_a, int cols_a, const 
                        uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, int ksteps, int ncols, float* out,
                        acn_stream);
 
+/* Timeline of the fused forward MLP kernel: when `trace` (device, 1024 int64) is non-NULL, CTA 0 of the
+ * following acn_field_fwd(ACN_F16) launches logs (SM clock << 8 | tag) pairs from row 0 of its first
+ * warpgroup (tools/field_trace.py decodes them).  NULL switches it off. */
+int acn_debug_field_trace(acn_ctx*, long long* trace_or_null);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -64,25 +64,87 @@ def _rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-300))
 
 
-@pytest.mark.parametrize("P", [1, 128, 129, 1000, 300_007])
-def test_field_bf16_backward_matches_fp32(P):
-    """tcgen05 backward (bf16 operands, fp32 accumulate, TMEM-resident weight gradients) vs the fp32
-    SIMT backward on the same inputs.  Bar: relative L2 <= 1e-2 per tensor."""
+def _emulate_fp16_field(enc16, dirs, ws, dy):
+    """Torch restatement of csrc/field_mma.cu's arithmetic (the reference's autocast path, models/metamodule/
+    metamodule.py:150-155): fp16 operands, exact products with wide accumulation (fp64 here, fp32 in TMEM), GEMM
+    result rounded to fp16 before the fp16 bias + ReLU; gradient tiles are fp16 carrying a power-of-two scale;
+    the ReLU masks are those of THIS forward.  Returns (rgb_sigma, 14 grads, d_enc)."""
+    from adaptive_city_nerf_b200 import ops
+    D = torch.float64
+    h = lambda t: t.half().to(D)                                   # round to fp16, continue exactly
+    W = [w.to(D) for w in ws]
+    wt0, bt0, wt1, bt1, wsg, bsg, wge, bge, wc0, bc0, wc1, bc1, wc2, bc2 = W
+    G = wge.shape[0]
+    x0 = enc16.to(D)
+    hid = lambda x, w, b: h(torch.relu(h(x @ h(w).t()) + h(b)))   # fma.rn.relu.f16x2: one rounding of the exact sum
+    h1 = hid(x0, wt0, bt0)
+    h2 = hid(h1, wt1, bt1)
+    sig_raw = (h2 @ h(wsg).t()).float().to(D) + bsg               # head accumulators stay fp32
+    geo = (h2 @ h(wge).t()).float().to(D) + bge
+    sh = ops.sh16(dirs).to(D)
+    cin = torch.cat([h(geo), h(sh)], dim=1)
+    c1 = hid(cin, wc0, bc0)
+    c2 = hid(c1, wc1, bc1)
+    y = torch.sigmoid((c2 @ h(wc2).t()).float().to(D) + bc2)
+    e = torch.exp(sig_raw.clamp(-88.722839111, 88.722839111))
+    out = torch.cat([y, e], dim=1).float()
+    # ---- backward ----
+    mx = float(dy.abs().max())
+    scale = 1.0 if not (mx > 0) else 2.0 ** (10 - int(np.frexp(mx)[1]))
+    dyd = dy.to(D)
+    drr = h(dyd[:, :3] * scale * y * (1 - y))
+    dsg = h(dyd[:, 3:] * scale * e)
+    g = [None] * 14
+    g[12], g[13] = drr.t() @ c2, drr.sum(0)
+    gc2 = h(drr @ h(wc2)) * (c2 > 0)
+    g[10], g[11] = gc2.t() @ c1, gc2.sum(0)
+    gc1 = h(gc2 @ h(wc1)) * (c1 > 0)
+    g[8], g[9] = gc1.t() @ cin, gc1.sum(0)
+    dgeo = h((gc1 @ h(wc0))[:, :G])
+    g[6], g[7] = dgeo.t() @ h2, dgeo.sum(0)
+    g[4], g[5] = dsg.t() @ h2, dsg.sum(0)
+    gh2 = h(dgeo @ h(wge) + dsg @ h(wsg)) * (h2 > 0)
+    g[2], g[3] = gh2.t() @ h1, gh2.sum(0)
+    gh1 = h(gh2 @ h(wt1)) * (h1 > 0)
+    g[0], g[1] = gh1.t() @ x0, gh1.sum(0)
+    d_enc = gh1 @ h(wt0)
+    return out, [(t / scale).float().reshape(w.shape) for t, w in zip(g, ws)], (d_enc / scale).float()
+
+
+@pytest.mark.parametrize("P,mag", [(1, 1.0), (128, 1e-7), (129, 1.0), (1000, 3e4), (300_007, 1e-7)])
+def test_field_fp16_backward(P, mag):
+    """tcgen05 backward (fp16 operands with a power-of-two loss scale, fp32 accumulate, TMEM-resident weight
+    gradients) against (a) a torch restatement of the same arithmetic -- tight: relative L2 <= 3e-3 per tensor --
+    and (b) the fp32 SIMT backward.  For (b) the gradients of a ReLU network evaluated in fp16 and in fp32 differ
+    mostly through the ~0.1 % of units whose pre-activation changes sign under fp16 rounding; with independent
+    random dL/dy that alone gives ~1-2 % relative L2 (measured with plain torch as well), hence the 4e-2 bar here
+    while the coherent-gradient case (tests/test_gpu_render.py) keeps 2e-2."""
     from adaptive_city_nerf_b200 import ops
     sd = synth.make_expert_params(5, log2T=4)
     wt = [cu(w) for w in synth.expert_weight_list(sd)]
     gen = torch.Generator(device="cuda").manual_seed(P)
     enc = (torch.rand(P, 32, device="cuda", generator=gen) - 0.5).half()
     dirs = torch.randn(P, 3, device="cuda", generator=gen)
-    # realistic magnitudes: gradients of a mean loss are tiny (this is what rules fp16 gradient tiles out)
-    dy = torch.randn(P, 4, device="cuda", generator=gen) * 1e-7
+    # per-sample gradients of a mean loss are tiny (1e-7), GradScaler-scaled ones are huge (3e4): both must work
+    dy = torch.randn(P, 4, device="cuda", generator=gen) * mag
     dy[::5] = 0.0
-    g32, de32 = ops.field_bwd(enc, dirs, 3, 1, wt, False, dy, True, [True] * 14)
     g16, de16 = ops.field_bwd(enc, dirs, 3, 1, wt, True, dy, True, [True] * 14)
-    for key, a, b in zip(synth.EXPERT_KEYS, g16, g32):
+    y_em, g_em, de_em = _emulate_fp16_field(enc, dirs, wt, dy)
+    y16 = ops.field_fwd(enc, dirs, 3, 1, wt, half=True)
+    # same arithmetic up to the accumulation order: a hidden unit lands on the other side of an fp16 rounding
+    # boundary now and then (one ulp), everything else agrees to MUFU precision
+    assert (y16[:, :3] - y_em[:, :3]).abs().max() < 1e-3 and (y16[:, :3] - y_em[:, :3]).abs().mean() < 1e-5
+    rel_s = (y16[:, 3] - y_em[:, 3]).abs() / (y_em[:, 3].abs() + 1e-6)
+    assert rel_s.max() < 5e-3 and rel_s.mean() < 1e-5
+    for key, a, b in zip(synth.EXPERT_KEYS, g16, g_em):
         assert torch.isfinite(a).all(), key
-        assert _rel_l2(a, b) < 1e-2, (key, _rel_l2(a, b))
-    assert _rel_l2(de16, de32) < 1e-2
+        assert _rel_l2(a, b) < 3e-3, ("vs fp16 restatement", key, _rel_l2(a, b))
+    assert _rel_l2(de16, de_em) < 3e-3
+    if P >= 1000:            # a statistical statement: with a few hundred points one flipped unit moves it by percents
+        g32, de32 = ops.field_bwd(enc, dirs, 3, 1, wt, False, dy, True, [True] * 14)
+        for key, a, b in zip(synth.EXPERT_KEYS, g16, g32):
+            assert _rel_l2(a, b) < 4e-2, ("vs fp32", key, _rel_l2(a, b))
+        assert _rel_l2(de16, de32) < 4e-2
     # skipping the input gradient (inner-loop steps) must not change the weight gradients
     g16b, none = ops.field_bwd(enc, dirs, 3, 1, wt, True, dy, False, [True] * 14)
     assert none is None
@@ -95,3 +157,19 @@ def test_field_bf16_backward_matches_fp32(P):
     for a, b, n in zip(g16c, g16, need):
         if n:
             assert _rel_l2(a, b) < 1e-5
+
+
+def test_field_fp16_backward_zero_and_nonfinite_gradients():
+    """All-zero dL/dy gives exactly zero gradients; the loss scale ignores NaN/inf entries (it falls back to 1)."""
+    from adaptive_city_nerf_b200 import ops
+    sd = synth.make_expert_params(5, log2T=4)
+    wt = [cu(w) for w in synth.expert_weight_list(sd)]
+    P = 777
+    enc = (torch.rand(P, 32, device="cuda") - 0.5).half()
+    dirs = torch.randn(P, 3, device="cuda")
+    g, de = ops.field_bwd(enc, dirs, 3, 1, wt, True, torch.zeros(P, 4, device="cuda"), True, [True] * 14)
+    assert all(float(t.abs().max()) == 0.0 for t in g) and float(de.abs().max()) == 0.0
+    dy = torch.randn(P, 4, device="cuda")
+    dy[3, 1] = float("inf")
+    g, de = ops.field_bwd(enc, dirs, 3, 1, wt, True, dy, True, [True] * 14)
+    assert not torch.isfinite(g[12]).all()          # the bad sample poisons what it touches, as in the reference

@@ -1,0 +1,32 @@
+"""Timeline of the fused forward MLP kernel: row 0 of warpgroup 0 in CTA 0 (run on the GPU box)."""
+import sys
+from pathlib import Path
+import torch
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests" / "golden")); sys.path.insert(0, str(ROOT / "tests"))
+import synth
+from helpers import cu
+from adaptive_city_nerf_b200 import ops
+
+P, S = 1 << 21, 64
+sd = synth.make_expert_params(5, log2T=4)
+wt = [cu(w) for w in synth.expert_weight_list(sd)]
+enc = (torch.rand(P, 32, device="cuda") - 0.5).half()
+rays = torch.randn(P // S, 8, device="cuda")
+ops.field_fwd(enc, rays[:, 3:], 8, S, wt, True)
+buf = torch.zeros(1024, dtype=torch.int64, device="cuda")
+ops.debug_field_trace(buf)
+ops.field_fwd(enc, rays[:, 3:], 8, S, wt, True)
+torch.cuda.synchronize()
+ops.debug_field_trace(None)
+b = buf.cpu().tolist()
+ev = [(v >> 8, v & 0xff) for v in b if v]
+names = {1: "pair start", 2: "both tiles staged + layer 1 issued", 3: "t0 done-wait returned (tile A)", 4: "t0 epilogue done (A)",
+         5: "group barrier passed", 6: "layer issued", 7: "done-wait returned (tile B)", 8: "t1 done-wait returned (A)",
+         9: "heads done-wait returned (A)", 10: "c0 done-wait returned (A)", 11: "c1 done-wait returned (A)",
+         12: "c2 done-wait returned (A)", 13: "pair finished"}
+t0 = ev[0][0]
+prev = t0
+for t, tag in ev[:140]:
+    print(f"  t={t - t0:7d} (+{t - prev:5d})  {tag:2d} {names.get(tag, '')}")
+    prev = t

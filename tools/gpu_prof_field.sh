@@ -1,0 +1,6 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 300 python tools/prof_field.py --small > gpurun_out/prof_field_small.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_field_ -c 2 -f -o gpurun_out/field_prof python tools/prof_field.py --small > gpurun_out/ncu_field.log 2>&1
+echo "ncu rc=$?"; tail -3 gpurun_out/ncu_field.log
