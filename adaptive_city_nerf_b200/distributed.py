@@ -1,0 +1,247 @@
+"""One process per GPU: the three ways the rendering hot path shards across a B200 box.
+
+The reference is single-process (nerf_runner.py:52-56); its only collective is the AABB / count all-reduce of the
+offline mask script (scripts/create_clusters.py:898-932).  Everything here is therefore new capability, laid over
+`torch.distributed` (NCCL over NVLink 5 / NVSwitch on the GPUs, gloo in the CPU tests):
+
+* expert sharding (`ExpertShardedContainer`): rank r owns experts [r*m, (r+1)*m).  Rays stay data parallel on their
+  home rank (clip, sample, route, composite); routed samples travel to the owner of their expert(s) with ONE
+  variable-size all-to-all each way -- 24 B/sample out ([xyz, dir]), 16 B/sample back ([rgb, sigma]) -- and the
+  backward mirrors it (dL/d[rgb, sigma] out, nothing back: positions carry no gradient).  Overlap samples inside
+  `boundary_margin` go to every owner with non-zero weight and are blended at home in expert order, exactly like
+  models/inr/meta_container.py:306-337.
+* per-expert meta-training (`active_module=cid`): experts share nothing but the background head and the global
+  gradient clip (pipelines/offline_stage/meta_core.py:181-190) -> `sharded_clip_grad_norm_` (one scalar all-reduce).
+* single-expert data parallel: `allreduce_grads_` sums the hash-table gradient (64 MiB at T = 2^19) and the 13 715
+  MLP gradients (flattened into one message).
+
+Only host logic lives here; all arithmetic on samples is in the CUDA kernels behind `ops`."""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import ops
+
+
+# --------------------------------------------------------------------------------------------- exchange primitives
+def exchange_counts(send_counts: Tensor, group=None) -> Tensor:
+    """send_counts (world, m) int64 on any device: rows I send to each (rank, local expert) -> the (world, m) counts
+    each rank sends ME.  One tiny all-to-all; the only host-visible quantity of a routed step."""
+    world = dist.get_world_size(group)
+    assert send_counts.dim() == 2 and send_counts.shape[0] == world
+    recv = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv, send_counts.contiguous(), group=group)
+    return recv
+
+
+class _AllToAllRows(torch.autograd.Function):
+    """Variable-size row exchange y = all_to_all(x) with autograd: the backward is the same exchange with the
+    splits swapped.  x: (sum(send_splits), C) grouped by destination rank."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, send_splits: List[int], recv_splits: List[int], group):
+        x = x.contiguous()
+        y = x.new_empty((sum(recv_splits),) + tuple(x.shape[1:]))
+        dist.all_to_all_single(y, x, output_split_sizes=recv_splits, input_split_sizes=send_splits, group=group)
+        ctx.splits, ctx.group = (send_splits, recv_splits), group
+        return y
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        send_splits, recv_splits = ctx.splits
+        g = g.contiguous()
+        gx = g.new_empty((sum(send_splits),) + tuple(g.shape[1:]))
+        dist.all_to_all_single(gx, g, output_split_sizes=send_splits, input_split_sizes=recv_splits, group=ctx.group)
+        return gx, None, None, None
+
+
+def all_to_all_rows(x: Tensor, send_splits: Sequence[int], recv_splits: Sequence[int], group=None) -> Tensor:
+    return _AllToAllRows.apply(x, [int(v) for v in send_splits], [int(v) for v in recv_splits], group)
+
+
+def expert_owner_layout(K: int, world: int) -> int:
+    """Experts per rank m for a contiguous block layout (rank r owns experts [r*m, (r+1)*m)); K must divide."""
+    if K % world != 0:
+        raise ValueError(f"{K} experts do not shard evenly over {world} ranks")
+    return K // world
+
+
+def regroup_by_expert(recv_counts: Tensor) -> Tuple[List[List[Tuple[int, int]]], List[int]]:
+    """recv_counts (world, m): the receive buffer is ordered by source rank, then local expert.  -> for each local
+    expert the list of (start, length) segments that belong to it, and the per-source-rank totals (recv splits)."""
+    world, m = recv_counts.shape
+    rc = recv_counts.tolist()
+    segs: List[List[Tuple[int, int]]] = [[] for _ in range(m)]
+    pos = 0
+    for r in range(world):
+        for e in range(m):
+            n = int(rc[r][e])
+            if n:
+                segs[e].append((pos, n))
+            pos += n
+    return segs, [int(sum(row)) for row in rc]
+
+
+def routed_exchange(xd: Tensor, counts: Tensor, local_fields, group=None) -> Tensor:
+    """The sample round trip of one routed step.
+
+    xd (total, C>=6): routed rows grouped by GLOBAL expert id (expert-major, as `ops.bucket_points` writes them);
+    counts (K,) host int tensor: rows per expert; local_fields: m callables, local_fields[e](rows (M,C)) -> (M,4),
+    the experts this rank owns.  -> y (total, 4) in the order of `xd`, differentiable w.r.t. whatever the owners'
+    fields depend on (their gradients arrive through the backward all-to-all)."""
+    world = dist.get_world_size(group)
+    K = counts.numel()
+    m = expert_owner_layout(K, world)
+    assert len(local_fields) == m
+    send_counts = counts.reshape(world, m).to(torch.int64)
+    dev_counts = send_counts.to(xd.device) if dist.get_backend(group) == "nccl" else send_counts
+    recv_counts = exchange_counts(dev_counts, group).cpu()
+    send_splits = [int(v) for v in send_counts.sum(1).tolist()]
+    segs, recv_splits = regroup_by_expert(recv_counts)
+    with torch.no_grad():                                   # positions / directions carry no gradient
+        rows = all_to_all_rows(xd, send_splits, recv_splits, group)
+    M = rows.shape[0]
+    if m == 1 and M:
+        y_recv = local_fields[0](rows).float()
+    else:
+        y_recv = rows.new_zeros((M, 4), dtype=torch.float32)
+        pieces, index = [], []
+        for e, field in enumerate(local_fields):
+            if segs[e]:
+                idx = torch.cat([torch.arange(s, s + n, device=rows.device) for s, n in segs[e]])
+                pieces.append(field(rows[idx]).float())
+                index.append(idx)
+        if pieces:
+            y_recv = y_recv.index_copy(0, torch.cat(index), torch.cat(pieces))
+    # The return trip's backward is a collective: every rank must run it, also one that received nothing or owns no
+    # trainable parameter -- give autograd a reason to.
+    if torch.is_grad_enabled() and not y_recv.requires_grad:
+        y_recv = y_recv.detach().requires_grad_()
+    return all_to_all_rows(y_recv, recv_splits, send_splits, group)
+
+
+# --------------------------------------------------------------------------------------------- expert sharding
+class ExpertShardedContainer(torch.nn.Module):
+    """A `MetaContainer` whose experts live on different ranks.  Built from a full container description; every
+    rank constructs the same object and then drops the experts it does not own (`shard_()`), so checkpoints keep the
+    reference's `submodules.{k}.*` keys on the owner.
+
+        forward(x (N,>=6)) -> (N,4)          the routed, blended field (meta_container.py:275-343)
+        render via nerfs.ray_rendering.render_rays(model, rays, ..., active_module=None) as usual
+    """
+
+    def __init__(self, container, group=None):
+        super().__init__()
+        self.inner = container
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.K = len(container.submodules)
+        self.m = expert_owner_layout(self.K, self.world)
+        self.local_ids = list(range(self.rank * self.m, (self.rank + 1) * self.m))
+        self.use_bg_nerf = container.use_bg_nerf
+        self.use_occ = False
+
+    def shard_(self):
+        """Free the experts this rank does not own (their slots stay in the ModuleList as empty modules)."""
+        for k in range(self.K):
+            if k not in self.local_ids:
+                self.inner.submodules[k] = torch.nn.Identity()
+        return self
+
+    @property
+    def submodules(self):
+        return self.inner.submodules
+
+    def background_color(self, d: Tensor) -> Tensor:
+        return self.inner.background_color(d)
+
+    def local_parameters(self) -> List[torch.nn.Parameter]:
+        return [p for k in self.local_ids for p in self.inner.submodules[k].parameters()]
+
+    def shared_parameters(self) -> List[torch.nn.Parameter]:
+        return [p for n, p in self.inner.named_parameters() if not n.startswith("submodules.")]
+
+    def forward(self, x: Tensor, params=None, active_module: Optional[int] = None) -> Tensor:
+        if active_module is not None:
+            if active_module not in self.local_ids:
+                raise RuntimeError(f"expert {active_module} is owned by rank {active_module // self.m}, not {self.rank}")
+            return self.inner(x, params=params, active_module=active_module)
+        c = self.inner
+        N = x.shape[0]
+        id6 = ops.dev_f32(x[:, :6], "points")
+        sub_params = c._sub_params(params)
+        with torch.no_grad():
+            w, hard, counts = ops.route_points(id6, c.centroids, 2 if c.cluster_2d else 3, c.boundary_margin, want_counts=True)
+            cnt = counts.cpu().to(torch.int64)
+            offsets = torch.zeros(self.K, dtype=torch.int32)
+            offsets[1:] = torch.cumsum(cnt, 0)[:-1].to(torch.int32)
+            sel, xd, wsel = ops.bucket_points(id6, w, hard, self.K, offsets.to(x.device), int(cnt.sum()))
+        fields = [(lambda rows, k=k: c.submodules[k](rows, params=sub_params[k])) for k in self.local_ids]
+        y = routed_exchange(xd, cnt, fields, self.group)
+        out = torch.zeros(N, 4, dtype=torch.float32, device=x.device) + 0.0 * y.sum()   # ties y in even if unused
+        off = offsets.tolist()
+        for k in range(self.K):                               # blend in expert order, like the reference
+            n = int(cnt[k])
+            if n:
+                sl = slice(off[k], off[k] + n)
+                out = ops.BlendFn.apply(out, y[sl], wsel[sl], sel[sl])
+        return out
+
+
+# --------------------------------------------------------------------------------------------- gradient plumbing
+def allreduce_grads_(params: Iterable[torch.nn.Parameter], group=None, average: bool = True, flat_below: int = 1 << 20) -> None:
+    """Sum (or average) .grad over the ranks: tensors below `flat_below` elements travel as ONE flattened message
+    (the 14 MLP tensors of an expert are 13 715 floats), large ones (the hash table) on their own."""
+    world = dist.get_world_size(group)
+    small, big = [], []
+    for p in params:
+        if p.grad is None:
+            continue
+        (small if p.grad.numel() < flat_below else big).append(p.grad)
+    for g in big:
+        dist.all_reduce(g, group=group)
+    if small:
+        flat = torch.cat([g.reshape(-1) for g in small])
+        dist.all_reduce(flat, group=group)
+        off = 0
+        for g in small:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+    if average and world > 1:
+        for g in big + small:
+            g.div_(world)
+
+
+def sharded_clip_grad_norm_(owned: Iterable[torch.nn.Parameter], shared: Iterable[torch.nn.Parameter], max_norm: float,
+                            group=None) -> Tensor:
+    """torch.nn.utils.clip_grad_norm_ over ALL experts' parameters when each rank only holds its own
+    (pipelines/offline_stage/meta_core.py:181-190 clips one global norm): `owned` gradients exist on exactly one rank,
+    `shared` ones (background head) are replicated and already all-reduced.  One scalar all-reduce."""
+    owned = [p for p in owned if p.grad is not None]
+    shared = [p for p in shared if p.grad is not None]
+    ref = (owned + shared)[0].grad if (owned or shared) else torch.zeros(())
+    sq = ref.new_zeros((), dtype=torch.float32)
+    for p in owned:
+        sq = sq + p.grad.float().pow(2).sum()
+    dist.all_reduce(sq, group=group)
+    for p in shared:
+        sq = sq + p.grad.float().pow(2).sum()
+    total = sq.sqrt()
+    coef = (max_norm / (total + 1e-6)).clamp(max=1.0)
+    for p in owned + shared:
+        p.grad.mul_(coef.to(p.grad.dtype))
+    return total
+
+
+def reduce_expert_aabbs(mins: Tensor, maxs: Tensor, counts: Tensor, group=None) -> Tuple[Tensor, Tensor, Tensor]:
+    """Combine the per-expert sample AABBs / counts of rank-strided mask generation
+    (scripts/create_clusters.py:898-904, 928-932): MIN / MAX / SUM all-reduces of (K,3), (K,3), (K,)."""
+    dist.all_reduce(mins, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=group)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return mins, maxs, counts

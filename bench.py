@@ -199,6 +199,7 @@ def run_ours(args):
     import torch.distributed as dist
     from adaptive_city_nerf_b200 import _lib
     from adaptive_city_nerf_b200.nerfs.ray_rendering import render_rays
+    from adaptive_city_nerf_b200.distributed import allreduce_grads_
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -218,8 +219,6 @@ def run_ours(args):
                             {"params": groups["sigma"]["params"], "lr": 2e-3},
                             {"params": groups["color"]["params"], "lr": 2e-3}], eps=1e-15, fused=True)
     params = [p for g in opt.param_groups for p in g["params"]]
-    mlp_params = [p for p in params if p.numel() < (1 << 20)]
-    table = [p for p in params if p.numel() >= (1 << 20)]
 
     def step(r, g):
         with torch.autocast("cuda", dtype=torch.float16):
@@ -228,16 +227,7 @@ def run_ours(args):
         opt.zero_grad(set_to_none=True)
         loss.backward()
         if world > 1:
-            for t in table:
-                dist.all_reduce(t.grad)
-            flat = torch.cat([p.grad.reshape(-1) for p in mlp_params])
-            dist.all_reduce(flat)
-            off = 0
-            for p in mlp_params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
-            for p in params:
-                p.grad.div_(world)
+            allreduce_grads_(params, average=True)
         opt.step()
         return loss
 
