@@ -41,6 +41,11 @@ ENC_BWD_BYTES = 2 * 1024 + 128                 # read-modify-write of the same 1
 FIELD_FWD_FLOP = 26880
 FIELD_BWD_FLOP = 2 * 26880                     # dgrad + wgrad (the recompute is not counted)
 COMPOSITE_BYTES = 24
+# DRAM bytes per launch at this workload (dram__bytes_read.sum + dram__bytes_write.sum, one `ncu --set full` capture:
+# profiles/r01_v1_stages_ncu_full_summary.csv).  The 64 MiB table is L2-resident, so the gather / scatter traffic that
+# the algorithmic byte count describes is served by L2, not HBM.
+NCU_DRAM_BYTES = {"acn_hashgrid_fwd_rays": 1.40e9, "acn_hashgrid_bwd_rays": 2.39e9, "acn_field_fwd": 1.33e9,
+                  "acn_field_bwd": 3.45e9, "acn_composite_fwd": 0.374e9, "acn_composite_bwd": 0.574e9}
 
 
 def peaks():
@@ -274,6 +279,24 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t)
 
+    # ---- render throughput: forward only, eval mode (no jitter), no autograd ----
+    model.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        for _ in range(2):
+            render_rays(model, rays, ray_samples=SAMPLES, active_module=0, chunk=1 << 30)
+        sync()
+        e0.record()
+        for _ in range(args.steps):
+            render_rays(model, rays, ray_samples=SAMPLES, active_module=0, chunk=1 << 30)
+        e1.record()
+        sync()
+    ms_render = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_render], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_render = float(t)
+    model.train()
+
     if rank == 0:
         pk = peaks()
         P = N_RAYS * SAMPLES
@@ -295,7 +318,8 @@ def run_ours(args):
         top = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches"])
         tk = kernels[top]
         roof = {"kernel": top, "bound": tk["bound"], "achieved": tk["achieved"], "peak": pk[tk["bound"]], "unit": tk["unit"],
-                "frac": tk["frac"], "traffic": None, "peak_source": pk["src"], "avg_ms": tk["avg_ms"]}
+                "frac": tk["frac"], "traffic": NCU_DRAM_BYTES.get(top), "traffic_unit": "DRAM bytes per launch (ncu)",
+                "algorithmic": work[top][1], "peak_source": pk["src"], "avg_ms": tk["avg_ms"]}
         n_cpu, ts, cores = time_cpu(steps=2, warmup=1) if world == 1 else (0, [], 0)
         out = {
             "metric": "train rays/s", "value": world * N_RAYS * args.steps / (ms * 1e-3), "unit": "rays/s",
@@ -310,6 +334,9 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(rays_h.numel() * 4 + gt_h.numel() * 4), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "last_loss": loss_val},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "kernels": kernels,
+            "render": {"metric": "render samples/s", "value": world * N_RAYS * SAMPLES * args.steps / (ms_render * 1e-3),
+                       "unit": "samples/s", "ms_per_batch": ms_render / args.steps,
+                       "what": "render_rays forward only (eval, no_grad, autocast fp16), same expert and rays"},
         }
         if ts:
             out["cpu_baseline"] = {"value": n_cpu / min(ts), "unit": "rays/s", "cores": cores, "kind": "port",
