@@ -1,7 +1,9 @@
 // Stage 3 under autocast(fp16): the expert's field MLPs on tcgen05 tensor cores, forward and backward.
 //
-// Reference numerics: models/metamodule/metamodule.py:150-155 under torch.autocast -- fp16 GEMM operands,
-// fp32 accumulation, the GEMM result rounded to fp16 before the bias add + ReLU.
+// Reference numerics: models/metamodule/metamodule.py:150-155 under torch.autocast -- fp16 GEMM operands, fp32
+// accumulation, bias + ReLU, fp16 activations into the next GEMM.  Here the (fp16-rounded) bias is added inside the
+// fp32 accumulator by one extra K step, so a hidden activation is fp16(relu(sum + b)): one rounding where the
+// reference has two (GEMM result, then the next layer's input cast).
 //
 // Both kernels are persistent (one CTA per SM).  Tiles are 128 points (MMA M = 128); a point owns row r of
 // every activation tile in shared memory (canonical no-swizzle UMMA layout, umma.cuh) and lane r of a TMEM
@@ -47,12 +49,25 @@ using umma::sts128;
 constexpr int TM = 128;                 // points per tile = MMA M
 constexpr uint32_t HALF2_ONE = 0x3C003C00u;
 
-struct Tile { uint32_t a; uint32_t rg; };   // shared-space byte address + row-group stride (= cols/8 * 128 B)
-__device__ __forceinline__ Tile mk_tile(uint32_t addr, int cols) { return Tile{ addr, (uint32_t)(cols / 8) * 128u }; }
+// A canonical tile: shared-space byte address >> 4 (all of shared memory fits the descriptor's 14-bit field) and
+// row-group stride (= cols/8 * 128 B).  Descriptors are built as `a16 + immediate` -- ONE uniform add per operand.
+// This matters: with umma::make_desc's mask-and-shift per MMA the issuing thread spent ~90 cycles per tcgen05.mma
+// on the uniform datapath and the kernels were bound by MMA ISSUE (26 / 140 MMAs per tile), not by the tensor pipe.
+struct Tile { uint32_t a16; uint32_t rg; };
+__device__ __forceinline__ Tile mk_tile(uint32_t addr, int cols) { return Tile{ addr >> 4, (uint32_t)(cols / 8) * 128u }; }
 
-__device__ __forceinline__ uint64_t desc_k(const Tile& t, int ks) { return umma::make_desc(t.a + ks * 256, 128, t.rg); }
-__device__ __forceinline__ uint64_t desc_mn(const Tile& t, int ks) { return umma::make_desc(t.a + ks * 2 * t.rg, t.rg, 128); }
-__device__ __forceinline__ uint32_t chunk_addr(const Tile& t, int r, int c) { return t.a + umma::chunk_off(r, c, t.rg); }
+// smem descriptor (cute::UMMA::SmemDescriptor): [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1
+__device__ __forceinline__ uint64_t desc_k(const Tile& t, int ks) {          // K-major: LBO = 128, SBO = RG, +256 B per K step
+    const uint32_t lo = t.a16 + (uint32_t)ks * 16u + (8u << 16);
+    const uint32_t hi = (t.rg >> 4) | (1u << 14);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint64_t desc_mn(const Tile& t, int ks) {         // MN-major: LBO = RG, SBO = 128, +2*RG per K step
+    const uint32_t lo = t.a16 + (uint32_t)ks * (t.rg >> 3) + ((t.rg >> 4) << 16);
+    const uint32_t hi = 8u | (1u << 14);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint32_t chunk_addr(const Tile& t, int r, int c) { return (t.a16 << 4) + umma::chunk_off(r, c, t.rg); }
 
 // ---- small PTX helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
@@ -60,10 +75,10 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
 }
-// relu(a * b + c) on packed halves, single rounding
-__device__ __forceinline__ uint32_t hfma2_relu(uint32_t a, uint32_t b, uint32_t c) {
+// two fp32 -> packed halves with ReLU, one instruction
+__device__ __forceinline__ uint32_t pack_relu_h2(float lo, float hi) {
     uint32_t d;
-    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
 }
 // g * [act > 0] on packed halves
@@ -111,9 +126,12 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 }
 
 // ---- shared-memory map of the weights (byte offsets from the weight block) ------------------------------
-// B-operand tiles, rows = output unit: t0 (64,E) t1 (64,64) hd (16,64) c0 (64,32) c1 (64,64) c2 (16,64);
-// hidden biases as packed halves (128 B each), head / output biases fp32 (64 B each).
-struct WMap { uint32_t t0, t1, hd, c0, c1, c2, bh_t0, bh_t1, bh_c0, bh_c1, b_hd, b_c2, end; };
+// B-operand tiles, rows = output unit: t0 (64,E) t1 (64,64) hd (16,64) c0 (64,32) c1 (64,64) c2 (16,64).
+// Hidden-layer biases are B operands too: (64,16) tiles whose column 0 holds the bias, multiplied by a constant A
+// tile `one` (128,16) whose column 0 is 1 -- one extra K=16 MMA per hidden layer adds the bias inside the fp32
+// accumulator, so the epilogue is a single cvt.rn.relu.f16x2.f32 per two activations.  Head / output biases stay
+// fp32 (64 B each) and are added in the epilogue.
+struct WMap { uint32_t t0, t1, hd, c0, c1, c2, bt_t0, bt_t1, bt_c0, bt_c1, one, b_hd, b_c2, end; };
 __host__ __device__ constexpr WMap wmap(int E) {
     WMap m{};
     uint32_t o = 0;
@@ -123,7 +141,8 @@ __host__ __device__ constexpr WMap wmap(int E) {
     m.c0 = o; o += 64 * 32 * 2;
     m.c1 = o; o += 64 * 64 * 2;
     m.c2 = o; o += 16 * 64 * 2;
-    m.bh_t0 = o; o += 128; m.bh_t1 = o; o += 128; m.bh_c0 = o; o += 128; m.bh_c1 = o; o += 128;
+    m.bt_t0 = o; o += 2048; m.bt_t1 = o; o += 2048; m.bt_c0 = o; o += 2048; m.bt_c1 = o; o += 2048;
+    m.one = o; o += 4096;
     m.b_hd = o; o += 64; m.b_c2 = o; o += 64;
     m.end = o;
     return m;
@@ -154,12 +173,11 @@ __device__ void stage_weights(const acn_field_weights& w, int G, uint32_t wb) {
     stage(wb + m.c0, 64, 32, [&](int n, int k) { const int sc = cin_src_col(k, G); return sc >= 0 ? __ldg(w.p[8] + n * (G + 16) + sc) : 0.0f; });
     stage(wb + m.c1, 64, 64, [&](int n, int k) { return __ldg(w.p[10] + n * 64 + k); });
     stage(wb + m.c2, 16, 64, [&](int n, int k) { return n < 3 ? __ldg(w.p[12] + n * 64 + k) : 0.0f; });
-    for (int i = threadIdx.x; i < 32; i += blockDim.x) {
-        umma::sts_u32(wb + m.bh_t0 + 4 * i, pack_h2(__ldg(w.p[1] + 2 * i), __ldg(w.p[1] + 2 * i + 1)));
-        umma::sts_u32(wb + m.bh_t1 + 4 * i, pack_h2(__ldg(w.p[3] + 2 * i), __ldg(w.p[3] + 2 * i + 1)));
-        umma::sts_u32(wb + m.bh_c0 + 4 * i, pack_h2(__ldg(w.p[9] + 2 * i), __ldg(w.p[9] + 2 * i + 1)));
-        umma::sts_u32(wb + m.bh_c1 + 4 * i, pack_h2(__ldg(w.p[11] + 2 * i), __ldg(w.p[11] + 2 * i + 1)));
-    }
+    stage(wb + m.bt_t0, 64, 16, [&](int n, int k) { return k == 0 ? __ldg(w.p[1] + n) : 0.0f; });
+    stage(wb + m.bt_t1, 64, 16, [&](int n, int k) { return k == 0 ? __ldg(w.p[3] + n) : 0.0f; });
+    stage(wb + m.bt_c0, 64, 16, [&](int n, int k) { return k == 0 ? __ldg(w.p[9] + n) : 0.0f; });
+    stage(wb + m.bt_c1, 64, 16, [&](int n, int k) { return k == 0 ? __ldg(w.p[11] + n) : 0.0f; });
+    stage(wb + m.one, 128, 16, [&](int, int k) { return k == 0 ? 1.0f : 0.0f; });
     for (int i = threadIdx.x; i < 16; i += blockDim.x) {
         umma::sts_f32(wb + m.b_hd + 4 * i, i < G ? __ldg(w.p[7] + i) : (i == 15 ? __ldg(w.p[5]) : 0.0f));
         umma::sts_f32(wb + m.b_c2 + 4 * i, i < 3 ? __ldg(w.p[13] + i) : 0.0f);
@@ -170,6 +188,12 @@ __device__ void stage_weights(const acn_field_weights& w, int G, uint32_t wb) {
 __device__ __forceinline__ void mma_fwd(uint32_t d, const Tile& a, const Tile& w, int N, int K) {
     const uint32_t id = umma::make_idesc_f16(128, N, false, false);
     for (int ks = 0; ks < K / 16; ++ks) umma::mma_f16_ss(d, desc_k(a, ks), desc_k(w, ks), id, ks > 0);
+}
+// hidden layer: D = A W^T + 1 b^T (the bias rides in as one more K step: `one` x `bias tile`)
+__device__ __forceinline__ void mma_fwd_bias(uint32_t d, const Tile& a, const Tile& w, const Tile& one, const Tile& bias, int K) {
+    const uint32_t id = umma::make_idesc_f16(128, 64, false, false);
+    for (int ks = 0; ks < K / 16; ++ks) umma::mma_f16_ss(d, desc_k(a, ks), desc_k(w, ks), id, ks > 0);
+    umma::mma_f16_ss(d, desc_k(one, 0), desc_k(bias, 0), id, true);
 }
 // acc += A^T B over the tile's 128 points: A, B canonical tiles whose ROWS are points (both MN-major views)
 __device__ __forceinline__ void mma_over_points(uint32_t acc, const Tile& a, const Tile& b, int N) {
@@ -197,21 +221,18 @@ __device__ __forceinline__ void wait_done(uint32_t bar_addr, uint32_t& phase) {
 }
 
 // ---- epilogue pieces (thread = row) ------------------------------------------------------------------------
-// 32 accumulator columns [col0, col0+32) -> fp16 -> + bias, ReLU (packed halves) -> chunks col0/8.. of `dst`
-__device__ __forceinline__ void epi_hidden32(uint32_t tmem_d, int col0, uint32_t bias_addr, const Tile& dst, int row) {
+// 32 accumulator columns [col0, col0+32) (bias already inside) -> ReLU -> fp16 -> chunks col0/8.. of `dst`
+__device__ __forceinline__ void epi_hidden32(uint32_t tmem_d, int col0, const Tile& dst, int row) {
     float v[32];
     ld32(tmem_d + col0, v);
-    uint4 b[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) b[q] = lds128(bias_addr + col0 * 2 + q * 16);
     umma::wait_ld();
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint4 o;
-        o.x = hfma2_relu(pack_h2(v[8 * q + 0], v[8 * q + 1]), HALF2_ONE, b[q].x);
-        o.y = hfma2_relu(pack_h2(v[8 * q + 2], v[8 * q + 3]), HALF2_ONE, b[q].y);
-        o.z = hfma2_relu(pack_h2(v[8 * q + 4], v[8 * q + 5]), HALF2_ONE, b[q].z);
-        o.w = hfma2_relu(pack_h2(v[8 * q + 6], v[8 * q + 7]), HALF2_ONE, b[q].w);
+        o.x = pack_relu_h2(v[8 * q + 0], v[8 * q + 1]);
+        o.y = pack_relu_h2(v[8 * q + 2], v[8 * q + 3]);
+        o.z = pack_relu_h2(v[8 * q + 4], v[8 * q + 5]);
+        o.w = pack_relu_h2(v[8 * q + 6], v[8 * q + 7]);
         sts128(chunk_addr(dst, row, col0 / 8 + q), o);
     }
 }
@@ -247,28 +268,62 @@ __device__ __forceinline__ void load_b_c2(uint32_t addr, float* b3) {
 }
 
 // Optional timeline for tools/field_trace.py: row 0 of warpgroup 0 in CTA 0 logs (SM clock << 8 | tag).
-struct Tracer {
+template <bool ON> struct Tracer {
     long long* buf; int n, cap;
     __device__ __forceinline__ void operator()(int tag) {
-        if (buf && n < cap) { buf[n++] = (clock64() << 8) | (long long)(tag & 0xff); }
+        if constexpr (ON) { if (buf && n < cap) { buf[n++] = (clock64() << 8) | (long long)(tag & 0xff); } }
     }
 };
 constexpr int TRACE_CAP = 1024;
 
 // ======================================================================================================
-// forward: FWG warpgroups x 2 tiles
+// forward: FWG warpgroups x 1 tile, activations chained through TENSOR MEMORY
 // ======================================================================================================
+// With both operands in shared memory an M=128, N=64, K=16 MMA fetches 4 KB of A and 2 KB of B per 32 tensor-pipe
+// cycles -- 192 B/cycle against a 128 B/cycle shared-memory port that the epilogue's stores also use.  The first
+// versions of this kernel were bound exactly there (tools/field_trace.py: a layer's MMAs took ~3x their tensor
+// time).  So the activations never touch shared memory: the epilogue writes the next layer's A operand back into
+// tensor memory (tcgen05.st, two halves per 32-bit column) and the MMA reads it from there
+// (tcgen05.mma [d], [a_tmem], b_desc); only the 2 KB weight slice comes from shared memory.
+//
+// TMEM map, 128 columns per tile = two halves H0 = [0,64), H1 = [64,128).  An accumulator is read by its owner
+// thread and the fp16 activations are written back over its first 32 columns (read cols 0..31 -> write 0..15, read
+// 32..63 -> write 16..31); the next layer accumulates into the OTHER half:
+//     enc -> H1[0,E/2) | L0: D=H0 | h1 -> H0[0,32) | L1: D=H1 | h2 -> H1[0,32) | heads: D=H0[0,16) | cin -> H0[0,16)
+//     | L3: D=H1 | c1 -> H1[0,32) | L4: D=H0 | c2 -> H0[0,32) | out: D=H1[0,16)
 constexpr int FWG = 4;
-constexpr uint32_t FWD_TMEM_COLS = 512;          // FWG * 2 windows of 64 columns
+constexpr uint32_t FWD_TMEM_COLS = 512;          // FWG windows of 128 columns
 template <int E> struct FwdMap {
     static constexpr uint32_t w = 0;
-    static constexpr uint32_t a = (wmap(E).end + 1023u) & ~1023u;           // FWG*2 A tiles of 16 KB
-    static constexpr uint32_t bars = a + FWG * 2 * 16384u;                   // FWG*2 mbarriers
-    static constexpr uint32_t tmem_ptr = bars + FWG * 2 * 8u;
+    static constexpr uint32_t bars = (wmap(E).end + 127u) & ~127u;          // FWG mbarriers
+    static constexpr uint32_t tmem_ptr = bars + FWG * 8u;
     static constexpr uint32_t bytes = tmem_ptr + 16u;
 };
 
-template <int E>
+// TS-mode layer: D = A[tmem] W^T (+ 1 b^T through the shared-memory `one` tile when `bias` is given)
+__device__ __forceinline__ void mma_layer_ts(uint32_t d, uint32_t a_tmem, const Tile& w, int N, int K, const Tile* one, const Tile* bias) {
+    const uint32_t id = umma::make_idesc_f16(128, N, false, false);
+    for (int ks = 0; ks < K / 16; ++ks) umma::mma_f16_ts(d, a_tmem + ks * 8, desc_k(w, ks), id, ks > 0);
+    if (bias) umma::mma_f16_ss(d, desc_k(*one, 0), desc_k(*bias, 0), id, true);
+}
+
+// hidden-layer epilogue in tensor memory: 64 fp32 accumulator columns at `acc` (bias inside) -> ReLU -> 64 halves
+// written back over columns [0,32) of the same window
+__device__ __forceinline__ void epi_hidden_tmem(uint32_t acc) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float v[32];
+        ld32(acc + h * 32, v);
+        umma::wait_ld();
+        uint32_t r[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = pack_relu_h2(v[2 * j], v[2 * j + 1]);
+        umma::st16(acc + h * 16, r);
+    }
+    umma::wait_st();
+}
+
+template <int E, bool TRACE>
 __global__ void __launch_bounds__(FWG * 128, 1) k_field_fwd_mma(
     const __half* __restrict__ enc, const float* __restrict__ dirs, int dstride, int dgroup, int64_t P, int G,
     acn_field_weights w, float4* __restrict__ rgb_sigma, long long* __restrict__ trace)
@@ -282,7 +337,7 @@ __global__ void __launch_bounds__(FWG * 128, 1) k_field_fwd_mma(
 
     stage_weights<E>(w, G, sb + M::w);
     if (tid == 0) {
-        for (int i = 0; i < FWG * 2; ++i) umma::mbar_init_a(sb + M::bars + 8 * i, 1);
+        for (int i = 0; i < FWG; ++i) umma::mbar_init_a(sb + M::bars + 8 * i, 1);
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(reinterpret_cast<uint32_t*>(smem_raw + M::tmem_ptr), FWD_TMEM_COLS);
@@ -293,33 +348,35 @@ __global__ void __launch_bounds__(FWG * 128, 1) k_field_fwd_mma(
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + M::tmem_ptr);
 
     const int wg = warp >> 2, row = tid & (TM - 1);
-    const bool issuer_warp = (warp & 3) == 0;
+    const bool issuer_warp = (warp & 3) == wg;        // one issuing warp per warpgroup, each on its own SM sub-partition
     const uint32_t bar_id = 1 + wg;
-    const Tile A0 = mk_tile(sb + M::a + (uint32_t)(wg * 2) * 16384u, 64), A1 = mk_tile(A0.a + 16384u, 64);
-    const uint32_t done0 = sb + M::bars + 8u * (wg * 2), done1 = done0 + 8u;
-    const uint32_t d0 = tmem_base + (uint32_t)(wg * 2) * 64u, d1 = d0 + 64u;                 // accumulator windows
+    const uint32_t done = sb + M::bars + 8u * wg;
+    const uint32_t H0 = tmem_base + (uint32_t)wg * 128u, H1 = H0 + 64u;     // issuer's view (lane 0)
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t h0 = H0 + lane_off, h1 = H1 + lane_off;                  // this thread's lanes
     const Tile Wt0 = mk_tile(sb + wm.t0, E), Wt1 = mk_tile(sb + wm.t1, 64), Whd = mk_tile(sb + wm.hd, 64),
                Wc0 = mk_tile(sb + wm.c0, 32), Wc1 = mk_tile(sb + wm.c1, 64), Wc2 = mk_tile(sb + wm.c2, 64);
-    const uint32_t bh_t0 = sb + wm.bh_t0, bh_t1 = sb + wm.bh_t1, bh_c0 = sb + wm.bh_c0, bh_c1 = sb + wm.bh_c1;
+    const Tile Bt0 = mk_tile(sb + wm.bt_t0, 16), Bt1 = mk_tile(sb + wm.bt_t1, 16), Bc0 = mk_tile(sb + wm.bt_c0, 16),
+               Bc1 = mk_tile(sb + wm.bt_c1, 16), One = mk_tile(sb + wm.one, 16);
 
     const int64_t ntiles = (P + TM - 1) / TM;
-    const int64_t npairs = (ntiles + 1) / 2;
-    const int64_t pair_stride = (int64_t)gridDim.x * FWG;
-    Tracer tr{ (trace && blockIdx.x == 0 && tid == 0) ? trace : nullptr, 0, TRACE_CAP };
+    const int64_t tile_stride = (int64_t)gridDim.x * FWG;
+    Tracer<TRACE> tr{ (trace && blockIdx.x == 0 && tid == 0) ? trace : nullptr, 0, TRACE_CAP };
 
-    // one elected lane of the warpgroup's first warp issues a layer and commits it to `done`
-    auto issue = [&](int step, const Tile& A, uint32_t d, uint32_t done) {
+    // every thread: my TMEM writes / reads are ordered before what the issuer launches next; then meet
+    auto sync_group = [&]() { umma::fence_before_sync(); umma::bar_sync(bar_id, 128); };
+    // one elected lane of the warpgroup's issuing warp launches a layer and commits it to `done`
+    auto issue = [&](int step) {
         if (issuer_warp) {
             if (umma::elect_one()) {
                 umma::fence_after_sync();
                 switch (step) {
-                    case 0: mma_fwd(d, A, Wt0, 64, E); break;
-                    case 1: mma_fwd(d, A, Wt1, 64, 64); break;
-                    case 2: mma_fwd(d, A, Whd, 16, 64); break;
-                    case 3: mma_fwd(d, A, Wc0, 64, 32); break;
-                    case 4: mma_fwd(d, A, Wc1, 64, 64); break;
-                    default: mma_fwd(d, A, Wc2, 16, 64); break;
+                    case 0: mma_layer_ts(H0, H1, Wt0, 64, E, &One, &Bt0); break;
+                    case 1: mma_layer_ts(H1, H0, Wt1, 64, 64, &One, &Bt1); break;
+                    case 2: mma_layer_ts(H0, H1, Whd, 16, 64, nullptr, nullptr); break;
+                    case 3: mma_layer_ts(H1, H0, Wc0, 64, 32, &One, &Bc0); break;
+                    case 4: mma_layer_ts(H0, H1, Wc1, 64, 64, &One, &Bc1); break;
+                    default: mma_layer_ts(H1, H0, Wc2, 16, 64, nullptr, nullptr); break;
                 }
                 umma::commit_a(done);
             }
@@ -329,89 +386,71 @@ __global__ void __launch_bounds__(FWG * 128, 1) k_field_fwd_mma(
     auto load_inputs = [&](int64_t tile, uint4* q, float* dir) {
         const int64_t p = tile * TM + row;
         const bool on = tile < ntiles && p < P;
+        const int64_t ps = on ? p : 0;                     // a safe address; no select sits between the loads and their use
 #pragma unroll
-        for (int c = 0; c < EC; ++c) q[c] = on ? __ldg(reinterpret_cast<const uint4*>(enc + p * E) + c) : make_uint4(0u, 0u, 0u, 0u);
-        dir[0] = 0.f; dir[1] = 0.f; dir[2] = 1.f;
-        if (on) { const float* dp = dir_of(dirs, dstride, dgroup, p); dir[0] = __ldg(dp); dir[1] = __ldg(dp + 1); dir[2] = __ldg(dp + 2); }
+        for (int c = 0; c < EC; ++c) q[c] = __ldg(reinterpret_cast<const uint4*>(enc + ps * E) + c);
+        const float* dp = dir_of(dirs, dstride, dgroup, ps);
+        dir[0] = __ldg(dp); dir[1] = __ldg(dp + 1); dir[2] = __ldg(dp + 2);
     };
 
-    uint32_t ph0 = 0, ph1 = 0;
-    uint4 q0[EC], q1[EC];
-    float dir0[3], dir1[3];
-    int64_t pair = (int64_t)blockIdx.x * FWG + wg;
-    load_inputs(2 * pair, q0, dir0);
-    load_inputs(2 * pair + 1, q1, dir1);
+    uint32_t phase = 0;
+    uint4 q[EC];
+    float dir[3];
+    int64_t tile = (int64_t)blockIdx.x * FWG + wg;
+    load_inputs(tile, q, dir);
+    float b_hd[16], b_c2[3];
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+        const uint4 u = lds128(sb + wm.b_hd + 16 * qd);
+        b_hd[4 * qd] = __uint_as_float(u.x); b_hd[4 * qd + 1] = __uint_as_float(u.y); b_hd[4 * qd + 2] = __uint_as_float(u.z); b_hd[4 * qd + 3] = __uint_as_float(u.w);
+    }
+    load_b_c2(sb + wm.b_c2, b_c2);
 
-    for (; pair < npairs; pair += pair_stride) {
-        const int64_t p0 = (2 * pair) * TM + row, p1 = p0 + TM;
-        float cdir0[3] = { dir0[0], dir0[1], dir0[2] }, cdir1[3] = { dir1[0], dir1[1], dir1[2] };
+    for (; tile < ntiles; tile += tile_stride) {
+        const int64_t p = tile * TM + row;
         tr(1);
-        // ---- stage both tiles' encoding rows, launch layer 1 of each ----
+        // ---- encoding row -> tensor memory (H1), layer 1 ----
 #pragma unroll
-        for (int c = 0; c < EC; ++c) sts128(chunk_addr(A0, row, c), q0[c]);
-        group_sync(bar_id, 128); issue(0, A0, d0, done0);
-#pragma unroll
-        for (int c = 0; c < EC; ++c) sts128(chunk_addr(A1, row, c), q1[c]);
-        group_sync(bar_id, 128); issue(0, A1, d1, done1);
+        for (int c = 0; c < EC; c += 2) {
+            const uint32_t r[8] = { q[c].x, q[c].y, q[c].z, q[c].w, q[c + 1].x, q[c + 1].y, q[c + 1].z, q[c + 1].w };
+            umma::st8(h1 + c * 4, r);
+        }
+        umma::wait_st();
+        const float cdir[3] = { dir[0], dir[1], dir[2] };
+        sync_group(); issue(0);
         tr(2);
-        // prefetch the next pair's inputs; they land while this pair's layers run
-        load_inputs(2 * (pair + pair_stride), q0, dir0);
-        load_inputs(2 * (pair + pair_stride) + 1, q1, dir1);
-        // ---- trunk layer 1 -> 2 ----
-        wait_done(done0, ph0); tr(3);
-        epi_hidden32(d0 + lane_off, 0, bh_t0, A0, row); epi_hidden32(d0 + lane_off, 32, bh_t0, A0, row); tr(4);
-        group_sync(bar_id, 128); tr(5); issue(1, A0, d0, done0); tr(6);
-        wait_done(done1, ph1); tr(7);
-        epi_hidden32(d1 + lane_off, 0, bh_t0, A1, row); epi_hidden32(d1 + lane_off, 32, bh_t0, A1, row);
-        group_sync(bar_id, 128); issue(1, A1, d1, done1);
-        // ---- trunk layer 2 -> heads ----
-        wait_done(done0, ph0); tr(8);
-        epi_hidden32(d0 + lane_off, 0, bh_t1, A0, row); epi_hidden32(d0 + lane_off, 32, bh_t1, A0, row);
-        group_sync(bar_id, 128); issue(2, A0, d0, done0);
-        wait_done(done1, ph1);
-        epi_hidden32(d1 + lane_off, 0, bh_t1, A1, row); epi_hidden32(d1 + lane_off, 32, bh_t1, A1, row);
-        group_sync(bar_id, 128); issue(2, A1, d1, done1);
-        // ---- heads -> colour layer 1 ----
-        wait_done(done0, ph0); tr(9);
-        epi_heads_sh(cdir0, A0, row);
-        const float sigma0 = trunc_exp_fast(epi_heads_geo(d0 + lane_off, sb + wm.b_hd, G, A0, row));
-        group_sync(bar_id, 128); issue(3, A0, d0, done0);
-        wait_done(done1, ph1);
-        epi_heads_sh(cdir1, A1, row);
-        const float sigma1 = trunc_exp_fast(epi_heads_geo(d1 + lane_off, sb + wm.b_hd, G, A1, row));
-        group_sync(bar_id, 128); issue(3, A1, d1, done1);
-        // ---- colour layer 1 -> 2 ----
-        wait_done(done0, ph0); tr(10);
-        epi_hidden32(d0 + lane_off, 0, bh_c0, A0, row); epi_hidden32(d0 + lane_off, 32, bh_c0, A0, row);
-        group_sync(bar_id, 128); issue(4, A0, d0, done0);
-        wait_done(done1, ph1);
-        epi_hidden32(d1 + lane_off, 0, bh_c0, A1, row); epi_hidden32(d1 + lane_off, 32, bh_c0, A1, row);
-        group_sync(bar_id, 128); issue(4, A1, d1, done1);
-        // ---- colour layer 2 -> out ----
-        wait_done(done0, ph0); tr(11);
-        epi_hidden32(d0 + lane_off, 0, bh_c1, A0, row); epi_hidden32(d0 + lane_off, 32, bh_c1, A0, row);
-        group_sync(bar_id, 128); issue(5, A0, d0, done0);
-        wait_done(done1, ph1);
-        epi_hidden32(d1 + lane_off, 0, bh_c1, A1, row); epi_hidden32(d1 + lane_off, 32, bh_c1, A1, row);
-        group_sync(bar_id, 128); issue(5, A1, d1, done1);
-        // ---- outputs ----
-        float bc2[3];
-        load_b_c2(sb + wm.b_c2, bc2);
-        wait_done(done0, ph0); tr(12);
+        load_inputs(tile + tile_stride, q, dir);       // prefetch: lands while this tile's layers run
+        wait_done(done, phase); tr(3); epi_hidden_tmem(h0); tr(4); sync_group(); tr(5); issue(1); tr(6);     // -> trunk layer 2
+        wait_done(done, phase); tr(7); epi_hidden_tmem(h1); sync_group(); issue(2);                          // -> heads
+        wait_done(done, phase); tr(8);
+        float sigma;
+        {   // heads: accumulator columns 0..G-1 = geo, 15 = raw sigma; colour input row [sh(16) | geo(G) | 0] -> H0[0,16)
+            float v[16], sh[16];
+            umma::ld16(h0, v);
+            sh16_fast(cdir[0], cdir[1], cdir[2], sh);
+            umma::wait_ld();
+            sigma = trunc_exp_fast(v[15] + b_hd[15]);
+            uint32_t r[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = pack_h2(sh[2 * j], sh[2 * j + 1]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = j < G ? v[j] + b_hd[j] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[8 + j] = pack_h2(v[2 * j], v[2 * j + 1]);
+            umma::st16(h0, r);
+            umma::wait_st();
+        }
+        sync_group(); issue(3);                                                                               // -> colour layer 1
+        wait_done(done, phase); tr(9); epi_hidden_tmem(h1); sync_group(); issue(4);                          // -> colour layer 2
+        wait_done(done, phase); tr(10); epi_hidden_tmem(h0); sync_group(); issue(5);                         // -> colour out
+        wait_done(done, phase); tr(11);
         {
             float v[16];
-            umma::ld16(d0 + lane_off, v);
+            umma::ld16(h1, v);
             umma::wait_ld();
-            if (p0 < P) rgb_sigma[p0] = make_float4(sigmoid_fast(v[0] + bc2[0]), sigmoid_fast(v[1] + bc2[1]), sigmoid_fast(v[2] + bc2[2]), sigma0);
+            if (p < P) rgb_sigma[p] = make_float4(sigmoid_fast(v[0] + b_c2[0]), sigmoid_fast(v[1] + b_c2[1]), sigmoid_fast(v[2] + b_c2[2]), sigma);
         }
-        wait_done(done1, ph1);
-        {
-            float v[16];
-            umma::ld16(d1 + lane_off, v);
-            umma::wait_ld();
-            if (p1 < P) rgb_sigma[p1] = make_float4(sigmoid_fast(v[0] + bc2[0]), sigmoid_fast(v[1] + bc2[1]), sigmoid_fast(v[2] + bc2[2]), sigma1);
-        }
-        tr(13);
+        tr(12);
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -530,7 +569,7 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     const int slot = warp >> 3;                    // 8 warps per slot
     const int hcol = (warp >> 2) & 1;              // which half of a row's columns this thread owns
     const int row = (warp & 3) * 32 + lane;
-    const bool issuer_warp = (warp & 7) == 0;
+    const bool issuer_warp = (warp & 7) == slot;      // slot 0 -> warp 0, slot 1 -> warp 9: different SM sub-partitions
     const uint32_t bar_id = 1 + slot;
     const uint32_t sbase = sb + M::slots + (uint32_t)slot * SM::bytes;
     const Tile Txe = mk_tile(sbase + SM::xe, E), Th1 = mk_tile(sbase + SM::h1, 64), Th2 = mk_tile(sbase + SM::h2, 64),
@@ -539,6 +578,8 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     const Tile Wt0 = mk_tile(sb + M::w + wm.t0, E), Wt1 = mk_tile(sb + M::w + wm.t1, 64), Whd = mk_tile(sb + M::w + wm.hd, 64),
                Wc0 = mk_tile(sb + M::w + wm.c0, 32), Wc1 = mk_tile(sb + M::w + wm.c1, 64), Wc2 = mk_tile(sb + M::w + wm.c2, 64);
     const uint32_t wb = sb + M::w;
+    const Tile Bt0 = mk_tile(wb + wm.bt_t0, 16), Bt1 = mk_tile(wb + wm.bt_t1, 16), Bc0 = mk_tile(wb + wm.bt_c0, 16),
+               Bc1 = mk_tile(wb + wm.bt_c1, 16), One = mk_tile(wb + wm.one, 16);
     const uint32_t done_d = sb + M::bars + 16u * slot, done_w = done_d + 8u;
     const uint32_t dwin = tmem_base + (uint32_t)slot * 64u;
     const uint32_t tmem_d = dwin + ((uint32_t)((warp & 3) * 32) << 16);
@@ -555,11 +596,11 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
             if (umma::elect_one()) {
                 umma::fence_after_sync();
                 switch (step) {
-                    case 0: mma_fwd(dwin, Txe, Wt0, 64, E); break;
-                    case 1: mma_fwd(dwin, Th1, Wt1, 64, 64); break;
+                    case 0: mma_fwd_bias(dwin, Txe, Wt0, One, Bt0, E); break;
+                    case 1: mma_fwd_bias(dwin, Th1, Wt1, One, Bt1, 64); break;
                     case 2: mma_fwd(dwin, Th2, Whd, 16, 64); break;
-                    case 3: mma_fwd(dwin, Tcin, Wc0, 64, 32); break;
-                    case 4: mma_fwd(dwin, Tc1, Wc1, 64, 64); break;
+                    case 3: mma_fwd_bias(dwin, Tcin, Wc0, One, Bc0, 32); break;
+                    case 4: mma_fwd_bias(dwin, Tc1, Wc1, One, Bc1, 64); break;
                     case 5: mma_fwd(dwin, Tc2, Wc2, 16, 64); break;
                     case 6:   // colour out: D = drr W_c2 ; dW^T (in x out) = c2^T drr ; db = drr^T 1
                         mma_dgrad(dwin, Tdrr, Wc2, 64, 16); umma::commit_a(done_d);
@@ -632,15 +673,15 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
         const float cdir[3] = { dir[0], dir[1], dir[2] };
         const float4 cdy = dy;
         load_inputs(tile + tile_stride, encq, dir, dy);        // prefetch: lands while this tile runs
-        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, wb + wm.bh_t0, Th1, row); group_sync(bar_id, 256); issue(1);
-        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, wb + wm.bh_t1, Th2, row); group_sync(bar_id, 256); issue(2);
+        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, Th1, row); group_sync(bar_id, 256); issue(1);
+        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, Th2, row); group_sync(bar_id, 256); issue(2);
         wait_done(done_d, ph_d);
         float sig_raw = 0.0f;
         if (hcol) epi_heads_sh(cdir, Tcin, row);
         else sig_raw = epi_heads_geo(tmem_d, wb + wm.b_hd, G, Tcin, row);
         group_sync(bar_id, 256); issue(3);
-        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, wb + wm.bh_c0, Tc1, row); group_sync(bar_id, 256); issue(4);
-        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, wb + wm.bh_c1, Tc2, row); group_sync(bar_id, 256); issue(5);
+        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, Tc1, row); group_sync(bar_id, 256); issue(4);
+        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, Tc2, row); group_sync(bar_id, 256); issue(5);
         wait_done(done_d, ph_d);
         float d_sig = 0.0f;
         if (!hcol) {   // output gradients (scaled): d rgb_raw = dy * y (1 - y); d sigma_raw = dy * exp(clamp(sigma_raw))
@@ -773,12 +814,18 @@ int launch_fwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride
                const acn_field_weights* w, float* rgb_sigma, cudaStream_t st) {
     constexpr uint32_t smem = FwdMap<E>::bytes;
     ACN_REQUIRE((int)smem <= ctx->max_smem_optin, ACN_EUNSUPPORTED, "acn_field_fwd(f16): needs %u B shared memory", smem);
-    const int64_t npairs = ((P + TM - 1) / TM + 1) / 2;
-    int64_t grid = (npairs + FWG - 1) / FWG;
+    const int64_t ntiles = (P + TM - 1) / TM;
+    int64_t grid = (ntiles + FWG - 1) / FWG;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
-    ACN_CUDA(cudaFuncSetAttribute(k_field_fwd_mma<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_field_fwd_mma<E><<<(int)grid, FWG * 128, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
-                                                            (float4*)rgb_sigma, g_field_trace);
+    if (g_field_trace && E == 32) {          // the timeline build of the kernel (tools/field_trace.py)
+        ACN_CUDA(cudaFuncSetAttribute(k_field_fwd_mma<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_field_fwd_mma<32, true><<<(int)grid, FWG * 128, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
+                                                                       (float4*)rgb_sigma, g_field_trace);
+    } else {
+        ACN_CUDA(cudaFuncSetAttribute(k_field_fwd_mma<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_field_fwd_mma<E, false><<<(int)grid, FWG * 128, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
+                                                                       (float4*)rgb_sigma, nullptr);
+    }
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }

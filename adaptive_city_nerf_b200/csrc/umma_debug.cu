@@ -76,7 +76,72 @@ __global__ void __launch_bounds__(TM) k_debug_umma(const __half* __restrict__ a,
     if (warp == 0) umma::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// Same product with the A operand in TENSOR MEMORY: thread r packs row r of A into 32-bit words (k even in the low
+// half) and stores them with tcgen05.st at columns [64, 64 + K/2); the MMA then reads A from TMEM and B from shared
+// memory.  Establishes the TMEM operand layout the forward MLP kernel's activation chain relies on.
+__global__ void __launch_bounds__(TM) k_debug_umma_ts(const __half* __restrict__ a, const __half* __restrict__ w, int N, int K,
+                                                      float* __restrict__ d)
+{
+    __shared__ __align__(128) uint8_t w_tile[64 * 64 * 2];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_ptr;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t w_sbo = (uint32_t)(K / 8) * 128u;
+    for (int idx = tid; idx < N * (K / 8); idx += TM) {
+        int n = idx / (K / 8), c = idx - n * (K / 8);
+        *reinterpret_cast<uint4*>(w_tile + umma::chunk_off(n, c, w_sbo)) = *reinterpret_cast<const uint4*>(w + (size_t)n * K + c * 8);
+    }
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_mbar_init(); }
+    if (warp == 0) umma::tmem_alloc(&tmem_ptr, 128);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = tmem_ptr;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c8 = 0; c8 < K / 16; ++c8) {           // 16 halves = 8 words per store
+        uint32_t r[8];
+        const uint4 q0 = *reinterpret_cast<const uint4*>(a + (size_t)tid * K + c8 * 16);
+        const uint4 q1 = *reinterpret_cast<const uint4*>(a + (size_t)tid * K + c8 * 16 + 8);
+        r[0] = q0.x; r[1] = q0.y; r[2] = q0.z; r[3] = q0.w; r[4] = q1.x; r[5] = q1.y; r[6] = q1.z; r[7] = q1.w;
+        umma::st8(tmem_row + 64 + c8 * 8, r);
+    }
+    umma::wait_st();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+        umma::fence_after_sync();
+        const uint32_t idesc = umma::make_idesc_f16(128, N);
+        const uint32_t w_addr = umma::smem_u32(w_tile);
+        for (int ks = 0; ks < K / 16; ++ks)
+            umma::mma_f16_ts(tmem_base, tmem_base + 64 + ks * 8, umma::make_desc(w_addr + ks * 256, 128, w_sbo), idesc, ks > 0);
+        umma::commit(&bar);
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    for (int q = 0; q < N / 16; ++q) {
+        float v[16];
+        umma::ld16(tmem_row + q * 16, v);
+        umma::wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) d[(size_t)tid * N + q * 16 + j] = v[j];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_base, 128);
+}
+
 }  // namespace
+
+extern "C" int acn_debug_umma_gemm_ts(acn_ctx* ctx, const void* a_f16, const void* w_f16, int N, int K, float* d, acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    ACN_REQUIRE(a_f16 && w_f16 && d, ACN_EINVAL, "acn_debug_umma_gemm_ts: null buffer");
+    ACN_REQUIRE((N == 16 || N == 32 || N == 64) && (K == 16 || K == 32 || K == 64), ACN_EUNSUPPORTED,
+                "acn_debug_umma_gemm_ts: N,K must be in {16,32,64}");
+    k_debug_umma_ts<<<1, TM, 0, (cudaStream_t)stream>>>((const __half*)a_f16, (const __half*)w_f16, N, K, d);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
 
 extern "C" int acn_debug_umma_gemm(acn_ctx* ctx, const void* a_f16, const void* w_f16, int N, int K, float* d, acn_stream stream) {
     ACN_CHECK_CTX(ctx);

@@ -410,6 +410,15 @@ def debug_umma_gemm(a: Tensor, w: Tensor) -> Tensor:
     return d
 
 
+def debug_umma_gemm_ts(a: Tensor, w: Tensor) -> Tensor:
+    """D = A @ W^T with A staged in tensor memory (tcgen05.st) and read by the MMA from there."""
+    assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.shape[0] == 128
+    a, w = a.contiguous(), w.contiguous()
+    d = torch.empty(128, w.shape[0], dtype=torch.float32, device=a.device)
+    check(lib().acn_debug_umma_gemm_ts(ctx(a.device), ptr(a), ptr(w), w.shape[0], a.shape[1], ptr(d), stream(a.device)))
+    return d
+
+
 def debug_field_trace(buf: Optional[Tensor]) -> None:
     """Arm (int64 CUDA tensor of 1024 words) or disarm (None) the forward-MLP timeline (acn_debug_field_trace)."""
     dev = buf.device if buf is not None else torch.device("cuda", torch.cuda.current_device())

@@ -182,6 +182,10 @@ int acn_blend_bwd(acn_ctx*, const float* d_out, const float* w, const int32_t* s
 int acn_debug_umma_gemm(acn_ctx*, const void* a_f16, const void* w_f16, int N, int K, float* d,
                         acn_stream);
 
+/* Same product with A read from TENSOR MEMORY (written there by tcgen05.st): validates the TMEM operand layout of
+ * the forward MLP kernel's activation chain. */
+int acn_debug_umma_gemm_ts(acn_ctx*, const void* a_f16, const void* w_f16, int N, int K, float* d, acn_stream);
+
 /* Raw harness: stages two 16-bit matrices as canonical tiles and issues `ksteps` MMAs with
  * host-supplied descriptors, then dumps TMEM lanes 0..127 x ncols.  Used by tools/umma_probe.py to
  * establish MN-major / mixed-dtype / M=64 layouts on hardware. */

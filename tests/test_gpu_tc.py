@@ -22,6 +22,18 @@ def test_umma_tile_gemm(N, K):
     assert np.array_equal(npy(d), ref), f"max err {np.abs(npy(d) - ref).max()}"
 
 
+@pytest.mark.parametrize("N,K", [(64, 64), (64, 32), (16, 64), (64, 16)])
+def test_umma_tile_gemm_a_in_tmem(N, K):
+    """Same product with the A operand written to tensor memory by tcgen05.st and read from there by the MMA."""
+    from adaptive_city_nerf_b200 import ops
+    rng = np.random.default_rng(7 + N * 100 + K)
+    a = rng.integers(-4, 5, (128, K)).astype(np.float16)
+    w = rng.integers(-4, 5, (N, K)).astype(np.float16)
+    d = ops.debug_umma_gemm_ts(cu(a), cu(w))
+    ref = a.astype(F32) @ w.astype(F32).T
+    assert np.array_equal(npy(d), ref), f"max err {np.abs(npy(d) - ref).max()}"
+
+
 def test_field_fp16_forward(golden, orc):
     from adaptive_city_nerf_b200 import ops
     g = golden("field")
@@ -66,8 +78,8 @@ def _rel_l2(a, b):
 
 def _emulate_fp16_field(enc16, dirs, ws, dy):
     """Torch restatement of csrc/field_mma.cu's arithmetic (the reference's autocast path, models/metamodule/
-    metamodule.py:150-155): fp16 operands, exact products with wide accumulation (fp64 here, fp32 in TMEM), GEMM
-    result rounded to fp16 before the fp16 bias + ReLU; gradient tiles are fp16 carrying a power-of-two scale;
+    metamodule.py:150-155): fp16 operands (bias included), exact products with wide accumulation (fp64 here, fp32
+    in TMEM), ReLU and one rounding to fp16; gradient tiles are fp16 carrying a power-of-two scale;
     the ReLU masks are those of THIS forward.  Returns (rgb_sigma, 14 grads, d_enc)."""
     from adaptive_city_nerf_b200 import ops
     D = torch.float64
@@ -76,7 +88,7 @@ def _emulate_fp16_field(enc16, dirs, ws, dy):
     wt0, bt0, wt1, bt1, wsg, bsg, wge, bge, wc0, bc0, wc1, bc1, wc2, bc2 = W
     G = wge.shape[0]
     x0 = enc16.to(D)
-    hid = lambda x, w, b: h(torch.relu(h(x @ h(w).t()) + h(b)))   # fma.rn.relu.f16x2: one rounding of the exact sum
+    hid = lambda x, w, b: h(torch.relu(x @ h(w).t() + h(b)))      # bias rides in the accumulator: ONE rounding, with ReLU
     h1 = hid(x0, wt0, bt0)
     h2 = hid(h1, wt1, bt1)
     sig_raw = (h2 @ h(wsg).t()).float().to(D) + bsg               # head accumulators stay fp32

@@ -21,10 +21,9 @@ torch.cuda.synchronize()
 ops.debug_field_trace(None)
 b = buf.cpu().tolist()
 ev = [(v >> 8, v & 0xff) for v in b if v]
-names = {1: "pair start", 2: "both tiles staged + layer 1 issued", 3: "t0 done-wait returned (tile A)", 4: "t0 epilogue done (A)",
-         5: "group barrier passed", 6: "layer issued", 7: "done-wait returned (tile B)", 8: "t1 done-wait returned (A)",
-         9: "heads done-wait returned (A)", 10: "c0 done-wait returned (A)", 11: "c1 done-wait returned (A)",
-         12: "c2 done-wait returned (A)", 13: "pair finished"}
+names = {1: "tile start", 2: "enc in TMEM + layer 1 issued", 3: "t0 done-wait returned", 4: "t0 epilogue done (TMEM -> TMEM)",
+         5: "group barrier passed", 6: "layer 2 issued", 7: "t1 done-wait returned", 8: "heads done-wait returned",
+         9: "c0 done-wait returned", 10: "c1 done-wait returned", 11: "c2 done-wait returned", 12: "tile finished"}
 t0 = ev[0][0]
 prev = t0
 for t, tag in ev[:140]:
