@@ -195,9 +195,12 @@ __device__ __forceinline__ void mma_fwd_bias(uint32_t d, const Tile& a, const Ti
     for (int ks = 0; ks < K / 16; ++ks) umma::mma_f16_ss(d, desc_k(a, ks), desc_k(w, ks), id, ks > 0);
     umma::mma_f16_ss(d, desc_k(one, 0), desc_k(bias, 0), id, true);
 }
-// acc += A^T B over the tile's 128 points: A, B canonical tiles whose ROWS are points (both MN-major views)
+// acc += A^T B over the tile's 128 points: A, B canonical tiles whose ROWS are points (both MN-major views).
+// M = 64: the A operand has at most 64 feature columns, and an M=64 MMA fetches half the A bytes of an M=128 one --
+// these MMAs are bound by shared-memory operand fetch, not by the tensor pipe.  Accumulator row m lands in TMEM
+// lane (m >> 4) * 32 + (m & 15) (measured: tools/umma_probe.py H5b).
 __device__ __forceinline__ void mma_over_points(uint32_t acc, const Tile& a, const Tile& b, int N) {
-    const uint32_t id = umma::make_idesc_f16(128, N, true, true);
+    const uint32_t id = umma::make_idesc_f16(64, N, true, true);
 #pragma unroll
     for (int ks = 0; ks < TM / 16; ++ks) umma::mma_f16_ss(acc, desc_mn(a, ks), desc_mn(b, ks), id, true);
 }
@@ -605,33 +608,33 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
                     case 6:   // colour out: D = drr W_c2 ; dW^T (in x out) = c2^T drr ; db = drr^T 1
                         mma_dgrad(dwin, Tdrr, Wc2, 64, 16); umma::commit_a(done_d);
                         mma_over_points(tmem_base + COL_WC2T, Tc2, Tdrr, 16);
-                        mma_over_points(tmem_base + COL_BC2, Tdrr, Tones, 16);
+                        mma_over_points(tmem_base + COL_BC2, Tdrr, Tones, 8);
                         break;
                     case 7:   // colour layer 2: g lives in the c2 tile now; dW (out x in) = g^T c1
                         mma_dgrad(dwin, Tc2, Wc1, 64, 64); umma::commit_a(done_d);
                         mma_over_points(tmem_base + COL_WC1, Tc2, Tc1, 64);
-                        mma_over_points(tmem_base + COL_BC1, Tc2, Tones, 16);
+                        mma_over_points(tmem_base + COL_BC1, Tc2, Tones, 8);
                         break;
                     case 8:   // colour layer 1
                         mma_dgrad(dwin, Tc1, Wc0, 32, 64); umma::commit_a(done_d);
                         mma_over_points(tmem_base + COL_WC0, Tc1, Tcin, 32);
-                        mma_over_points(tmem_base + COL_BC0, Tc1, Tones, 16);
+                        mma_over_points(tmem_base + COL_BC0, Tc1, Tones, 8);
                         break;
                     case 9:   // heads: dW^T (in x out) = h2^T ghd
                         mma_dgrad(dwin, Tghd, Whd, 64, 16); umma::commit_a(done_d);
                         mma_over_points(tmem_base + COL_WHDT, Th2, Tghd, 16);
-                        mma_over_points(tmem_base + COL_BHD, Tghd, Tones, 16);
+                        mma_over_points(tmem_base + COL_BHD, Tghd, Tones, 8);
                         break;
                     case 10:  // trunk layer 2
                         mma_dgrad(dwin, Th2, Wt1, 64, 64); umma::commit_a(done_d);
                         mma_over_points(tmem_base + COL_WT1, Th2, Th1, 64);
-                        mma_over_points(tmem_base + COL_BT1, Th2, Tones, 16);
+                        mma_over_points(tmem_base + COL_BT1, Th2, Tones, 8);
                         break;
                     default:  // trunk layer 1 (+ optional d enc)
                         if (want_denc) mma_dgrad(dwin, Th1, Wt0, E, 64);
                         umma::commit_a(done_d);
                         mma_over_points(tmem_base + COL_WT0, Th1, Txe, E);
-                        mma_over_points(tmem_base + COL_BT0, Th1, Tones, 16);
+                        mma_over_points(tmem_base + COL_BT0, Th1, Tones, 8);
                         break;
                 }
                 umma::commit_a(step < 6 ? done_d : done_w);
@@ -748,8 +751,9 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     umma::fence_after_sync();
     if (warp < 4) {
         const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int t = tid;     // TMEM lane
-        // accumulator(lane t, column n) -> dst[n * ld_col] for n < nvalid (dst null: skip)
+        // M = 64 accumulators: rows 16w..16w+15 live in lanes 32w..32w+15; the upper half of each warp holds nothing
+        const int t = (lane < 16) ? warp * 16 + lane : 1 << 20;     // accumulator row of this lane (or none)
+        // accumulator(row t, column n) -> dst[n * ld_col] for n < nvalid (dst null: skip)
         auto flush = [&](uint32_t col, int ncols, float* dst, int ld_col, int nvalid) {
             for (int q = 0; q < ncols / 16; ++q) {
                 float v[16];
