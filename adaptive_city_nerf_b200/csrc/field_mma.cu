@@ -47,7 +47,6 @@ using umma::lds128;
 using umma::sts128;
 
 constexpr int TM = 128;                 // points per tile = MMA M
-constexpr uint32_t HALF2_ONE = 0x3C003C00u;
 
 // A canonical tile: shared-space byte address >> 4 (all of shared memory fits the descriptor's 14-bit field) and
 // row-group stride (= cols/8 * 128 B).  Descriptors are built as `a16 + immediate` -- ONE uniform add per operand.
@@ -199,8 +198,8 @@ __device__ __forceinline__ void mma_fwd_bias(uint32_t d, const Tile& a, const Ti
 // M = 64: the A operand has at most 64 feature columns, and an M=64 MMA fetches half the A bytes of an M=128 one --
 // these MMAs are bound by shared-memory operand fetch, not by the tensor pipe.  Accumulator row m lands in TMEM
 // lane (m >> 4) * 32 + (m & 15) (measured: tools/umma_probe.py H5b).
-__device__ __forceinline__ void mma_over_points(uint32_t acc, const Tile& a, const Tile& b, int N) {
-    const uint32_t id = umma::make_idesc_f16(64, N, true, true);
+__device__ __forceinline__ void mma_over_points(uint32_t acc, const Tile& a, const Tile& b, int N, int M = 64) {
+    const uint32_t id = umma::make_idesc_f16(M, N, true, true);
 #pragma unroll
     for (int ks = 0; ks < TM / 16; ++ks) umma::mma_f16_ss(acc, desc_mn(a, ks), desc_mn(b, ks), id, true);
 }
@@ -241,7 +240,7 @@ __device__ __forceinline__ void epi_hidden32(uint32_t tmem_d, int col0, const Ti
 }
 // heads, geo part: accumulator columns 0..G-1 = geo, 15 = raw sigma -> cin chunks 2,3 ([geo(G) | 0]);
 // returns raw sigma (bias added)
-__device__ __forceinline__ float epi_heads_geo(uint32_t tmem_d, uint32_t b_hd_addr, int G, const Tile& cin, int row) {
+__device__ __forceinline__ float epi_heads_geo(uint32_t tmem_d, uint32_t b_hd_addr, int G, const Tile& cin, int row, float pad_last = 0.0f) {
     float v[16];
     umma::ld16(tmem_d, v);
     float b[16];
@@ -254,6 +253,7 @@ __device__ __forceinline__ float epi_heads_geo(uint32_t tmem_d, uint32_t b_hd_ad
     const float sig_raw = v[15] + b[15];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = j < G ? v[j] + b[j] : 0.0f;
+    v[15] = pad_last;                      // column 31 of the colour input: always zero weight; the backward sets it to 1
     sts128(chunk_addr(cin, row, 2), pack8(v));
     sts128(chunk_addr(cin, row, 3), pack8(v + 8));
     return sig_raw;
@@ -464,23 +464,27 @@ __global__ void __launch_bounds__(FWG * 128, 1) k_field_fwd_mma(
 // backward: 2 slots x 1 tile, 256 threads per slot (two threads per row)
 // ======================================================================================================
 constexpr int BNS = 2;
-// TMEM columns: per-slot D windows, then the persistent weight / bias gradient accumulators
+// TMEM columns: per-slot D windows, then the persistent weight-gradient accumulators.  Bias gradients ride inside
+// them (see "ones" below) except for the first trunk layer, which keeps a separate G^T 1 accumulator (8 columns).
 constexpr uint32_t COL_ACC0 = 128;
-constexpr uint32_t COL_WC1 = 128, COL_WT1 = 192, COL_WC0 = 256, COL_WT0 = 288, COL_WC2T = 352, COL_WHDT = 368;
-constexpr uint32_t COL_BC2 = 384, COL_BC1 = 400, COL_BC0 = 416, COL_BHD = 432, COL_BT1 = 448, COL_BT0 = 464;
-constexpr uint32_t COL_ACC1 = 480;
+constexpr uint32_t COL_WC1 = 128, COL_WT1 = 208, COL_WC0 = 288, COL_WT0 = 320, COL_WC2T = 384, COL_WHDT = 400, COL_BT0 = 416;
+constexpr uint32_t COL_ACC1 = 432;
 constexpr uint32_t BWD_TMEM_COLS = 512;
+constexpr int HW = 72;   // hidden activation tiles are 72 columns wide: 64 units + a chunk [1,0,0,0,0,0,0,0]
 
-// per-slot tiles (byte offsets inside the slot block).  Activation / gradient tiles first: MN-major M=128 views
-// of 64- and 16-column tiles read up to 2 KB past the tile into whatever follows, which must be mapped.
+// Per-slot tiles (byte offsets inside the slot block).  The four hidden tiles carry a constant ONES column (col 64):
+// as the B operand of a weight-gradient MMA (N = 72) it makes column 64 of dW the bias gradient, as the A operand
+// of a transposed one (M = 128) it makes lane 64 the bias gradient -- no separate G^T 1 MMAs (48 of 140 per tile).
+// The colour-MLP input has a free column (31) that plays the same role.  `dg` holds d rgb_raw (forward end) and
+// later the heads gradient: their lifetimes are disjoint.  MN-major M=128 views read up to 2 KB past a tile into
+// whatever follows, which must be mapped shared memory.
 template <int E> struct SlotMap {
-    static constexpr uint32_t drr = 0, ghd = 4096, c2 = 8192, c1 = c2 + 16384, h2 = c1 + 16384, h1 = h2 + 16384;
-    static constexpr uint32_t xe = h1 + 16384, cin = xe + TM * E * 2, bytes = cin + TM * 32 * 2;
+    static constexpr uint32_t dg = 0, c2 = 4096, c1 = c2 + TM * HW * 2, h2 = c1 + TM * HW * 2, h1 = h2 + TM * HW * 2;
+    static constexpr uint32_t xe = h1 + TM * HW * 2, cin = xe + TM * E * 2, bytes = cin + TM * 32 * 2;
 };
 template <int E> struct BwdMap {
     static constexpr uint32_t slots = 0;
-    static constexpr uint32_t ones = BNS * SlotMap<E>::bytes;
-    static constexpr uint32_t w = ones + 4096;
+    static constexpr uint32_t w = BNS * SlotMap<E>::bytes;
     static constexpr uint32_t bars = (w + wmap(E).end + 127u) & ~127u;     // per slot: done_d, done_w
     static constexpr uint32_t tmem_ptr = bars + BNS * 2 * 8u;
     static constexpr uint32_t bytes = tmem_ptr + 16u;
@@ -529,11 +533,11 @@ __device__ __forceinline__ void epi_mask32_store(const Tile& act, int row, int c
     for (int q = 0; q < 4; ++q) sts128(chunk_addr(act, row, col0 / 8 + q), o[q]);
 }
 
-template <int E>
+template <int E, bool TRACE>
 __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     const __half* __restrict__ enc, const float* __restrict__ dirs, int dstride, int dgroup, int64_t P, int G,
     acn_field_weights w, const float4* __restrict__ d_rgb_sigma, const unsigned int* __restrict__ absmax_bits,
-    acn_field_grads g, float* __restrict__ d_enc)
+    acn_field_grads g, float* __restrict__ d_enc, long long* __restrict__ trace)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     using M = BwdMap<E>;
@@ -545,11 +549,10 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     stage_weights<E>(w, G, sb + M::w);
-    for (int r = tid; r < TM; r += blockDim.x) {
-        const uint4 one = make_uint4(HALF2_ONE, HALF2_ONE, HALF2_ONE, HALF2_ONE);
-        const Tile ones = mk_tile(sb + M::ones, 16);
-        sts128(chunk_addr(ones, r, 0), one);
-        sts128(chunk_addr(ones, r, 1), one);
+    for (int i = tid; i < BNS * 4 * TM; i += blockDim.x) {      // the ones chunk (chunk 8) of every hidden tile
+        const int r = i & (TM - 1), t = (i >> 7) & 3, sl = i >> 9;
+        const Tile ht = mk_tile(sb + M::slots + (uint32_t)sl * SM::bytes + SM::c2 + (uint32_t)t * (TM * HW * 2), HW);
+        sts128(chunk_addr(ht, r, 8), make_uint4(0x00003C00u, 0u, 0u, 0u));
     }
     if (tid == 0) {
         for (int i = 0; i < BNS * 2; ++i) umma::mbar_init_a(sb + M::bars + 8 * i, 1);
@@ -575,9 +578,9 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     const bool issuer_warp = (warp & 7) == slot;      // slot 0 -> warp 0, slot 1 -> warp 9: different SM sub-partitions
     const uint32_t bar_id = 1 + slot;
     const uint32_t sbase = sb + M::slots + (uint32_t)slot * SM::bytes;
-    const Tile Txe = mk_tile(sbase + SM::xe, E), Th1 = mk_tile(sbase + SM::h1, 64), Th2 = mk_tile(sbase + SM::h2, 64),
-               Tcin = mk_tile(sbase + SM::cin, 32), Tc1 = mk_tile(sbase + SM::c1, 64), Tc2 = mk_tile(sbase + SM::c2, 64),
-               Tdrr = mk_tile(sbase + SM::drr, 16), Tghd = mk_tile(sbase + SM::ghd, 16), Tones = mk_tile(sb + M::ones, 16);
+    const Tile Txe = mk_tile(sbase + SM::xe, E), Th1 = mk_tile(sbase + SM::h1, HW), Th2 = mk_tile(sbase + SM::h2, HW),
+               Tcin = mk_tile(sbase + SM::cin, 32), Tc1 = mk_tile(sbase + SM::c1, HW), Tc2 = mk_tile(sbase + SM::c2, HW),
+               Tdrr = mk_tile(sbase + SM::dg, 16), Tghd = mk_tile(sbase + SM::dg, 16);
     const Tile Wt0 = mk_tile(sb + M::w + wm.t0, E), Wt1 = mk_tile(sb + M::w + wm.t1, 64), Whd = mk_tile(sb + M::w + wm.hd, 64),
                Wc0 = mk_tile(sb + M::w + wm.c0, 32), Wc1 = mk_tile(sb + M::w + wm.c1, 64), Wc2 = mk_tile(sb + M::w + wm.c2, 64);
     const uint32_t wb = sb + M::w;
@@ -605,36 +608,31 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
                     case 3: mma_fwd_bias(dwin, Tcin, Wc0, One, Bc0, 32); break;
                     case 4: mma_fwd_bias(dwin, Tc1, Wc1, One, Bc1, 64); break;
                     case 5: mma_fwd(dwin, Tc2, Wc2, 16, 64); break;
-                    case 6:   // colour out: D = drr W_c2 ; dW^T (in x out) = c2^T drr ; db = drr^T 1
+                    case 6:   // colour out: D = drr W_c2 ; [dW^T ; db] (in+1 x out) = [c2 | 1]^T drr
                         mma_dgrad(dwin, Tdrr, Wc2, 64, 16); umma::commit_a(done_d);
-                        mma_over_points(tmem_base + COL_WC2T, Tc2, Tdrr, 16);
-                        mma_over_points(tmem_base + COL_BC2, Tdrr, Tones, 8);
+                        mma_over_points(tmem_base + COL_WC2T, Tc2, Tdrr, 16, 128);
                         break;
-                    case 7:   // colour layer 2: g lives in the c2 tile now; dW (out x in) = g^T c1
+                    case 7:   // colour layer 2: g lives in the c2 tile now; [dW | db] (out x in+1) = g^T [c1 | 1]
                         mma_dgrad(dwin, Tc2, Wc1, 64, 64); umma::commit_a(done_d);
-                        mma_over_points(tmem_base + COL_WC1, Tc2, Tc1, 64);
-                        mma_over_points(tmem_base + COL_BC1, Tc2, Tones, 8);
+                        mma_over_points(tmem_base + COL_WC1, Tc2, Tc1, HW);
                         break;
-                    case 8:   // colour layer 1
+                    case 8:   // colour layer 1: column 31 of the input tile is the ones column
                         mma_dgrad(dwin, Tc1, Wc0, 32, 64); umma::commit_a(done_d);
                         mma_over_points(tmem_base + COL_WC0, Tc1, Tcin, 32);
-                        mma_over_points(tmem_base + COL_BC0, Tc1, Tones, 8);
                         break;
-                    case 9:   // heads: dW^T (in x out) = h2^T ghd
+                    case 9:   // heads: [dW^T ; db] (in+1 x out) = [h2 | 1]^T ghd
                         mma_dgrad(dwin, Tghd, Whd, 64, 16); umma::commit_a(done_d);
-                        mma_over_points(tmem_base + COL_WHDT, Th2, Tghd, 16);
-                        mma_over_points(tmem_base + COL_BHD, Tghd, Tones, 8);
+                        mma_over_points(tmem_base + COL_WHDT, Th2, Tghd, 16, 128);
                         break;
                     case 10:  // trunk layer 2
                         mma_dgrad(dwin, Th2, Wt1, 64, 64); umma::commit_a(done_d);
-                        mma_over_points(tmem_base + COL_WT1, Th2, Th1, 64);
-                        mma_over_points(tmem_base + COL_BT1, Th2, Tones, 8);
+                        mma_over_points(tmem_base + COL_WT1, Th2, Th1, HW);
                         break;
-                    default:  // trunk layer 1 (+ optional d enc)
+                    default:  // trunk layer 1 (+ optional d enc); the encoding tile has no spare column: separate G^T 1
                         if (want_denc) mma_dgrad(dwin, Th1, Wt0, E, 64);
                         umma::commit_a(done_d);
                         mma_over_points(tmem_base + COL_WT0, Th1, Txe, E);
-                        mma_over_points(tmem_base + COL_BT0, Th1, Tones, 8);
+                        mma_over_points(tmem_base + COL_BT0, Th1, One, 8);
                         break;
                 }
                 umma::commit_a(step < 6 ? done_d : done_w);
@@ -665,6 +663,7 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     float4 dy;
     int64_t tile = (int64_t)blockIdx.x * BNS + slot;
     load_inputs(tile, encq, dir, dy);
+    Tracer<TRACE> tr{ (trace && blockIdx.x == 0 && tid == 0) ? trace : nullptr, 0, TRACE_CAP };
 
     for (; tile < ntiles; tile += tile_stride) {
         const int64_t p = tile * TM + row;
@@ -672,16 +671,17 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
         // ---------------- forward recompute (same arithmetic as k_field_fwd_mma) ----------------
 #pragma unroll
         for (int j = 0; j < ECH; ++j) if (2 * j + hcol < EC) sts128(chunk_addr(Txe, row, 2 * j + hcol), encq[j]);
-        group_sync(bar_id, 256); issue(0);
+        tr(1);
+        group_sync(bar_id, 256); tr(2); issue(0); tr(3);
         const float cdir[3] = { dir[0], dir[1], dir[2] };
         const float4 cdy = dy;
         load_inputs(tile + tile_stride, encq, dir, dy);        // prefetch: lands while this tile runs
-        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, Th1, row); group_sync(bar_id, 256); issue(1);
+        wait_done(done_d, ph_d); tr(4); epi_hidden32(tmem_d, col0, Th1, row); tr(5); group_sync(bar_id, 256); tr(6); issue(1); tr(7);
         wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, Th2, row); group_sync(bar_id, 256); issue(2);
         wait_done(done_d, ph_d);
         float sig_raw = 0.0f;
         if (hcol) epi_heads_sh(cdir, Tcin, row);
-        else sig_raw = epi_heads_geo(tmem_d, wb + wm.b_hd, G, Tcin, row);
+        else sig_raw = epi_heads_geo(tmem_d, wb + wm.b_hd, G, Tcin, row, 1.0f);
         group_sync(bar_id, 256); issue(3);
         wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, Tc1, row); group_sync(bar_id, 256); issue(4);
         wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, Tc2, row); group_sync(bar_id, 256); issue(5);
@@ -700,11 +700,12 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
             sts128(chunk_addr(Tdrr, row, 0), pack8(drr));
             sts128(chunk_addr(Tdrr, row, 1), pack8(drr + 8));
         }
-        group_sync(bar_id, 256); issue(6);
+        tr(8);
+        group_sync(bar_id, 256); tr(9); issue(6); tr(10);
         // ---------------- backward ----------------
         uint4 o[4];
-        wait_done(done_d, ph_d); epi_mask32_load(tmem_d, col0, Tc2, row, o); wait_done(done_w, ph_w); epi_mask32_store(Tc2, row, col0, o);
-        group_sync(bar_id, 256); issue(7);
+        wait_done(done_d, ph_d); tr(11); epi_mask32_load(tmem_d, col0, Tc2, row, o); tr(12); wait_done(done_w, ph_w); tr(13); epi_mask32_store(Tc2, row, col0, o);
+        tr(14); group_sync(bar_id, 256); tr(15); issue(7); tr(16);
         wait_done(done_d, ph_d); epi_mask32_load(tmem_d, col0, Tc1, row, o); wait_done(done_w, ph_w); epi_mask32_store(Tc1, row, col0, o);
         group_sync(bar_id, 256); issue(8);
         wait_done(done_d, ph_d);
@@ -743,6 +744,7 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
             }
         }
         wait_done(done_w, ph_w);     // the xe / h1 tiles are free again only now
+        tr(17);
     }
 
     // ---------------- add the TMEM-resident weight gradients to global memory ----------------
@@ -751,9 +753,11 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     umma::fence_after_sync();
     if (warp < 4) {
         const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-        // M = 64 accumulators: rows 16w..16w+15 live in lanes 32w..32w+15; the upper half of each warp holds nothing
-        const int t = (lane < 16) ? warp * 16 + lane : 1 << 20;     // accumulator row of this lane (or none)
-        // accumulator(row t, column n) -> dst[n * ld_col] for n < nvalid (dst null: skip)
+        // M = 64 accumulators: rows 16w..16w+15 live in lanes 32w..32w+15 (the upper half of each warp holds nothing);
+        // M = 128 accumulators: row = lane.
+        const int t = (lane < 16) ? warp * 16 + lane : 1 << 20;     // row of this lane in an M=64 accumulator (or none)
+        const int u = tid;                                           // row of this lane in an M=128 accumulator
+        // accumulator(this lane, column c0 + j) -> dst[j * ld_col] for j < nvalid (dst null: skip); ncols multiple of 16
         auto flush = [&](uint32_t col, int ncols, float* dst, int ld_col, int nvalid) {
             for (int q = 0; q < ncols / 16; ++q) {
                 float v[16];
@@ -770,32 +774,41 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
         };
         auto at = [&](float* base, bool valid, int off) { return (base && valid) ? base + off : (float*)nullptr; };
         const int CIN = G + 16;
-        // dW (out x in) accumulators: lane = output unit, column = input unit
+        // [dW | db] (out x in+1) accumulators, M = 64: lane = output unit, columns 0..63 = input units, column 64 = bias
         flush(COL_WC1, 64, at(g.p[10], t < 64, t * 64), 1, 64);
+        flush(COL_WC1 + 64, 16, at(g.p[11], t < 64, t), 1, 1);
         flush(COL_WT1, 64, at(g.p[2], t < 64, t * 64), 1, 64);
+        flush(COL_WT1 + 64, 16, at(g.p[3], t < 64, t), 1, 1);
         flush(COL_WT0, 64, at(g.p[0], t < 64, t * E), 1, E);
-        // colour layer 1: tile column k' is source column cin_src_col(k'): SH block, then geo block
+        flush(COL_BT0, 16, at(g.p[1], t < 64, t), 1, 1);
+        // colour layer 1: tile column k' is source column cin_src_col(k'): SH block, geo block, then the ones column (31)
         flush(COL_WC0, 16, at(g.p[8], t < 64, t * CIN + G), 1, 16);
-        flush(COL_WC0 + 16, 16, at(g.p[8], t < 64, t * CIN), 1, G);
-        // dW^T (in x out) accumulators: lane = input unit, column = output unit
-        flush(COL_WC2T, 16, at(g.p[12], t < 64, t), 64, 3);
+        {
+            float v[16];
+            umma::ld16(tmem_row + COL_WC0 + 16, v);
+            umma::wait_ld();
+            if (t < 64) {
+#pragma unroll
+                for (int j = 0; j < 15; ++j) if (g.p[8] && j < G && v[j] != 0.0f) atomicAdd(g.p[8] + t * CIN + j, v[j] * inv_scale);
+                if (g.p[9] && v[15] != 0.0f) atomicAdd(g.p[9] + t, v[15] * inv_scale);
+            }
+        }
+        // [dW^T ; db] (in+1 x out) accumulators, M = 128: lane = input unit (lane 64 = bias), column = output unit
+        flush(COL_WC2T, 16, u < 64 ? at(g.p[12], true, u) : (u == 64 ? g.p[13] : (float*)nullptr), u < 64 ? 64 : 1, 3);
         {
             float v[16];
             umma::ld16(tmem_row + COL_WHDT, v);
             umma::wait_ld();
-            if (t < 64) {
+            if (u < 64) {
 #pragma unroll
-                for (int j = 0; j < 15; ++j) if (g.p[6] && j < G && v[j] != 0.0f) atomicAdd(g.p[6] + j * 64 + t, v[j] * inv_scale);
-                if (g.p[4] && v[15] != 0.0f) atomicAdd(g.p[4] + t, v[15] * inv_scale);
+                for (int j = 0; j < 15; ++j) if (g.p[6] && j < G && v[j] != 0.0f) atomicAdd(g.p[6] + j * 64 + u, v[j] * inv_scale);
+                if (g.p[4] && v[15] != 0.0f) atomicAdd(g.p[4] + u, v[15] * inv_scale);
+            } else if (u == 64) {
+#pragma unroll
+                for (int j = 0; j < 15; ++j) if (g.p[7] && j < G && v[j] != 0.0f) atomicAdd(g.p[7] + j, v[j] * inv_scale);
+                if (g.p[5] && v[15] != 0.0f) atomicAdd(g.p[5], v[15] * inv_scale);
             }
         }
-        // bias gradients: every column of a G^T 1 accumulator holds the same sum; take column 0
-        flush(COL_BC2, 16, at(g.p[13], t < 3, t), 1, 1);
-        flush(COL_BC1, 16, at(g.p[11], t < 64, t), 1, 1);
-        flush(COL_BC0, 16, at(g.p[9], t < 64, t), 1, 1);
-        flush(COL_BHD, 16, t == 15 ? g.p[5] : at(g.p[7], t < G, t), 1, 1);
-        flush(COL_BT1, 16, at(g.p[3], t < 64, t), 1, 1);
-        flush(COL_BT0, 16, at(g.p[1], t < 64, t), 1, 1);
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -843,9 +856,15 @@ int launch_bwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride
     const int64_t ntiles = (P + TM - 1) / TM;
     int64_t grid = (ntiles + BNS - 1) / BNS;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
-    ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_field_bwd_mma<E><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
-                                                            (const float4*)d_rgb_sigma, absmax, *g, d_enc);
+    if (g_field_trace && E == 32) {          // the timeline build of the kernel (tools/field_trace.py --bwd)
+        ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_field_bwd_mma<32, true><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
+                                                                       (const float4*)d_rgb_sigma, absmax, *g, d_enc, g_field_trace);
+    } else {
+        ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_field_bwd_mma<E, false><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
+                                                                       (const float4*)d_rgb_sigma, absmax, *g, d_enc, nullptr);
+    }
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }
