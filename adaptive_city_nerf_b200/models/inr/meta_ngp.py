@@ -168,13 +168,18 @@ class MetaNGP(MetaModule):
             return sigma
         return {"sigma": sigma, "geo_feat": self.geo_head(h, params=self.get_subdict(params, "geo_head"))}
 
+    def _use_half(self, device: torch.device) -> bool:
+        """tcgen05 fp16 kernels under autocast -- when the encoding width is one their backward is built for (16 or 32
+        = L*F; its activation tiles fill shared memory).  Wider encodings run the fp32 CUDA kernels instead."""
+        return autocast_half(device) and self.xyz_encoder.out_dim in (16, 32)
+
     def forward(self, x_d: Tensor, params=None) -> Tensor:
         """(...,>=6) [xyz, dir] -> (...,4) [rgb, sigma] (reference :226-241), fused."""
         assert x_d.shape[-1] >= 6, f"Expected (...,6) [xyz,dir], got {x_d.shape}"
         self._check_fused()
         x2 = x_d.reshape(-1, x_d.shape[-1])
         out = ops.ExpertFieldFn.apply(x2, None, None, self.xyz_encoder.hash_table, self.xyz_encoder.grid_spec(),
-                                      self.box6(), autocast_half(x2.device), *self.fused_weights(params))
+                                      self.box6(), self._use_half(x2.device), *self.fused_weights(params))
         return out.view(*x_d.shape[:-1], 4)
 
     def forward_rays(self, rays: Tensor, t_vals: Tensor, params=None) -> Tensor:
@@ -182,7 +187,7 @@ class MetaNGP(MetaModule):
         (N*S,6) point tensor (nerfs/ray_rendering.py:317-319) -> (N,S,4)."""
         self._check_fused()
         out = ops.ExpertFieldFn.apply(None, rays, t_vals, self.xyz_encoder.hash_table, self.xyz_encoder.grid_spec(),
-                                      self.box6(), autocast_half(rays.device), *self.fused_weights(params))
+                                      self.box6(), self._use_half(rays.device), *self.fused_weights(params))
         return out.view(t_vals.shape[0], t_vals.shape[1], 4)
 
     # ------------------------------------------------------------------ optimizer groups
