@@ -185,3 +185,36 @@ def test_field_fp16_backward_zero_and_nonfinite_gradients():
     dy[3, 1] = float("inf")
     g, de = ops.field_bwd(enc, dirs, 3, 1, wt, True, dy, True, [True] * 14)
     assert not torch.isfinite(g[12]).all()          # the bad sample poisons what it touches, as in the reference
+
+
+@pytest.mark.parametrize("E,G,mode", [(16, 7, "points"), (32, 1, "points"), (32, 15, "rays"), (16, 12, "rays")])
+def test_field_fp16_other_widths_and_ray_mode(E, G, mode):
+    """Encoding width 16 / geo width != 15 (runtime G: the colour-input columns are permuted in the kernels), and the
+    ray-indexed direction mode (one direction per S consecutive points) against the per-point mode and the torch
+    restatement."""
+    from adaptive_city_nerf_b200 import ops
+    sd = synth.make_expert_params(11, E=E, G=G, log2T=4)
+    wt = [cu(w) for w in synth.expert_weight_list(sd)]
+    S, N = 48, 211
+    P = N * S
+    gen = torch.Generator(device="cuda").manual_seed(E * 100 + G)
+    enc = (torch.rand(P, E, device="cuda", generator=gen) - 0.5).half()
+    rays = torch.randn(N, 8, device="cuda", generator=gen)
+    dirs_pt = rays[:, 3:6].repeat_interleave(S, dim=0).contiguous()
+    dy = torch.randn(P, 4, device="cuda", generator=gen) * 1e-3
+    if mode == "rays":
+        y = ops.field_fwd(enc, rays[:, 3:], 8, S, wt, half=True)
+        g, de = ops.field_bwd(enc, rays[:, 3:], 8, S, wt, True, dy, True, [True] * 14)
+        y_pt = ops.field_fwd(enc, dirs_pt, 3, 1, wt, half=True)
+        assert torch.equal(y, y_pt)                       # same arithmetic, only the direction addressing differs
+    else:
+        y = ops.field_fwd(enc, dirs_pt, 3, 1, wt, half=True)
+        g, de = ops.field_bwd(enc, dirs_pt, 3, 1, wt, True, dy, True, [True] * 14)
+    y_em, g_em, de_em = _emulate_fp16_field(enc, dirs_pt, wt, dy)
+    assert (y[:, :3] - y_em[:, :3]).abs().max() < 1e-3
+    for key, a, b in zip(synth.EXPERT_KEYS, g, g_em):
+        assert a.shape == b.shape and torch.isfinite(a).all(), key
+        assert _rel_l2(a, b) < 3e-3, (key, _rel_l2(a, b))
+    assert _rel_l2(de, de_em) < 3e-3
+    y32 = ops.field_fwd(enc, dirs_pt, 3, 1, wt, half=False)
+    assert (y[:, :3] - y32[:, :3]).abs().max() < 4e-3
