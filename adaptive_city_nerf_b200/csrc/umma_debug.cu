@@ -131,7 +131,60 @@ __global__ void __launch_bounds__(TM) k_debug_umma_ts(const __half* __restrict__
     if (warp == 0) umma::tmem_dealloc(tmem_base, 128);
 }
 
+// Dispatch-rate probe: `issuers` threads (one per warp, warps 0..issuers-1 = different SM sub-partitions) each issue
+// `nmma` back-to-back MMAs into their own accumulator window, commit and wait, `reps` times; thread 0 reports the
+// average SM cycles per round.  mode 0: A and B from shared memory; 1: A from tensor memory.
+__global__ void __launch_bounds__(TM) k_umma_rate(int mode, int M, int N, int nmma, int reps, int issuers, long long* __restrict__ out)
+{
+    __shared__ __align__(128) uint8_t a_tile[TM * 64 * 2];
+    __shared__ __align__(128) uint8_t w_tile[64 * 64 * 2];
+    __shared__ __align__(8) uint64_t bar[4];
+    __shared__ uint32_t tmem_ptr;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < TM * 64 * 2 / 16; i += TM) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 64 * 64 * 2 / 16; i += TM) reinterpret_cast<uint4*>(w_tile)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { for (int i = 0; i < 4; ++i) umma::mbar_init(&bar[i], 1); umma::fence_mbar_init(); }
+    if (warp == 0) umma::tmem_alloc(&tmem_ptr, 512);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = tmem_ptr;
+    if (warp < issuers && lane == 0) {
+        const uint32_t idesc = umma::make_idesc_f16(M, N);
+        const uint32_t a_addr = umma::smem_u32(a_tile), w_addr = umma::smem_u32(w_tile);
+        const uint32_t d = tmem_base + warp * 128, a_t = d + 64;
+        uint32_t phase = 0;
+        long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            for (int i = 0; i < nmma; ++i) {
+                const int ks = i & 3;
+                const uint64_t db = umma::make_desc(w_addr + ks * 256, 128, 1024);
+                if (mode == 0) umma::mma_f16_ss(d, umma::make_desc(a_addr + ks * 256, 128, 1024), db, idesc, true);
+                else umma::mma_f16_ts(d, a_t + ks * 8, db, idesc, true);
+            }
+            umma::commit(&bar[warp]);
+            umma::mbar_wait(&bar[warp], phase);
+            phase ^= 1u;
+        }
+        long long t1 = clock64();
+        if (blockIdx.x == 0) out[warp] = (t1 - t0) / reps;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
+
+extern "C" int acn_debug_umma_rate(acn_ctx* ctx, int mode, int M, int N, int nmma, int reps, int issuers, long long* out4, acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    ACN_REQUIRE(out4 && (mode == 0 || mode == 1) && (M == 64 || M == 128) && N >= 8 && N <= 64 && N % 8 == 0 && nmma >= 1 && reps >= 1 &&
+                issuers >= 1 && issuers <= 4, ACN_EINVAL, "acn_debug_umma_rate: bad arguments");
+    k_umma_rate<<<ctx->sm_count, TM, 0, (cudaStream_t)stream>>>(mode, M, N, nmma, reps, issuers, out4);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
 
 extern "C" int acn_debug_umma_gemm_ts(acn_ctx* ctx, const void* a_f16, const void* w_f16, int N, int K, float* d, acn_stream stream) {
     ACN_CHECK_CTX(ctx);

@@ -419,6 +419,14 @@ def debug_umma_gemm_ts(a: Tensor, w: Tensor) -> Tensor:
     return d
 
 
+def debug_umma_rate(mode: int, M: int, N: int, nmma: int, reps: int = 200, issuers: int = 1) -> List[int]:
+    """Average SM cycles for `nmma` back-to-back tcgen05.mma + commit + wait, per issuing thread (acn_debug_umma_rate)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = torch.zeros(4, dtype=torch.int64, device=dev)
+    check(lib().acn_debug_umma_rate(ctx(dev), mode, M, N, nmma, reps, issuers, ptr(out), stream(dev)))
+    return out.cpu().tolist()[:issuers]
+
+
 def debug_field_trace(buf: Optional[Tensor]) -> None:
     """Arm (int64 CUDA tensor of 1024 words) or disarm (None) the forward-MLP timeline (acn_debug_field_trace)."""
     dev = buf.device if buf is not None else torch.device("cuda", torch.cuda.current_device())

@@ -186,6 +186,11 @@ int acn_debug_umma_gemm(acn_ctx*, const void* a_f16, const void* w_f16, int N, i
  * the forward MLP kernel's activation chain. */
 int acn_debug_umma_gemm_ts(acn_ctx*, const void* a_f16, const void* w_f16, int N, int K, float* d, acn_stream);
 
+/* Dispatch-rate probe: `issuers` threads each issue `nmma` back-to-back M x N x 16 MMAs (mode 0: operands in shared
+ * memory, 1: A in tensor memory), commit and wait, `reps` times, on every SM; out4[i] = average SM cycles per round of
+ * issuer i on CTA 0 (tools/umma_rate.py). */
+int acn_debug_umma_rate(acn_ctx*, int mode, int M, int N, int nmma, int reps, int issuers, long long* out4, acn_stream);
+
 /* Raw harness: stages two 16-bit matrices as canonical tiles and issues `ksteps` MMAs with
  * host-supplied descriptors, then dumps TMEM lanes 0..127 x ncols.  Used by tools/umma_probe.py to
  * establish MN-major / mixed-dtype / M=64 layouts on hardware. */
