@@ -4,7 +4,7 @@ The reference is single-process (nerf_runner.py:52-56); its only collective is t
 offline mask script (scripts/create_clusters.py:898-932).  Everything here is therefore new capability, laid over
 `torch.distributed` (NCCL over NVLink 5 / NVSwitch on the GPUs, gloo in the CPU tests):
 
-* expert sharding (`ExpertShardedContainer`): rank r owns experts [r*m, (r+1)*m).  Rays stay data parallel on their
+* expert sharding (`ExpertShardedContainer`): expert k lives on rank k % world.  Rays stay data parallel on their
   home rank (clip, sample, route, composite); routed samples travel to the owner of their expert(s) with ONE
   variable-size all-to-all each way -- 24 B/sample out ([xyz, dir]), 16 B/sample back ([rgb, sigma]) -- and the
   backward mirrors it (dL/d[rgb, sigma] out, nothing back: positions carry no gradient).  Overlap samples inside
@@ -28,16 +28,6 @@ from . import ops
 
 
 # --------------------------------------------------------------------------------------------- exchange primitives
-def exchange_counts(send_counts: Tensor, group=None) -> Tensor:
-    """send_counts (world, m) int64 on any device: rows I send to each (rank, local expert) -> the (world, m) counts
-    each rank sends ME.  One tiny all-to-all; the only host-visible quantity of a routed step."""
-    world = dist.get_world_size(group)
-    assert send_counts.dim() == 2 and send_counts.shape[0] == world
-    recv = torch.empty_like(send_counts)
-    dist.all_to_all_single(recv, send_counts.contiguous(), group=group)
-    return recv
-
-
 class _AllToAllRows(torch.autograd.Function):
     """Variable-size row exchange y = all_to_all(x) with autograd: the backward is the same exchange with the
     splits swapped.  x: (sum(send_splits), C) grouped by destination rank."""
@@ -64,59 +54,64 @@ def all_to_all_rows(x: Tensor, send_splits: Sequence[int], recv_splits: Sequence
 
 
 def expert_owner_layout(K: int, world: int) -> int:
-    """Experts per rank m for a contiguous block layout (rank r owns experts [r*m, (r+1)*m)); K must divide."""
+    """Experts per rank m.  Ownership is INTERLEAVED: expert k lives on rank k % world as its local expert k // world,
+    so neighbouring Voronoi cells -- the ones a single camera view sees -- sit on different GPUs."""
     if K % world != 0:
         raise ValueError(f"{K} experts do not shard evenly over {world} ranks")
     return K // world
 
 
-def regroup_by_expert(recv_counts: Tensor) -> Tuple[List[List[Tuple[int, int]]], List[int]]:
-    """recv_counts (world, m): the receive buffer is ordered by source rank, then local expert.  -> for each local
-    expert the list of (start, length) segments that belong to it, and the per-source-rank totals (recv splits)."""
-    world, m = recv_counts.shape
-    rc = recv_counts.tolist()
-    segs: List[List[Tuple[int, int]]] = [[] for _ in range(m)]
-    pos = 0
-    for r in range(world):
+def expert_send_order(K: int, world: int) -> List[int]:
+    """Global expert ids in the order their rows must be laid out for the exchange: destination rank major, local
+    expert minor."""
+    m = expert_owner_layout(K, world)
+    return [e * world + r for r in range(world) for e in range(m)]
+
+
+def gather_counts(counts_dev: Tensor, group=None) -> Tensor:
+    """counts (K,) on the device -> (world, K) host matrix of every rank's per-expert row counts: one collective and
+    ONE device-to-host copy give both the send and the receive splits of a routed step."""
+    world = dist.get_world_size(group)
+    c = counts_dev.to(torch.int64).contiguous()
+    parts = [torch.empty_like(c) for _ in range(world)]
+    dist.all_gather(parts, c, group=group)
+    return torch.stack(parts).cpu()
+
+
+def exchange_segments(all_counts: Tensor, rank: int) -> Tuple[List[int], List[int], List[Tuple[int, int, int]]]:
+    """all_counts (world, K) -> (send_splits, recv_splits, segments) for `rank`.  The receive buffer is ordered by
+    source rank, then local expert; segments lists (local expert, start, length) in buffer order."""
+    world, K = all_counts.shape
+    m = expert_owner_layout(K, world)
+    ac = all_counts.tolist()
+    send_splits = [int(sum(ac[rank][e * world + r] for e in range(m))) for r in range(world)]
+    recv_splits, segs, pos = [], [], 0
+    for src in range(world):
+        tot = 0
         for e in range(m):
-            n = int(rc[r][e])
-            if n:
-                segs[e].append((pos, n))
+            n = int(ac[src][e * world + rank])
+            segs.append((e, pos, n))
             pos += n
-    return segs, [int(sum(row)) for row in rc]
+            tot += n
+        recv_splits.append(tot)
+    return send_splits, recv_splits, segs
 
 
-def routed_exchange(xd: Tensor, counts: Tensor, local_fields, group=None) -> Tensor:
+def routed_exchange(xd: Tensor, all_counts: Tensor, local_fields, group=None) -> Tensor:
     """The sample round trip of one routed step.
 
-    xd (total, C>=6): routed rows grouped by GLOBAL expert id (expert-major, as `ops.bucket_points` writes them);
-    counts (K,) host int tensor: rows per expert; local_fields: m callables, local_fields[e](rows (M,C)) -> (M,4),
-    the experts this rank owns.  -> y (total, 4) in the order of `xd`, differentiable w.r.t. whatever the owners'
-    fields depend on (their gradients arrive through the backward all-to-all)."""
-    world = dist.get_world_size(group)
-    K = counts.numel()
-    m = expert_owner_layout(K, world)
-    assert len(local_fields) == m
-    send_counts = counts.reshape(world, m).to(torch.int64)
-    dev_counts = send_counts.to(xd.device) if dist.get_backend(group) == "nccl" else send_counts
-    recv_counts = exchange_counts(dev_counts, group).cpu()
-    send_splits = [int(v) for v in send_counts.sum(1).tolist()]
-    segs, recv_splits = regroup_by_expert(recv_counts)
+    xd (total, C>=6): this rank's routed rows laid out in `expert_send_order`; all_counts (world, K) host matrix from
+    `gather_counts`; local_fields: m callables, local_fields[e](rows (M,C)) -> (M,4), the experts this rank owns.
+    -> y (total, 4) in the order of `xd`, differentiable w.r.t. whatever the owners' fields depend on (their
+    gradients arrive through the backward all-to-all).  Every (source rank, expert) segment of the receive buffer is
+    evaluated where it lies -- no gather / scatter copies on either pass."""
+    rank = dist.get_rank(group)
+    send_splits, recv_splits, segs = exchange_segments(all_counts, rank)
+    assert len(local_fields) == expert_owner_layout(all_counts.shape[1], all_counts.shape[0])
     with torch.no_grad():                                   # positions / directions carry no gradient
         rows = all_to_all_rows(xd, send_splits, recv_splits, group)
-    M = rows.shape[0]
-    if m == 1 and M:
-        y_recv = local_fields[0](rows).float()
-    else:
-        y_recv = rows.new_zeros((M, 4), dtype=torch.float32)
-        pieces, index = [], []
-        for e, field in enumerate(local_fields):
-            if segs[e]:
-                idx = torch.cat([torch.arange(s, s + n, device=rows.device) for s, n in segs[e]])
-                pieces.append(field(rows[idx]).float())
-                index.append(idx)
-        if pieces:
-            y_recv = y_recv.index_copy(0, torch.cat(index), torch.cat(pieces))
+    pieces = [local_fields[e](rows[s:s + n]).float() if n else rows.new_zeros((0, 4), dtype=torch.float32) for e, s, n in segs]
+    y_recv = pieces[0] if len(pieces) == 1 else torch.cat(pieces)
     # The return trip's backward is a collective: every rank must run it, also one that received nothing or owns no
     # trainable parameter -- give autograd a reason to.
     if torch.is_grad_enabled() and not y_recv.requires_grad:
@@ -142,7 +137,7 @@ class ExpertShardedContainer(torch.nn.Module):
         self.rank = dist.get_rank(group)
         self.K = len(container.submodules)
         self.m = expert_owner_layout(self.K, self.world)
-        self.local_ids = list(range(self.rank * self.m, (self.rank + 1) * self.m))
+        self.local_ids = [e * self.world + self.rank for e in range(self.m)]          # interleaved ownership
         self.use_bg_nerf = container.use_bg_nerf
         self.use_occ = False
 
@@ -169,7 +164,7 @@ class ExpertShardedContainer(torch.nn.Module):
     def forward(self, x: Tensor, params=None, active_module: Optional[int] = None) -> Tensor:
         if active_module is not None:
             if active_module not in self.local_ids:
-                raise RuntimeError(f"expert {active_module} is owned by rank {active_module // self.m}, not {self.rank}")
+                raise RuntimeError(f"expert {active_module} is owned by rank {active_module % self.world}, not {self.rank}")
             return self.inner(x, params=params, active_module=active_module)
         c = self.inner
         N = x.shape[0]
@@ -177,12 +172,16 @@ class ExpertShardedContainer(torch.nn.Module):
         sub_params = c._sub_params(params)
         with torch.no_grad():
             w, hard, counts = ops.route_points(id6, c.centroids, 2 if c.cluster_2d else 3, c.boundary_margin, want_counts=True)
-            cnt = counts.cpu().to(torch.int64)
+            all_counts = gather_counts(counts, self.group)              # the step's one host read
+            cnt = all_counts[self.rank]
             offsets = torch.zeros(self.K, dtype=torch.int32)
-            offsets[1:] = torch.cumsum(cnt, 0)[:-1].to(torch.int32)
-            sel, xd, wsel = ops.bucket_points(id6, w, hard, self.K, offsets.to(x.device), int(cnt.sum()))
+            pos = 0
+            for k in expert_send_order(self.K, self.world):             # rows grouped by destination rank, then expert
+                offsets[k] = pos
+                pos += int(cnt[k])
+            sel, xd, wsel = ops.bucket_points(id6, w, hard, self.K, offsets.to(x.device), pos)
         fields = [(lambda rows, k=k: c.submodules[k](rows, params=sub_params[k])) for k in self.local_ids]
-        y = routed_exchange(xd, cnt, fields, self.group)
+        y = routed_exchange(xd, all_counts, fields, self.group)
         out = torch.zeros(N, 4, dtype=torch.float32, device=x.device) + 0.0 * y.sum()   # ties y in even if unused
         off = offsets.tolist()
         for k in range(self.K):                               # blend in expert order, like the reference

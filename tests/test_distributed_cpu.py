@@ -48,11 +48,16 @@ class _ToyExpert(torch.nn.Module):
         return rows[:, :6] @ self.w
 
 
-def _toy_problem(rank, K=4, N=257):
+def _toy_problem(rank, world, K=4, N=257):
+    """Rows of one rank, bucketed the way ExpertShardedContainer does it on the device: grouped by destination rank,
+    then by that rank's local expert (expert k lives on rank k % world)."""
+    from adaptive_city_nerf_b200 import distributed as D
     g = torch.Generator().manual_seed(7 + rank)
     x = torch.randn(N, 6, generator=g)
     hard = torch.randint(0, K, (N,), generator=g)
-    order = torch.argsort(hard, stable=True)            # what ops.bucket_points does on the device
+    pos = torch.empty(K, dtype=torch.long)
+    pos[torch.tensor(D.expert_send_order(K, world))] = torch.arange(K)
+    order = torch.argsort(pos[hard], stable=True)
     counts = torch.bincount(hard, minlength=K)
     return x, hard, order, counts
 
@@ -62,22 +67,24 @@ def _exchange_worker(rank, world):
     K = 4
     m = D.expert_owner_layout(K, world)
     experts = [_ToyExpert(k) for k in range(K)]                       # same seeds on every rank
-    x, hard, order, counts = _toy_problem(rank, K)
+    x, hard, order, counts = _toy_problem(rank, world, K)
     xd = x[order]
-    local = [experts[k] for k in range(rank * m, (rank + 1) * m)]
-    y = D.routed_exchange(xd, counts, local)
-    ref = torch.cat([experts[k](xd[hard[order] == k]) for k in range(K)])
+    owned = [e * world + rank for e in range(m)]
+    local = [experts[k] for k in owned]
+    all_counts = D.gather_counts(counts)
+    y = D.routed_exchange(xd, all_counts, local)
+    ref = torch.cat([experts[k](xd[hard[order] == k]) for k in D.expert_send_order(K, world)])
     err = float((y - ref).abs().max())
     # gradient of sum(y * c) w.r.t. every expert: owners receive the other rank's contribution through the backward exchange
     c = torch.arange(y.numel(), dtype=torch.float32).view_as(y) / y.numel()
     (y * c).sum().backward()
-    grads = {k: experts[k].w.grad.clone() for k in range(rank * m, (rank + 1) * m)}
+    grads = {k: experts[k].w.grad.clone() for k in owned}
     # reference: both ranks' data on one process
     full = [_ToyExpert(k) for k in range(K)]
     tot = 0.0
     for r in range(world):
-        xr, hr, orr, _ = _toy_problem(r, K)
-        yr = torch.cat([full[k](xr[orr][hr[orr] == k]) for k in range(K)])
+        xr, hr, orr, _ = _toy_problem(r, world, K)
+        yr = torch.cat([full[k](xr[orr][hr[orr] == k]) for k in D.expert_send_order(K, world)])
         cr = torch.arange(yr.numel(), dtype=torch.float32).view_as(yr) / yr.numel()
         tot = tot + (yr * cr).sum()
     tot.backward()
@@ -98,7 +105,7 @@ def _empty_worker(rank, world):
     n = 33 if rank == 0 else 0
     xd = torch.randn(n, 6)
     counts = torch.tensor([n, 0])
-    y = D.routed_exchange(xd, counts, [experts[rank]])
+    y = D.routed_exchange(xd, D.gather_counts(counts), [experts[rank]])
     (y.sum() * 1.0).backward()
     return tuple(y.shape), experts[rank].w.grad is not None
 
@@ -136,11 +143,16 @@ def test_allreduce_grads_clip_and_aabbs():
         assert mins == [[0.0, 0.0, -1.0]] and maxs == [[2.0, 1.0, 1.0]] and cnt == 3
 
 
-def test_regroup_by_expert_layout():
+def test_exchange_segments_layout():
     from adaptive_city_nerf_b200 import distributed as D
-    segs, splits = D.regroup_by_expert(torch.tensor([[2, 0], [3, 4], [0, 1]]))
-    assert splits == [2, 7, 1]
-    assert segs == [[(0, 2), (2, 3)], [(5, 4), (9, 1)]]
+    assert D.expert_send_order(4, 2) == [0, 2, 1, 3]                 # rank 0 owns {0, 2}, rank 1 owns {1, 3}
+    all_counts = torch.tensor([[5, 1, 0, 2], [3, 4, 7, 0]])          # rows (rank) x experts
+    send, recv, segs = D.exchange_segments(all_counts, rank=0)
+    assert send == [5 + 0, 1 + 2]                                     # to rank 0: experts 0, 2; to rank 1: experts 1, 3
+    assert recv == [5 + 0, 3 + 7]                                     # from rank 0 / rank 1, my experts 0 and 2
+    assert segs == [(0, 0, 5), (1, 5, 0), (0, 5, 3), (1, 8, 7)]       # (local expert, start, length) in buffer order
+    send1, recv1, _ = D.exchange_segments(all_counts, rank=1)
+    assert send1 == [3 + 7, 4 + 0] and recv1 == [1 + 2, 4 + 0]
     with pytest.raises(ValueError):
         D.expert_owner_layout(6, 4)
     assert D.expert_owner_layout(8, 4) == 2

@@ -89,5 +89,5 @@ def test_expert_sharded_container_matches_single_process(margin):
         err, gerr, n_owned, total, ref_total = ret[rank]
         assert err < 1e-5, (rank, err)                      # same kernels, same order of blending
         assert gerr < 1e-4, (rank, gerr)                    # float atomics reorder sums; nothing else differs
-        assert n_owned == 2 * 15                            # two experts' 14 MLP tensors + table each
+        assert n_owned == 2 * 15                            # two experts' 14 MLP tensors + table each (experts r and r + 2)
         assert abs(total - ref_total) / ref_total < 1e-4    # the sharded global norm is the global norm
