@@ -150,6 +150,45 @@ __global__ void __launch_bounds__(256) k_bucket_points(
     }
 }
 
+// Fused dispatch for expert sharding: the same bucketing, but the routed [xyz, dir] row of expert k is stored straight
+// into the receive buffer of the GPU that owns k -- row_base[k] is that buffer's address as mapped into this process
+// (NVLink peer memory, or local memory for the experts this rank owns), row_off[k] the first row reserved there for
+// (this source rank, expert k).  sel / w_out stay local.  The dispatch half of the all-to-all is therefore the
+// kernel's own store stream; no staging copy, no NCCL send.
+__global__ void __launch_bounds__(256) k_dispatch_points(
+    const float* __restrict__ id6, int64_t P, const float* __restrict__ weights, const int32_t* __restrict__ hard,
+    int K, const int32_t* __restrict__ offsets, int32_t* __restrict__ cursor, int32_t* __restrict__ sel,
+    float* __restrict__ w_out, const unsigned long long* __restrict__ row_base, const int32_t* __restrict__ row_off)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = p < P;
+    const int lane = threadIdx.x & 31;
+    const int h = (on && hard) ? hard[p] : -1;
+    float2 r0 = make_float2(0.f, 0.f), r1 = r0, r2 = r0;
+    if (on) {
+        const float2* src = reinterpret_cast<const float2*>(id6 + p * 6);
+        r0 = __ldg(src); r1 = __ldg(src + 1); r2 = __ldg(src + 2);
+    }
+    for (int k = 0; k < K; ++k) {
+        float w = weights ? (on ? weights[p * K + k] : 0.0f) : (h == k ? 1.0f : 0.0f);
+        bool in = on && w > 0.0f;
+        unsigned m = __ballot_sync(FULL, in);
+        if (!m) continue;
+        int base = 0;
+        int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(cursor + k, __popc(m));
+        base = __shfl_sync(FULL, base, leader);
+        if (in) {
+            const int idx = base + __popc(m & ((1u << lane) - 1u));
+            const int slot = __ldg(offsets + k) + idx;
+            sel[slot] = (int32_t)p;
+            w_out[slot] = w;
+            float2* dst = reinterpret_cast<float2*>(__ldg(row_base + k)) + ((size_t)__ldg(row_off + k) + idx) * 3;
+            dst[0] = r0; dst[1] = r1; dst[2] = r2;
+        }
+    }
+}
+
 __global__ void k_blend_add(const float4* __restrict__ y, const float* __restrict__ w, const int32_t* __restrict__ sel,
                             int64_t M, float4* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,6 +263,22 @@ extern "C" int acn_bucket_points(acn_ctx* ctx, const float* id6, int64_t P, cons
     if (P == 0) return ACN_OK;
     k_bucket_points<<<acn_grid_1d(P, 256), 256, 0, (cudaStream_t)stream>>>(id6, P, weights_or_null, hard_or_null, K, offsets,
                                                                            cursor, sel, xd_out, w_out);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
+
+extern "C" int acn_dispatch_points(acn_ctx* ctx, const float* id6, int64_t P, const float* weights_or_null,
+                                   const int32_t* hard_or_null, int K, const int32_t* offsets, int32_t* cursor, int32_t* sel,
+                                   float* w_out, const uint64_t* row_base, const int32_t* row_off, acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    ACN_REQUIRE(P >= 0 && K >= 1, ACN_EINVAL, "acn_dispatch_points: bad arguments");
+    ACN_REQUIRE((weights_or_null != nullptr) != (hard_or_null != nullptr), ACN_EINVAL,
+                "acn_dispatch_points: exactly one of weights / hard must be given");
+    ACN_REQUIRE(offsets && cursor && sel && w_out && row_base && row_off, ACN_EINVAL, "acn_dispatch_points: null buffer");
+    if (P == 0) return ACN_OK;
+    ACN_REQUIRE(id6 && ((uintptr_t)id6 & 7) == 0, ACN_EINVAL, "acn_dispatch_points: id6 null or not 8-byte aligned");
+    k_dispatch_points<<<acn_grid_1d(P, 256), 256, 0, (cudaStream_t)stream>>>(id6, P, weights_or_null, hard_or_null, K, offsets, cursor,
+                                                                             sel, w_out, (const unsigned long long*)row_base, row_off);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }

@@ -119,6 +119,69 @@ def routed_exchange(xd: Tensor, all_counts: Tensor, local_fields, group=None) ->
     return all_to_all_rows(y_recv, recv_splits, send_splits, group)
 
 
+# --------------------------------------------------------------------------------------------- peer-memory exchange
+class PeerExchange:
+    """Symmetric (peer-mapped) buffers for the routed exchange of one rank group: every rank allocates the same three
+    buffers -- rows (cap,6), y (cap,4), dy (cap,4) fp32 -- and maps everybody else's over NVLink
+    (torch.distributed._symmetric_memory).  The dispatch kernel stores routed rows straight into the owners' `rows`;
+    the blend kernel loads the owners' `y` straight out of peer memory; the blend backward stores dL/dy straight into
+    the owners' `dy`.  Cross-GPU ordering is a device-side barrier on the stream (signal pads), no host involvement."""
+
+    def __init__(self, cap_rows: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.cap = int(cap_rows)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.rows = symm.empty((self.cap, 6), dtype=torch.float32, device=device)
+        self.y = symm.empty((self.cap, 4), dtype=torch.float32, device=device)
+        self.dy = symm.empty((self.cap, 4), dtype=torch.float32, device=device)
+        self.h_rows = symm.rendezvous(self.rows, self.group)
+        self.h_y = symm.rendezvous(self.y, self.group)
+        self.h_dy = symm.rendezvous(self.dy, self.group)
+        self.rows_ptrs = [int(p) for p in self.h_rows.buffer_ptrs]
+
+    def peer_y(self, r: int) -> Tensor:
+        return self.y if r == self.rank else self.h_y.get_buffer(r, (self.cap, 4), torch.float32)
+
+    def peer_dy(self, r: int) -> Tensor:
+        return self.dy if r == self.rank else self.h_dy.get_buffer(r, (self.cap, 4), torch.float32)
+
+
+class _PeerCombine(torch.autograd.Function):
+    """out[sel] += w * y over all experts, y read from the owners' symmetric buffers; backward stores w * dL/dout[sel]
+    into the owners' dy buffers and hands the owner ITS dy as the gradient of what it put into y."""
+
+    @staticmethod
+    def forward(ctx, y_local: Tensor, px: "PeerExchange", M: int, plan, sel: Tensor, wsel: Tensor, N: int):
+        # plan: list of (k, owner, local_off, remote_off, n) in expert order
+        if M:
+            px.y[:M].copy_(y_local)
+        px.h_y.barrier()                                     # every owner's y is complete and visible
+        out = torch.zeros(N, 4, dtype=torch.float32, device=sel.device)
+        for k, owner, lo, ro, n in plan:                     # blend in expert order, like the reference
+            if n:
+                yk = px.peer_y(owner)[ro:ro + n]
+                ops.check(ops.lib().acn_blend_add(ops.ctx(out.device), ops.ptr(yk), ops.ptr(wsel[lo:lo + n]), ops.ptr(sel[lo:lo + n]), n,
+                                                  ops.ptr(out), ops.stream(out.device)))
+        ctx.px, ctx.M, ctx.plan = px, M, plan
+        ctx.save_for_backward(sel, wsel)
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        px, M, plan = ctx.px, ctx.M, ctx.plan
+        sel, wsel = ctx.saved_tensors
+        g = g.contiguous()
+        px.h_dy.barrier()                                    # nobody is still reading dy from the previous use
+        for k, owner, lo, ro, n in plan:
+            if n:
+                dyk = px.peer_dy(owner)[ro:ro + n]
+                ops.check(ops.lib().acn_blend_bwd(ops.ctx(g.device), ops.ptr(g), ops.ptr(wsel[lo:lo + n]), ops.ptr(sel[lo:lo + n]), n,
+                                                  ops.ptr(dyk), ops.stream(g.device)))
+        px.h_dy.barrier()                                    # every home rank's dL/dy has landed in my dy
+        return px.dy[:M].clone(), None, None, None, None, None, None
+
+
 # --------------------------------------------------------------------------------------------- expert sharding
 class ExpertShardedContainer(torch.nn.Module):
     """A `MetaContainer` whose experts live on different ranks.  Built from a full container description; every
@@ -129,10 +192,15 @@ class ExpertShardedContainer(torch.nn.Module):
         render via nerfs.ray_rendering.render_rays(model, rays, ..., active_module=None) as usual
     """
 
-    def __init__(self, container, group=None):
+    def __init__(self, container, group=None, peer_rows: int = 0):
+        """peer_rows > 0 switches the sample exchange from NCCL all-to-all to kernels that store to / load from peer
+        memory directly (`PeerExchange` with that many rows of capacity per rank; a step that would overflow it falls
+        back to NCCL on every rank alike)."""
         super().__init__()
         self.inner = container
         self.group = group
+        self._peer_rows = int(peer_rows)
+        self._px = None
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.K = len(container.submodules)
@@ -179,8 +247,12 @@ class ExpertShardedContainer(torch.nn.Module):
             for k in expert_send_order(self.K, self.world):             # rows grouped by destination rank, then expert
                 offsets[k] = pos
                 pos += int(cnt[k])
-            sel, xd, wsel = ops.bucket_points(id6, w, hard, self.K, offsets.to(x.device), pos)
+            use_peer = self._peer_rows > 0 and int(all_counts.sum(0).reshape(self.m, self.world).sum(0).max()) <= self._peer_rows
+            if not use_peer:
+                sel, xd, wsel = ops.bucket_points(id6, w, hard, self.K, offsets.to(x.device), pos)
         fields = [(lambda rows, k=k: c.submodules[k](rows, params=sub_params[k])) for k in self.local_ids]
+        if use_peer:
+            return self._forward_peer(id6, w, hard, all_counts, cnt, offsets, pos, fields, N)
         y = routed_exchange(xd, all_counts, fields, self.group)
         out = torch.zeros(N, 4, dtype=torch.float32, device=x.device) + 0.0 * y.sum()   # ties y in even if unused
         off = offsets.tolist()
@@ -190,6 +262,33 @@ class ExpertShardedContainer(torch.nn.Module):
                 sl = slice(off[k], off[k] + n)
                 out = ops.BlendFn.apply(out, y[sl], wsel[sl], sel[sl])
         return out
+
+    def _forward_peer(self, id6, w, hard, all_counts, cnt, offsets, total, fields, N):
+        """The routed step over peer memory: dispatch kernel -> barrier -> owners' fields -> barrier -> blend from peers."""
+        dev = id6.device
+        if self._px is None:
+            self._px = PeerExchange(self._peer_rows, dev, self.group)
+        px, W, m = self._px, self.world, self.m
+        ac = all_counts.tolist()
+        # first row of (source rank src, expert k) in the receive buffer of k's owner: buffer order is (src, local expert)
+        def remote_off(src, k):
+            owner, e = k % W, k // W
+            return sum(ac[s][ee * W + owner] for s in range(src) for ee in range(m)) + sum(ac[src][ee * W + owner] for ee in range(e))
+        plan = [(k, k % W, int(offsets[k]), remote_off(self.rank, k), int(cnt[k])) for k in range(self.K)]
+        with torch.no_grad():
+            row_base = torch.tensor([px.rows_ptrs[k % W] for k in range(self.K)], dtype=torch.int64, device=dev)
+            row_off = torch.tensor([p[3] for p in plan], dtype=torch.int32, device=dev)
+            px.h_rows.barrier()                               # the owners are done with the previous contents of `rows`
+            sel, wsel = ops.dispatch_points(id6, w, hard, self.K, offsets.to(dev), total, row_base, row_off)
+            px.h_rows.barrier()                               # every rank's rows have landed in every owner
+            _, recv_splits, segs = exchange_segments(all_counts, self.rank)
+            M = sum(recv_splits)
+            rows = px.rows[:M].clone()                        # the fields keep their input for the backward; free the buffer
+        pieces = [fields[e](rows[s:s + n]).float() if n else rows.new_zeros((0, 4)) for e, s, n in segs]
+        y_local = pieces[0] if len(pieces) == 1 else torch.cat(pieces)
+        if torch.is_grad_enabled() and not y_local.requires_grad:
+            y_local = y_local.detach().requires_grad_()       # the combine's backward is collective: every rank must run it
+        return _PeerCombine.apply(y_local, px, M, plan, sel, wsel, N)
 
 
 # --------------------------------------------------------------------------------------------- gradient plumbing

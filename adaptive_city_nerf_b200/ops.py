@@ -378,6 +378,20 @@ def bucket_points(id6: Tensor, weights: Optional[Tensor], hard: Optional[Tensor]
     return sel, xd, w
 
 
+def dispatch_points(id6: Tensor, weights: Optional[Tensor], hard: Optional[Tensor], K: int, offsets: Tensor, total: int,
+                    row_base: Tensor, row_off: Tensor):
+    """bucket_points whose [xyz,dir] rows are stored into per-expert destination buffers (peer memory): row_base (K,)
+    int64 device addresses, row_off (K,) int32 first rows.  -> sel (total,) int32, w (total,) local."""
+    dev = id6.device
+    sel = torch.empty(total, dtype=torch.int32, device=dev)
+    w = torch.empty(total, dtype=torch.float32, device=dev)
+    cursor = torch.zeros(K, dtype=torch.int32, device=dev)
+    assert row_base.dtype == torch.int64 and row_off.dtype == torch.int32 and row_base.numel() == K and row_off.numel() == K
+    check(lib().acn_dispatch_points(ctx(dev), ptr(id6), id6.shape[0], ptr(weights), ptr(hard), K, ptr(offsets), ptr(cursor), ptr(sel),
+                                    ptr(w), ptr(row_base), ptr(row_off), stream(dev)))
+    return sel, w
+
+
 class BlendFn(torch.autograd.Function):
     """out[sel[i]] += y[i] * w[i] (models/inr/meta_container.py:321 index_add_ / :336 index_copy_)
     for one expert's routed rows; `out` is threaded through so experts accumulate in k order."""

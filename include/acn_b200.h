@@ -168,7 +168,17 @@ int acn_bucket_points(acn_ctx*, const float* id6, int64_t P, const float* weight
                       const int32_t* hard_or_null, int K, const int32_t* offsets, int32_t* cursor,
                       int32_t* sel, float* xd_out, float* w_out, acn_stream);
 
-/* out[sel[i]] += y[i] * w[i]  (index_add_, meta_container.py:321) over M routed rows of 4. */
+/* Expert sharding, fused dispatch: acn_bucket_points whose [xyz,dir] rows go straight into the owning GPU's receive
+ * buffer.  row_base (K) holds, per expert, that buffer's DEVICE ADDRESS as mapped into this process (peer memory over
+ * NVLink, e.g. torch symmetric memory; local memory for experts this rank owns) and row_off (K) the first row reserved
+ * there for (this source rank, expert k); rows are 6 floats, 8-byte aligned.  sel / w_out are local, as above.  The
+ * caller orders the stores against the owner's reads with a cross-GPU barrier on the same stream.  There is no
+ * reference counterpart (the reference is single-GPU, meta_container.py:306-337). */
+int acn_dispatch_points(acn_ctx*, const float* id6, int64_t P, const float* weights_or_null,
+                        const int32_t* hard_or_null, int K, const int32_t* offsets, int32_t* cursor,
+                        int32_t* sel, float* w_out, const uint64_t* row_base, const int32_t* row_off, acn_stream);
+
+/* out[sel[i]] += y[i] * w[i]  (index_add_, meta_container.py:321) over M routed rows of 4.  y may be peer memory. */
 int acn_blend_add(acn_ctx*, const float* y, const float* w, const int32_t* sel, int64_t M,
                   float* out, acn_stream);
 /* d_y[i] = d_out[sel[i]] * w[i] */

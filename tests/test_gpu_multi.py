@@ -35,7 +35,7 @@ def _rays(rank, dev, n=3000):
     return rays[valid].contiguous()
 
 
-def _worker(rank, world, port, margin, ret):
+def _worker(rank, world, port, margin, peer_rows, ret):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -57,7 +57,7 @@ def _worker(rank, world, port, margin, ret):
         ref_grads = {n: p.grad.clone() for n, p in full.named_parameters() if p.grad is not None}
         full.zero_grad(set_to_none=True)
         # sharded: this rank's rays only
-        model = ExpertShardedContainer(full).shard_().eval()
+        model = ExpertShardedContainer(full, peer_rows=peer_rows).shard_().eval()
         mine = _rays(rank, dev)
         rgb, dep, _, _ = render_rays(model, mine, ray_samples=S, active_module=None)
         err = float((rgb.detach() - ref_rgb[rank]).abs().max())
@@ -79,12 +79,14 @@ def _worker(rank, world, port, margin, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("margin", [1.05, 1.0])
-def test_expert_sharded_container_matches_single_process(margin):
+@pytest.mark.parametrize("margin,peer_rows", [(1.05, 0), (1.0, 0), (1.05, 1 << 18), (1.0, 1 << 18), (1.05, 1000)])
+def test_expert_sharded_container_matches_single_process(margin, peer_rows):
+    """peer_rows = 0: NCCL all-to-all exchange; 2^18: kernels storing to / loading from peer memory over NVLink
+    (symmetric memory); 1000: a capacity the step overflows, i.e. the consistent fall-back to NCCL."""
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), margin, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), margin, peer_rows, ret), nprocs=2, join=True)
     for rank in range(2):
         err, gerr, n_owned, total, ref_total = ret[rank]
         assert err < 1e-5, (rank, err)                      # same kernels, same order of blending

@@ -33,7 +33,8 @@ box = SceneBox(T(AABB).to(dev))
 full = MetaContainer(num_submodules=8, centroids=T(cen), aabb=T(AABB), boundary_margin=1.05, cluster_2d=True, use_bg_nerf=True,
                      expert_box_list=[box] * 8, hidden=64, sigma_depth=2, color_depth=2, color_hidden=64, dir_encoding="spherical",
                      hash_enc_conf=CONF, occ_conf={"use_occ": False}).to(dev)
-model = ExpertShardedContainer(full).shard_() if world > 1 else full
+peer = "--peer" in sys.argv
+model = ExpertShardedContainer(full, peer_rows=(1 << 25) if peer else 0).shard_() if world > 1 else full
 torch.cuda.empty_cache()
 H, W, S = 1080, 1920, 64
 cam = synth.nadir_rays(0, 1, H=H, W=W, f=1481.0 * W / 2048)[0]
@@ -101,5 +102,6 @@ if rank == 0:
     what = (f"routed training step, 2^18 rays x {S} total" if train else f"one {W}x{H} frame, S={S}, eval fp16")
     total = (1 << 18) if train else rays.shape[0]
     print(json.dumps({"config": f"8 experts (2x4 grid, margin 1.05, bg head) sharded over {world} B200, {what}", "n_gpus": world,
+                      "exchange": ("peer memory (fused dispatch / combine kernels)" if peer and world > 1 else "nccl all-to-all") if world > 1 else "none",
                       "ms": round(float(ms), 2), "samples_per_s": total * S / (float(ms) * 1e-3)}))
 dist.destroy_process_group()
