@@ -174,3 +174,34 @@ def test_training_psnr_matches_reference(golden):
         rgb, *_ = render_rays(m, all_rays[:2048], ray_samples=S, active_module=0)
     final = -10.0 * np.log10(float(torch.nn.functional.mse_loss(rgb, gt[:2048])) + 1e-24)
     assert abs(final - float(g["final_eval_psnr"])) < 0.1
+
+
+def test_graphed_task_adapt_matches_eager(golden):
+    """The inner loop (meta_core.py:14-68, first order) replayed as one CUDA graph gives the weights the launch-by-launch
+    loop gives, task after task, and its fast weights drive a first-order outer gradient."""
+    from adaptive_city_nerf_b200.meta import GraphedTaskAdapt, accumulate_first_order_grads, task_adapt_eager
+    from adaptive_city_nerf_b200.nerfs.ray_rendering import render_rays
+    m = make_container(1, np.zeros((1, 3), F32), [synth.AABB_GLOBAL], 1.0, False, seed0=500).eval()   # eval: no jitter
+    ex = m.submodules[0]
+    N, S = 1500, 24
+    kw = dict(active_module=0, ray_samples=S, iterations=4, inner_lr=5e-2)
+    adapt = GraphedTaskAdapt(m, n_rays=N, **kw)
+    for task in range(3):
+        o, d = synth.random_rays_in_box(600 + task, N)
+        rays = torch.cat([cu(o), cu(d), torch.zeros(N, 1, device="cuda"), torch.full((N, 1), 0.4, device="cuda")], dim=1)
+        rgbs = torch.rand(N, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(task))
+        fast_g, losses_g = adapt(rays, rgbs)
+        fast_e, losses_e = task_adapt_eager(m, rays, rgbs, **kw)
+        for k in fast_e:
+            assert torch.allclose(fast_g[k], fast_e[k].detach(), rtol=0, atol=1e-6), (task, k)
+        assert abs(float(losses_g[-1]) - float(losses_e[-1])) < 1e-6
+        assert float(losses_e[-1]) < float(losses_e[0])                    # it does adapt
+        with torch.no_grad():                                              # an "outer update": theta moves between tasks
+            for p in ex.sigma_head.parameters():
+                p.add_(0.01)
+    fast = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in fast_g.items())
+    rgb, *_ = render_rays(m, rays, ray_samples=S, params=fast, active_module=0)
+    ((rgb - rgbs) ** 2).mean().backward()
+    ex.zero_grad(set_to_none=True)
+    accumulate_first_order_grads(ex, fast)
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for _, p in ex.meta_named_parameters())
