@@ -24,8 +24,10 @@ from .nerfs.ray_rendering import render_rays
 def task_adapt_eager(model, rays: Tensor, rgbs: Tensor, *, active_module: int, ray_samples: int, iterations: int,
                      inner_lr: float, use_amp: bool = True, fast: Optional[OrderedDict] = None,
                      loss_fn: Callable[[Tensor, Tensor], Tensor] = torch.nn.functional.mse_loss,
-                     chunk: int = 1 << 30) -> Tuple[OrderedDict, List[Tensor]]:
-    """meta_core.py:14-68 for the first-order algorithms, launch by launch (the reference's own control flow)."""
+                     chunk: int = 1 << 30, detach_updates: bool = False) -> Tuple[OrderedDict, List[Tensor]]:
+    """meta_core.py:14-68 for the first-order algorithms, launch by launch (the reference's own control flow).
+    detach_updates=True applies each SGD step as one multi-tensor kernel outside autograd (the adapted weights then
+    carry no history back to theta -- what a captured graph returns anyway)."""
     base = model.submodules[active_module]
     if fast is None:
         fast = OrderedDict((n, p) for n, p in base.meta_named_parameters())
@@ -35,7 +37,13 @@ def task_adapt_eager(model, rays: Tensor, rgbs: Tensor, *, active_module: int, r
             pred, *_ = render_rays(model, rays, ray_samples=ray_samples, params=fast, active_module=active_module, chunk=chunk)
             loss = loss_fn(pred, rgbs)
         grads = torch.autograd.grad(loss, tuple(fast.values()), create_graph=False, allow_unused=True)
-        fast = OrderedDict((n, w if g is None else (w - inner_lr * g.to(w.dtype))) for (n, w), g in zip(fast.items(), grads))
+        if detach_updates and all(g is not None for g in grads):
+            with torch.no_grad():
+                new = torch._foreach_add([w.detach() for w in fast.values()], [g.to(w.dtype) for g, w in zip(grads, fast.values())],
+                                         alpha=-float(inner_lr))
+            fast = OrderedDict((n, t.requires_grad_(True)) for n, t in zip(fast.keys(), new))
+        else:
+            fast = OrderedDict((n, w if g is None else (w - inner_lr * g.to(w.dtype))) for (n, w), g in zip(fast.items(), grads))
         losses.append(loss.detach())
     return fast, losses
 
@@ -66,7 +74,7 @@ class GraphedTaskAdapt:
         self.rgbs = torch.zeros(n_rays, 3, dtype=torch.float32, device=dev)
         self._w = OrderedDict((n, p.detach().clone().requires_grad_(True)) for n, p in self.expert.meta_named_parameters())
         kw = dict(active_module=self.cid, ray_samples=int(ray_samples), iterations=int(iterations), inner_lr=float(inner_lr),
-                  use_amp=bool(use_amp), loss_fn=loss_fn)
+                  use_amp=bool(use_amp), loss_fn=loss_fn, detach_updates=True)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                       # warm-up off the capture: lazy tables, cuda attributes, allocator

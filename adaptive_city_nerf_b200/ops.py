@@ -228,7 +228,13 @@ def field_bwd(enc: Tensor, dirs: Tensor, dirs_stride: int, dirs_group: int, ws: 
     if half and enc.dtype != torch.float16:
         enc = enc.half()
     enc = enc.contiguous()
-    grads: List[Optional[Tensor]] = [torch.zeros_like(w, dtype=torch.float32) if n else None for w, n in zip(ws, need)]
+    # one zero-filled buffer behind all the gradient tensors: one memset instead of up to 14 fill launches
+    flat = torch.zeros(sum(w.numel() for w, n in zip(ws, need) if n), dtype=torch.float32, device=dev)
+    grads: List[Optional[Tensor]] = []
+    off = 0
+    for w, n in zip(ws, need):
+        grads.append(flat[off:off + w.numel()].view(w.shape) if n else None)
+        off += w.numel() if n else 0
     # d_enc stays fp32 even for an fp16 encoding: per-sample gradients of a mean loss over 2^18 rays are
     # ~1e-9 and would flush to zero in fp16 (the reference needs GradScaler for the same reason)
     d_enc = torch.empty(P, E, dtype=torch.float32, device=dev) if want_enc_grad else None

@@ -24,21 +24,7 @@ base = OrderedDict((n, p.detach().clone()) for n, p in ex.meta_named_parameters(
 jit = torch.rand(N, S, device=dev)
 
 
-def adapt(fast):
-    """8 first-order inner steps; returns the adapted weights and the last loss."""
-    loss = None
-    for _ in range(STEPS):
-        with torch.autocast("cuda", dtype=torch.float16):
-            rgb, *_ = render_rays(model, rays, ray_samples=S, params=fast,
-                                  active_module=0, jitter=jit)
-        loss = torch.nn.functional.mse_loss(rgb, gt)
-        grads = torch.autograd.grad(loss, list(fast.values()))
-        fast = OrderedDict((k, w - LR * g) for (k, w), g in zip(fast.items(), grads))
-    return fast, loss
-
-
-def fresh():
-    return OrderedDict((k, v.clone().requires_grad_(True)) for k, v in base.items())
+from adaptive_city_nerf_b200.meta import GraphedTaskAdapt, task_adapt_eager
 
 
 def timed(fn, n=20):
@@ -51,33 +37,26 @@ def timed(fn, n=20):
     return e0.elapsed_time(e1) / n
 
 
+model.eval()       # fixed sample positions so that the two paths can be compared value for value (train mode re-jitters)
+kw = dict(active_module=0, ray_samples=S, iterations=STEPS, inner_lr=LR)
+eager_ms = timed(lambda: task_adapt_eager(model, rays, gt, **kw))
+ref_fast, ref_losses = task_adapt_eager(model, rays, gt, **kw)
+adapt = GraphedTaskAdapt(model, n_rays=N, **kw)
+graph_ms = timed(lambda: adapt(rays, gt))
+out_fast, out_losses = adapt(rays, gt)
+torch.cuda.synchronize()
+err = max(float((out_fast[k] - ref_fast[k].detach()).abs().max()) for k in out_fast)
 model.train()
-eager_ms = timed(lambda: adapt(fresh()))
-ref_fast, ref_loss = adapt(fresh())
-
-# ---- one CUDA graph for the whole adaptation
-static_in = fresh()
-side = torch.cuda.Stream()
-side.wait_stream(torch.cuda.current_stream())
-with torch.cuda.stream(side):
-    for _ in range(3):
-        adapt(static_in)
-torch.cuda.current_stream().wait_stream(side)
-graph = torch.cuda.CUDAGraph()
-with torch.cuda.graph(graph):
-    out_fast, out_loss = adapt(static_in)
-
-
-def replay():
-    for k, v in base.items():
-        static_in[k].data.copy_(v)
-    graph.replay()
-
-
-graph_ms = timed(replay)
-replay(); torch.cuda.synchronize()
-err = max(float((out_fast[k] - ref_fast[k]).abs().max()) for k in base)
+adapt_t = GraphedTaskAdapt(model, n_rays=N, **kw)
+graph_train_ms = timed(lambda: adapt_t(rays, gt))
+eager_train_ms = timed(lambda: task_adapt_eager(model, rays, gt, **kw))
 print(json.dumps({"what": f"task_adapt: {STEPS} inner SGD steps, {N} rays x {S} samples, MLP fast weights only, autocast fp16",
-                  "eager_ms": round(eager_ms, 3), "graph_ms": round(graph_ms, 3), "eager_ms_per_step": round(eager_ms / STEPS, 3),
-                  "graph_ms_per_step": round(graph_ms / STEPS, 3), "rays_per_s_graph": N * STEPS / (graph_ms * 1e-3),
-                  "max_abs_diff_adapted_weights": err, "loss": float(out_loss)}))
+                  "eval_mode": {"eager_ms_per_step": round(eager_ms / STEPS, 3), "graph_ms_per_step": round(graph_ms / STEPS, 3)},
+                  "train_mode_jitter": {"eager_ms_per_step": round(eager_train_ms / STEPS, 3), "graph_ms_per_step": round(graph_train_ms / STEPS, 3)},
+                  "rays_per_s_graph_train": N * STEPS / (graph_train_ms * 1e-3),
+                  "max_abs_diff_adapted_weights": err, "last_loss": float(out_losses[-1])}))
+if "--profile" in sys.argv:
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as pr:
+        adapt_t(rays, gt); torch.cuda.synchronize()
+    print(pr.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=70))
