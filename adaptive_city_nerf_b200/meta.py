@@ -5,7 +5,7 @@ The reference's meta-training spends 8 of every 9 render passes in `task_adapt`
 table is not a MetaModule parameter, so it gets no gradient) over a few thousand support rays.  At that batch size the
 loop is launch-bound -- ~25 kernel launches and a few hundred microseconds of Python per step -- while every kernel
 behind `render_rays` is capture-safe (no host syncs; scratch is chosen at capture time).  `GraphedTaskAdapt` captures
-the whole adaptation once and replays it per task: 1.05 -> 0.66 ms per inner step on a B200 (tools/bench_inner.py),
+the whole adaptation once and replays it per task: 0.99 -> 0.30 ms per inner step on a B200 (tools/bench_inner.py),
 with bit-identical adapted weights.
 
 Scope: `algo` in {fomaml, reptile} (first order, `create_graph=False`) and the plain MSE loss

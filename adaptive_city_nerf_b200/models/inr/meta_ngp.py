@@ -178,16 +178,18 @@ class MetaNGP(MetaModule):
         assert x_d.shape[-1] >= 6, f"Expected (...,6) [xyz,dir], got {x_d.shape}"
         self._check_fused()
         x2 = x_d.reshape(-1, x_d.shape[-1])
-        out = ops.ExpertFieldFn.apply(x2, None, None, self.xyz_encoder.hash_table, self.xyz_encoder.grid_spec(),
-                                      self.box6(), self._use_half(x2.device), *self.fused_weights(params))
+        table = self.xyz_encoder.hash_table
+        out = ops.ExpertFieldFn.apply(x2, None, None, table, self.xyz_encoder.grid_spec(),
+                                      self.box6(), self._use_half(x2.device), ops.grad_node_of(table), *self.fused_weights(params))
         return out.view(*x_d.shape[:-1], 4)
 
     def forward_rays(self, rays: Tensor, t_vals: Tensor, params=None) -> Tensor:
         """Same field evaluated at the samples o + d*t of packed rays without materialising the
         (N*S,6) point tensor (nerfs/ray_rendering.py:317-319) -> (N,S,4)."""
         self._check_fused()
-        out = ops.ExpertFieldFn.apply(None, rays, t_vals, self.xyz_encoder.hash_table, self.xyz_encoder.grid_spec(),
-                                      self.box6(), self._use_half(rays.device), *self.fused_weights(params))
+        table = self.xyz_encoder.hash_table
+        out = ops.ExpertFieldFn.apply(None, rays, t_vals, table, self.xyz_encoder.grid_spec(),
+                                      self.box6(), self._use_half(rays.device), ops.grad_node_of(table), *self.fused_weights(params))
         return out.view(t_vals.shape[0], t_vals.shape[1], 4)
 
     # ------------------------------------------------------------------ optimizer groups

@@ -254,7 +254,7 @@ class ExpertFieldFn(torch.autograd.Function):
     fast weights).  The backward recomputes the MLP activations from the saved encoding."""
 
     @staticmethod
-    def forward(ctx_, x6, rays, t, table, spec, box6, half, *ws):
+    def forward(ctx_, x6, rays, t, table, spec, box6, half, table_node, *ws):
         ws = [dev_f32(w, "MLP weight") for w in ws]
         table_c = dev_f32(table, "hash_table")
         enc_dtype = torch.float16 if half else torch.float32
@@ -273,6 +273,7 @@ class ExpertFieldFn(torch.autograd.Function):
         out = field_fwd(enc, dirs, dstride, dgroup, ws, half)
         ctx_.save_for_backward(enc, *pos, *(t_ for t_ in (box6,) if t_ is not None), *ws)
         ctx_.meta = (spec, half, len(pos), box6 is not None, dstride, dgroup, table.shape)
+        ctx_.table_node = table_node
         return out
 
     @staticmethod
@@ -283,8 +284,11 @@ class ExpertFieldFn(torch.autograd.Function):
         enc, pos = saved[0], saved[1:1 + npos]
         box6 = saved[1 + npos] if has_box else None
         ws = saved[1 + npos + int(has_box):]
-        need_table = ctx_.needs_input_grad[3]
-        need_w = ctx_.needs_input_grad[7:]
+        # needs_input_grad is static (the table is a Parameter); what THIS backward pass wants is not: the inner loop
+        # asks torch.autograd.grad for the 14 fast weights only (meta_core.py:54-59) and must not pay for d_enc and the
+        # table scatter -- the reference's un-fused graph gets that pruning from the engine for free.
+        need_table = ctx_.needs_input_grad[3] and engine_wants(ctx_.table_node)
+        need_w = ctx_.needs_input_grad[8:]
         dirs = pos[0][:, 3:]
         g = g.contiguous().float()
         grads, d_enc = field_bwd(enc, dirs, dstride, dgroup, ws, half, g, need_table, need_w)
@@ -295,7 +299,25 @@ class ExpertFieldFn(torch.autograd.Function):
                 hashgrid_bwd_rays(pos[0], pos[1], d_enc, spec, box6, dtable)
             else:
                 hashgrid_bwd(pos[0], d_enc, spec, box6, dtable)
-        return (None, None, None, dtable, None, None, None, *grads)
+        return (None, None, None, dtable, None, None, None, None, *grads)
+
+
+def grad_node_of(t: Optional[Tensor]):
+    """The autograd node that receives `t`'s gradient (AccumulateGrad for a leaf), or None.  Call with grad mode on,
+    outside any autograd.Function."""
+    if t is None or not t.requires_grad or not torch.is_grad_enabled():
+        return None
+    return t.grad_fn if t.grad_fn is not None else t.view_as(t).grad_fn.next_functions[0][0]
+
+
+def engine_wants(node) -> bool:
+    """Inside a backward: will the running autograd pass deliver a gradient to `node`?  (True when unknown.)"""
+    if node is None:
+        return True
+    try:
+        return bool(torch._C._will_engine_execute_node(node))
+    except Exception:
+        return True
 
 
 # ------------------------------------------------------------------------------------------ stage 4

@@ -205,3 +205,34 @@ def test_graphed_task_adapt_matches_eager(golden):
     ex.zero_grad(set_to_none=True)
     accumulate_first_order_grads(ex, fast)
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for _, p in ex.meta_named_parameters())
+
+
+def test_inner_loop_backward_skips_the_table(golden):
+    """torch.autograd.grad(loss, fast weights) -- the inner loop -- must not compute d_enc or scatter into the hash table
+    (the fused autograd node learns from the engine what this pass wants); a full backward still does."""
+    from adaptive_city_nerf_b200 import _lib
+    from adaptive_city_nerf_b200.nerfs.ray_rendering import render_rays
+    m = make_container(1, np.zeros((1, 3), F32), [synth.AABB_GLOBAL], 1.0, False, seed0=510).eval()
+    ex = m.submodules[0]
+    N, S = 700, 16
+    o, d = synth.random_rays_in_box(77, N)
+    rays = torch.cat([cu(o), cu(d), torch.zeros(N, 1, device="cuda"), torch.full((N, 1), 0.4, device="cuda")], dim=1)
+    fast = OrderedDict((n, p) for n, p in ex.meta_named_parameters())
+    for amp in (False, True):
+        with torch.autocast("cuda", enabled=amp, dtype=torch.float16):
+            rgb, *_ = render_rays(m, rays, ray_samples=S, params=fast, active_module=0)
+        loss = (rgb ** 2).mean()
+        _lib._Profile.start()
+        g_inner = torch.autograd.grad(loss, tuple(fast.values()), retain_graph=True)
+        torch.cuda.synchronize()
+        calls = set(_lib._Profile.stop())
+        assert "acn_field_bwd" in calls and not any(k.startswith("acn_hashgrid_bwd") for k in calls), calls
+        _lib._Profile.start()
+        loss.backward()
+        torch.cuda.synchronize()
+        calls = set(_lib._Profile.stop())
+        assert any(k.startswith("acn_hashgrid_bwd") for k in calls), calls
+        assert ex.xyz_encoder.hash_table.grad is not None and float(ex.xyz_encoder.hash_table.grad.abs().sum()) > 0
+        for (n, p), g in zip(ex.meta_named_parameters(), g_inner):
+            assert torch.allclose(p.grad, g, rtol=1e-4, atol=1e-7), n          # same weight gradients either way
+        m.zero_grad(set_to_none=True)
