@@ -597,6 +597,11 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     const float inv_scale = 1.0f / scale;
     const bool want_denc = d_enc != nullptr;
 
+    // Two warps of the slot issue: the chain issuer launches the MMAs the next epilogue waits for (forward layers, dgrad)
+    // and commits them to done_d; a second warp, on another SM sub-partition, launches the weight-gradient MMAs of the
+    // same step and commits them to done_w.  The two groups touch different accumulators, so their order is free; one
+    // thread issuing all ~20 MMAs of a backward step made its warp ~800 cycles late to the slot's next barrier.
+    const bool wgrad_warp = (warp & 7) == ((slot + 2) & 7);
     auto issue = [&](int step) {
         if (issuer_warp) {
             if (umma::elect_one()) {
@@ -608,34 +613,32 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
                     case 3: mma_fwd_bias(dwin, Tcin, Wc0, One, Bc0, 32); break;
                     case 4: mma_fwd_bias(dwin, Tc1, Wc1, One, Bc1, 64); break;
                     case 5: mma_fwd(dwin, Tc2, Wc2, 16, 64); break;
-                    case 6:   // colour out: D = drr W_c2 ; [dW^T ; db] (in+1 x out) = [c2 | 1]^T drr
-                        mma_dgrad(dwin, Tdrr, Wc2, 64, 16); umma::commit_a(done_d);
-                        mma_over_points(tmem_base + COL_WC2T, Tc2, Tdrr, 16, 128);
-                        break;
-                    case 7:   // colour layer 2: g lives in the c2 tile now; [dW | db] (out x in+1) = g^T [c1 | 1]
-                        mma_dgrad(dwin, Tc2, Wc1, 64, 64); umma::commit_a(done_d);
-                        mma_over_points(tmem_base + COL_WC1, Tc2, Tc1, HW);
-                        break;
-                    case 8:   // colour layer 1: column 31 of the input tile is the ones column
-                        mma_dgrad(dwin, Tc1, Wc0, 32, 64); umma::commit_a(done_d);
-                        mma_over_points(tmem_base + COL_WC0, Tc1, Tcin, 32);
-                        break;
-                    case 9:   // heads: [dW^T ; db] (in+1 x out) = [h2 | 1]^T ghd
-                        mma_dgrad(dwin, Tghd, Whd, 64, 16); umma::commit_a(done_d);
-                        mma_over_points(tmem_base + COL_WHDT, Th2, Tghd, 16, 128);
-                        break;
-                    case 10:  // trunk layer 2
-                        mma_dgrad(dwin, Th2, Wt1, 64, 64); umma::commit_a(done_d);
-                        mma_over_points(tmem_base + COL_WT1, Th2, Th1, HW);
-                        break;
-                    default:  // trunk layer 1 (+ optional d enc); the encoding tile has no spare column: separate G^T 1
-                        if (want_denc) mma_dgrad(dwin, Th1, Wt0, E, 64);
-                        umma::commit_a(done_d);
+                    case 6: mma_dgrad(dwin, Tdrr, Wc2, 64, 16); break;          // colour out: D = drr W_c2
+                    case 7: mma_dgrad(dwin, Tc2, Wc1, 64, 64); break;           // colour layer 2 (g lives in the c2 tile now)
+                    case 8: mma_dgrad(dwin, Tc1, Wc0, 32, 64); break;           // colour layer 1
+                    case 9: mma_dgrad(dwin, Tghd, Whd, 64, 16); break;          // heads
+                    case 10: mma_dgrad(dwin, Th2, Wt1, 64, 64); break;          // trunk layer 2
+                    default: if (want_denc) mma_dgrad(dwin, Th1, Wt0, E, 64); break;   // trunk layer 1 (optional d enc)
+                }
+                umma::commit_a(done_d);
+            }
+            __syncwarp();
+        }
+        if (wgrad_warp && step >= 6) {
+            if (umma::elect_one()) {
+                umma::fence_after_sync();
+                switch (step) {
+                    case 6: mma_over_points(tmem_base + COL_WC2T, Tc2, Tdrr, 16, 128); break;   // [dW^T ; db] = [c2 | 1]^T drr
+                    case 7: mma_over_points(tmem_base + COL_WC1, Tc2, Tc1, HW); break;          // [dW | db] = g^T [c1 | 1]
+                    case 8: mma_over_points(tmem_base + COL_WC0, Tc1, Tcin, 32); break;         // column 31 of cin is the ones column
+                    case 9: mma_over_points(tmem_base + COL_WHDT, Th2, Tghd, 16, 128); break;   // [dW^T ; db] = [h2 | 1]^T ghd
+                    case 10: mma_over_points(tmem_base + COL_WT1, Th2, Th1, HW); break;
+                    default:   // the encoding tile has no spare column: separate G^T 1
                         mma_over_points(tmem_base + COL_WT0, Th1, Txe, E);
                         mma_over_points(tmem_base + COL_BT0, Th1, One, 8);
                         break;
                 }
-                umma::commit_a(step < 6 ? done_d : done_w);
+                umma::commit_a(done_w);
             }
             __syncwarp();
         }
