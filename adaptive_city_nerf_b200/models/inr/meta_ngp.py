@@ -169,9 +169,15 @@ class MetaNGP(MetaModule):
         return {"sigma": sigma, "geo_feat": self.geo_head(h, params=self.get_subdict(params, "geo_head"))}
 
     def _use_half(self, device: torch.device) -> bool:
-        """tcgen05 fp16 kernels under autocast -- when the encoding width is one their backward is built for (16 or 32
-        = L*F; its activation tiles fill shared memory).  Wider encodings run the fp32 CUDA kernels instead."""
-        return autocast_half(device) and self.xyz_encoder.out_dim in (16, 32)
+        """tcgen05 kernels (fp16 operands, fp32 accumulate) when the caller runs under autocast(float16) -- or when it
+        has allowed TF32 matmuls (`torch.backends.cuda.matmul.allow_tf32`, which the reference's runner switches on:
+        nerf_runner.py:41-42).  TF32 and fp16 carry the same 10-bit mantissa, the accumulators are fp32 either way, and
+        the backward scales its gradient tiles into fp16 range, so this is the precision the reference's own GPU path
+        has with that flag; without it the strict fp32 SIMT kernels run (40x / 14x slower forward / backward).  Only for
+        the encoding widths the tensor-core backward is built for (16 or 32 = L*F)."""
+        if self.xyz_encoder.out_dim not in (16, 32) or device.type != "cuda":
+            return False
+        return autocast_half(device) or bool(torch.backends.cuda.matmul.allow_tf32)
 
     def forward(self, x_d: Tensor, params=None) -> Tensor:
         """(...,>=6) [xyz, dir] -> (...,4) [rgb, sigma] (reference :226-241), fused."""

@@ -236,3 +236,36 @@ def test_inner_loop_backward_skips_the_table(golden):
         for (n, p), g in zip(ex.meta_named_parameters(), g_inner):
             assert torch.allclose(p.grad, g, rtol=1e-4, atol=1e-7), n          # same weight gradients either way
         m.zero_grad(set_to_none=True)
+
+
+def test_allow_tf32_selects_the_tensor_core_path(golden):
+    """Without autocast the strict fp32 kernels run -- unless the caller allowed TF32 matmuls, as the reference's runner
+    does (nerf_runner.py:41-42): then the tcgen05 kernels serve the fp32-mode calls too, at TF32-level accuracy."""
+    from adaptive_city_nerf_b200 import _lib
+    from adaptive_city_nerf_b200.nerfs.ray_rendering import render_rays
+    m = make_container(1, np.zeros((1, 3), F32), [synth.AABB_GLOBAL], 1.0, False, seed0=520).eval()
+    N, S = 900, 16
+    o, d = synth.random_rays_in_box(78, N)
+    rays = torch.cat([cu(o), cu(d), torch.zeros(N, 1, device="cuda"), torch.full((N, 1), 0.4, device="cuda")], dim=1)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        rgb32, dep32, *_ = render_rays(m, rays, ray_samples=S, active_module=0)
+        (rgb32.sum() + dep32.sum()).backward()
+        g32 = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+        m.zero_grad(set_to_none=True)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        _lib._Profile.start()
+        rgb, dep, *_ = render_rays(m, rays, ray_samples=S, active_module=0)
+        (rgb.sum() + dep.sum()).backward()
+        torch.cuda.synchronize()
+        _lib._Profile.stop()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    assert rgb.dtype == torch.float32
+    assert (rgb - rgb32).abs().max() < 1e-3 and (dep - dep32).abs().max() < 1e-3
+    assert not torch.equal(rgb, rgb32)                                   # a different (tensor-core) kernel did run
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            a, b = p.grad.double(), g32[n].double()
+            assert float((a - b).norm() / (b.norm() + 1e-30)) < 3e-2, n
