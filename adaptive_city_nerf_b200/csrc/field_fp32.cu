@@ -2,7 +2,7 @@
 // (models/inr/meta_ngp.py:171-241) as ONE SIMT kernel per direction.  This is the path the
 // reference runs with autocast off (meta-training query loss, pipelines/offline_stage/
 // meta_train_step.py:110) and the tight-tolerance (<= 1e-5) parity anchor for the tcgen05
-// kernels in field_tc.cu, which serve the autocast(fp16) case.
+// kernels in field_mma.cu, which serve the autocast(fp16) / TF32-allowed case.
 //
 // A 256-thread block owns a tile of 64 points.  Weights live in shared memory in nn.Linear
 // layout; activations live in shared memory feature-major ([feature][point], row stride LDP),

@@ -5,38 +5,36 @@
 // fp32 accumulator by one extra K step, so a hidden activation is fp16(relu(sum + b)): one rounding where the
 // reference has two (GEMM result, then the next layer's input cast).
 //
-// Both kernels are persistent (one CTA per SM).  Tiles are 128 points (MMA M = 128); a point owns row r of
-// every activation tile in shared memory (canonical no-swizzle UMMA layout, umma.cuh) and lane r of a TMEM
-// accumulator window.  All six weight matrices stay resident in shared memory as B operands.  The layers of a
-// tile are serially dependent (MMA -> epilogue -> MMA ...), so the tensor pipe is kept busy by running several
-// tiles per SM out of phase, with no __syncthreads and no dedicated issuer thread in the steady state:
+// Both kernels are persistent (one CTA per SM).  Tiles are 128 points (MMA M = 128); thread r of a tile's warpgroup owns
+// point r: lane r of the tile's TMEM window (and, in the backward, row r of its shared-memory tiles, canonical
+// no-swizzle UMMA layout, umma.cuh).  All six weight matrices stay resident in shared memory as B operands.  The layers
+// of a tile are serially dependent (MMA -> epilogue -> MMA ...), so several tiles run out of phase per SM, with no
+// __syncthreads and no dedicated issuer thread in the steady state: after an epilogue the tile's threads meet on a
+// named barrier and ONE elected lane of one of their warps issues the next layer's tcgen05.mma's from warp-uniform code
+// and commits them to the tile's mbarrier.  (A single issuer thread serving all tiles was measured at ~1200 cycles per
+// layer step -- tools/field_trace.py -- because ptxas wrapped every UTCHMMA in a waterfall loop.)
 //
-//   forward   4 warpgroups x 2 tiles.  Each warpgroup (128 threads, thread = row) ping-pongs two tiles: while
-//             the tensor core runs tile A's layer, the same threads run tile B's epilogue.  After an epilogue
-//             the warpgroup meets on a named barrier and ONE elected lane of its first warp issues the next
-//             layer's tcgen05.mma's and commits to that tile's mbarrier.  (A single issuer thread serving all
-//             tiles was measured at ~1200 cycles per layer step -- see tools/field_trace.py -- and was the
-//             bottleneck; per-warpgroup issue from warp-uniform code with elect.sync is ~10x cheaper.)
-//   backward  2 slots x 1 tile (the six activation tiles of a tile take 88 KB), 256 threads per slot: two
-//             threads per row, each owning 32 of a layer's 64 columns, to halve the epilogue latency on the
-//             critical path.  Per layer the issuer launches dgrad FIRST and commits it separately, then wgrad
-//             and bgrad: the epilogue starts on the dgrad result while the weight-gradient MMAs still run and
-//             only its in-place stores wait for them.
+//   forward   4 warpgroups x 1 tile, activations chained through TENSOR MEMORY (A operand in TMEM): see the kernel.
+//   backward  2 slots x 1 tile (the activation tiles of a tile take 92 KB of shared memory), 256 threads per slot: two
+//             threads per row, each owning 32 of a layer's 64 columns.  Per layer dgrad is issued FIRST and committed
+//             separately, the weight-gradient MMAs by a second warp: the epilogue starts on the dgrad result while
+//             they still run and only its in-place stores wait for them.
 //
-// Backward (autograd of the forward): recomputes the tile's forward with the SAME instructions as the
-// forward kernel (bit-identical activations, hence the ReLU masks the forward used), then walks the layers
-// in reverse: wgrad (contraction over the tile's 128 points, both operands viewed MN-major, accumulator
-// PERSISTENT in TMEM across every tile the CTA processes), bgrad (G^T 1 against a constant ones tile) and
-// dgrad; the epilogue masks with [act > 0] and overwrites the dead activation tile with the gradient tile.
-// Gradient tiles are fp16 carrying one global power-of-two scale (max|dL/dy| * 2^k in [2^9, 2^10)) measured
-// by a max-reduction over dL/dy before the launch -- the job GradScaler does for the reference -- and divided
-// out of d_enc and the weight gradients in fp32.  After its last tile the CTA adds its TMEM-resident weight
-// gradients to global memory (one atomicAdd per weight per CTA).
+// Backward (autograd of the forward): recomputes the tile's forward with the forward kernel's arithmetic (identical
+// activations, hence the ReLU masks the forward used), then walks the layers in reverse: wgrad = G^T X (contraction over
+// the tile's 128 points, both operands viewed MN-major, M = 64, accumulators PERSISTENT in TMEM across every tile the
+// CTA processes) and dgrad; the epilogue masks with [act > 0] and overwrites the dead activation tile with the gradient
+// tile.  Hidden tiles carry a constant ones column, so the bias gradients come out of the wgrad MMAs themselves.
+// Gradient tiles are fp16 carrying one global power-of-two scale (max|dL/dy| * 2^k in [2^9, 2^10)) measured by a
+// max-reduction over dL/dy before the launch -- the job GradScaler does for the reference -- and divided out of d_enc
+// and the weight gradients in fp32.  After its last tile the CTA adds its TMEM-resident weight gradients to global
+// memory (one atomicAdd per weight per CTA).
 //
-// Operand-layout facts were established on hardware with tools/umma_probe.py (profiles/): for a canonical
-// tile with row-group stride RG the K-major view is (lbo=128, sbo=RG, +256 B per K step), the MN-major view
-// is (lbo=RG, sbo=128, +2*RG per K step); an M=128 MMA whose MN-major A tile has only 64 (or 16) columns
-// reads on into the following shared memory and leaves garbage in TMEM lanes >= 64 (16), which are never read.
+// Operand-layout facts were established on hardware with tools/umma_probe.py (profiles/): for a canonical tile with
+// row-group stride RG the K-major view is (lbo=128, sbo=RG, +256 B per K step), the MN-major view is (lbo=RG, sbo=128,
+// +2*RG per K step); an MN-major A view wider than its tile reads on into the following shared memory and leaves
+// garbage in the TMEM lanes beyond the tile's columns, which are never read; an M = 64 accumulator keeps row m in lane
+// (m >> 4) * 32 + (m & 15); a TMEM A operand holds row r in lane r, two consecutive K elements per 32-bit column.
 #include "field_common.cuh"
 #include "field_internal.cuh"
 #include "umma.cuh"

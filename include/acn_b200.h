@@ -23,7 +23,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define ACN_VERSION 100 /* major*100 + minor */
+#define ACN_VERSION 101 /* major*100 + minor */
 
 typedef struct acn_ctx acn_ctx;
 typedef void* acn_stream; /* cudaStream_t */
