@@ -29,6 +29,17 @@ class FieldWeights(C.Structure):
     _fields_ = [("p", c_p * 14)]
 
 
+class AdamTensor(C.Structure):
+    """acn_adam_tensor (include/acn_b200.h)"""
+    _fields_ = [("p", c_p), ("g", c_p), ("m", c_p), ("v", c_p), ("n", c_i64), ("lr", C.c_double),
+                ("weight_decay", C.c_double)]
+
+
+ADAM_MAX_TENSORS = 48
+LOSS_PARTIALS = 1024
+COLOR_SPACE = {"linear": 0, "srgb": 1, "identity": 2}
+
+
 HEADER = _PKG.parent / "include" / "acn_b200.h"
 
 
@@ -50,6 +61,8 @@ def _parse_header(path: Path):
                     types.append(c_i64)
                 elif a.startswith("float"):
                     types.append(c_f)
+                elif a.startswith("double"):
+                    types.append(C.c_double)
                 elif a.startswith("uint32_t"):
                     types.append(C.c_uint32)
                 elif a.startswith("int"):

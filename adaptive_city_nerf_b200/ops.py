@@ -364,6 +364,46 @@ class CompositeFn(torch.autograd.Function):
         return d.view_as(rs), None, d_bg, None
 
 
+# ------------------------------------------------------------------------------------------ loss epilogue
+def color_mse(pred: Tensor, gt: Tensor, color_space: str, reduction: str = "mean", want_grad: bool = False):
+    """nerfs/color_space.py:22-66 + F.mse_loss in one launch.  -> (loss | per-element squared errors, d loss / d pred | None)"""
+    cs = str(color_space).lower()
+    if cs not in _lib.COLOR_SPACE:
+        raise ValueError(f"Invalid color_space={color_space!r}; use 'linear'|'srgb'|'identity'")
+    if reduction not in ("mean", "sum", "none"):
+        raise ValueError(f"{reduction} is not a valid value for reduction")
+    p = dev_f32(pred, "pred_rgb")
+    g = dev_f32(gt.to(p.device), "gt_rgb")
+    if g.shape != p.shape:
+        g = g.expand_as(p).contiguous()
+    dev, n = p.device, p.numel()
+    reduced = reduction != "none"
+    loss = torch.empty((), dtype=torch.float32, device=dev) if reduced else None
+    elem = torch.empty_like(p) if not reduced else None
+    dpred = torch.empty_like(p) if want_grad else None
+    partial = torch.empty(_lib.LOSS_PARTIALS, dtype=torch.float64, device=dev) if reduced else None
+    check(lib().acn_color_mse(ctx(dev), ptr(p), ptr(g), n, _lib.COLOR_SPACE[cs], int(reduction == "mean"), ptr(loss),
+                              ptr(elem), ptr(dpred), ptr(partial), stream(dev)))
+    return (loss if reduced else elem), dpred
+
+
+class ColorMSEFn(torch.autograd.Function):
+    """color_space_transformer(pred, gt, cs) -> F.mse_loss (nerfs/losses.py:29-32); the ground truth carries no gradient."""
+
+    @staticmethod
+    def forward(ctx_, pred, gt, color_space, reduction):
+        out, dpred = color_mse(pred, gt, color_space, reduction, want_grad=pred.requires_grad)
+        ctx_.save_for_backward(dpred)
+        ctx_.shape, ctx_.dtype = pred.shape, pred.dtype
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx_, g_out):
+        (dpred,) = ctx_.saved_tensors
+        return (dpred * g_out).view(ctx_.shape).to(ctx_.dtype), None, None, None
+
+
 # ------------------------------------------------------------------------------------------ stage 5
 def route_points(pts: Tensor, centroids: Tensor, dims: int, margin: float, want_counts: bool = False):
     """-> (weights (P,K) | None, hard (P,) int32 | None, counts (K,) int32 | None)"""

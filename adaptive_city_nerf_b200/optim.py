@@ -1,0 +1,182 @@
+"""Optimizer tail of a training step behind the reference's own entry points.
+
+Reference: common/utils.py:16-76 `get_optimizer` (Adam / AdamW over the model's named parameter groups),
+pipelines/offline_stage/meta_core.py:123-141 `maml_meta_update` and :181-190 `clip_all_grads`,
+pipelines/online_stage/runtime_adapt.py:262-268 -- i.e. per step
+
+    scaler.unscale_(opt); clip_grad_norm_(params, c); scaler.step(opt); scaler.update()
+
+which in PyTorch is 12 passes over the 64 MiB hash table per expert and one host read (the inf check).  `FusedAdam`
+does it in 8 passes and three launches (`acn_grad_sqnorm`, `acn_adam_prepare`, `acn_adam_apply`) and reads nothing
+back: skip / clip coefficient / bias corrections are decided on the device.  The arithmetic per element is
+torch.optim.Adam's (same op order, constants rounded from the same doubles).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import AdamTensor, check, ctx, lib, ptr, stream
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam (adamw=False) / AdamW (adamw=True) with the gradient unscale, the global-norm clip and the
+    non-finite skip folded into the update.
+
+    Three ways to drive it, all without a host sync:
+      opt.step(max_norm=c)                      fp32 training: clip + step
+      scaler.step(opt, max_norm=c); scaler.update()    public GradScaler protocol (the scaler hands over its scale and
+                                                its own inf check through `opt.grad_scale` / `opt.found_inf`)
+      opt.step_scaled(scaler, max_norm=c)       everything in the three launches, including the inf check; also
+                                                performs `scaler.update()`
+    `opt.last_norm` is the unscaled global gradient norm of the last step (a device scalar, what clip_grad_norm_
+    returns)."""
+
+    _step_supports_amp_scaling = True
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 adamw: bool = False, max_norm: Optional[float] = None, write_grads: bool = False):
+        if lr < 0.0 or eps < 0.0 or weight_decay < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
+            raise ValueError(f"invalid Adam hyper-parameters lr={lr} betas={betas} eps={eps} weight_decay={weight_decay}")
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        self.adamw, self.max_norm, self.write_grads = bool(adamw), max_norm, bool(write_grads)
+        self._dev: Optional[torch.device] = None
+        self._state8 = self._acc2 = self._found_inf = None
+
+    # ---- device-side step state ---------------------------------------------------------------------------------
+    def _device_state(self, dev: torch.device):
+        if self._dev is None:
+            self._dev = dev
+            self._state8 = torch.zeros(8, dtype=torch.float64, device=dev)
+            self._acc2 = torch.zeros(2, dtype=torch.float64, device=dev)
+            self._found_inf = torch.zeros(1, dtype=torch.float32, device=dev)
+        elif dev != self._dev:
+            raise RuntimeError(f"FusedAdam: parameters on {dev} and {self._dev}; use one optimizer per device")
+
+    @property
+    def last_norm(self) -> torch.Tensor:
+        return self._state8[5].float()
+
+    @property
+    def steps_taken(self) -> torch.Tensor:
+        """Number of steps that were not skipped (device scalar)."""
+        return self._state8[0]
+
+    def _tensors(self):
+        betas, eps = self.param_groups[0]["betas"], self.param_groups[0]["eps"]
+        out, keep = [], []
+        for group in self.param_groups:
+            if tuple(group["betas"]) != tuple(betas) or group["eps"] != eps:
+                raise RuntimeError("FusedAdam: all parameter groups must share betas and eps (lr and weight_decay may differ)")
+            for p in group["params"]:
+                g = p.grad
+                if g is None:
+                    continue
+                if not p.is_cuda:
+                    raise RuntimeError("FusedAdam needs CUDA parameters; there is no CPU path")
+                if g.is_sparse or p.dtype != torch.float32 or g.dtype != torch.float32:
+                    raise RuntimeError("FusedAdam: dense fp32 parameters and gradients only")
+                if not p.is_contiguous() or not g.is_contiguous():
+                    raise RuntimeError("FusedAdam: parameters and gradients must be contiguous")
+                self._device_state(p.device)
+                st = self.state[p]
+                if "exp_avg" not in st:
+                    st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)   # filled in by state_dict()
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                t = AdamTensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                               p.numel(), float(group["lr"]), float(group["weight_decay"]))
+                out.append(t)
+                keep.append((p, g))
+        return out, keep, betas, eps
+
+    def _run(self, grad_scale, found_inf_in, max_norm):
+        tensors, keep, betas, eps = self._tensors()
+        if not tensors:
+            return
+        dev = self._dev
+        c, s, L = ctx(dev), stream(dev), lib()
+        chunks = []
+        for i in range(0, len(tensors), _lib.ADAM_MAX_TENSORS):
+            part = tensors[i:i + _lib.ADAM_MAX_TENSORS]
+            chunks.append(((AdamTensor * len(part))(*part), len(part)))
+        gs = None if grad_scale is None else grad_scale.reshape(-1)
+        if gs is not None and (gs.dtype != torch.float32 or gs.device != dev):
+            gs = gs.to(device=dev, dtype=torch.float32)
+        fi = None if found_inf_in is None else found_inf_in.reshape(-1).to(device=dev, dtype=torch.float32)
+        for arr, n in chunks:
+            check(L.acn_grad_sqnorm(c, C.cast(arr, C.c_void_p), n, ptr(gs), ptr(self._acc2), s))
+        check(L.acn_adam_prepare(c, ptr(self._acc2), ptr(gs), ptr(fi), float(max_norm) if max_norm else 0.0,
+                                 float(betas[0]), float(betas[1]), ptr(self._state8), ptr(self._found_inf), s))
+        for arr, n in chunks:
+            check(L.acn_adam_apply(c, C.cast(arr, C.c_void_p), n, ptr(self._state8), float(betas[0]), float(betas[1]),
+                                   float(eps), int(self.adamw), int(self.write_grads), s))
+        del keep
+
+    @torch.no_grad()
+    def step(self, closure=None, *, max_norm: Optional[float] = ...):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        if max_norm is ...:
+            max_norm = self.max_norm
+        # torch.amp.GradScaler.step() sets these two attributes on optimizers that declare _step_supports_amp_scaling
+        self._run(getattr(self, "grad_scale", None), getattr(self, "found_inf", None), max_norm)
+        return loss
+
+    @torch.no_grad()
+    def step_scaled(self, scaler, *, max_norm: Optional[float] = ...):
+        """`scaler.unscale_(opt); clip_grad_norm_(...); scaler.step(opt); scaler.update()` in three launches plus the
+        scale update; call it after `scaler.scale(loss).backward()`.  A disabled scaler degrades to `step()`."""
+        if max_norm is ...:
+            max_norm = self.max_norm
+        if not scaler.is_enabled():
+            self._run(None, None, max_norm)
+            return
+        if scaler._scale is None:
+            raise RuntimeError("step_scaled: call scaler.scale(loss).backward() first")
+        self._run(scaler._scale, None, max_norm)
+        if self._found_inf is not None:
+            torch._amp_update_scale_(scaler._scale, scaler._growth_tracker, self._found_inf, scaler.get_growth_factor(),
+                                     scaler.get_backoff_factor(), scaler.get_growth_interval())
+
+    # ---- checkpoints in torch.optim.Adam's layout (reference: utils.py save/load_checkpoint) ------------------------
+    def state_dict(self) -> Dict[str, Any]:
+        if self._state8 is not None:
+            step = self._state8[0].float()
+            for st in self.state.values():
+                if "step" in st:
+                    st["step"] = step.clone()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict: Dict[str, Any]) -> None:
+        super().load_state_dict(state_dict)
+        steps = [float(st["step"]) for st in self.state.values() if "step" in st]
+        if steps:
+            p0 = next(p for p in self.state if "step" in self.state[p])
+            self._dev = None
+            self._device_state(p0.device)
+            self._state8[0] = max(steps)
+
+
+def get_optimizer(P, model: torch.nn.Module) -> FusedAdam:
+    """common/utils.py:16-76: parameter groups 'encoding' / 'sigma' / 'color' / 'background' from
+    `model.get_param_groups()` with `P.encoding_lr`, `P.sigma_lr`, `P.color_lr`, `P.bg_lr` (fallback `P.lr`)."""
+    base_lr = float(getattr(P, "lr", 1e-3))
+    weight_decay = float(getattr(P, "weight_decay", 0.0))
+    group_dict = model.get_param_groups()
+    groups = []
+    for name, attr in (("encoding", "encoding_lr"), ("sigma", "sigma_lr"), ("color", "color_lr"), ("background", "bg_lr")):
+        if name not in group_dict:
+            continue
+        assert "params" in group_dict[name], f"{name} group must contain 'params'."
+        lr = getattr(P, attr, None)
+        groups.append({"params": list(group_dict[name]["params"]), "lr": float(base_lr if lr is None else lr), "name": name})
+    opt_name = str(getattr(P, "optimizer", "adamw")).lower()
+    if opt_name not in ("adam", "adamw"):
+        raise ValueError(f"Unknown optimizer for the fused step: {opt_name} (adam | adamw; use torch.optim for sgd)")
+    return FusedAdam(groups, lr=base_lr, weight_decay=weight_decay, adamw=opt_name == "adamw")

@@ -6,8 +6,8 @@
 
 Workload (BASELINE.json configs[1]): ONE Instant-NGP expert (16-level hash grid, T = 2^19, F = 2,
 64-wide MLPs), 2^18 rays x 64 samples per batch, one TRAINING step = render_rays (train mode,
-stratified jitter, fp16 tcgen05 MLP under autocast) + MSE + backward (table + 14 MLP tensors) +
-fused Adam step.  Synthetic rays: 64 nadir 64x64 pinhole views inside the shipped scene box
+stratified jitter, fp16 tcgen05 MLP under autocast) + colour-space MSE (acn_color_mse) + backward (table + 14 MLP
+tensors) + global-norm clip and Adam in one pass (optim.FusedAdam).  Synthetic rays: 64 nadir 64x64 pinhole views inside the shipped scene box
 (SURVEY 8d); random-init weights (reference init).  Metric: train rays/s (whole job).
 
 N > 1 (torchrun): single-expert data parallel -- every rank renders its own 2^18-ray batch (weak
@@ -205,6 +205,8 @@ def run_ours(args):
     from adaptive_city_nerf_b200 import _lib
     from adaptive_city_nerf_b200.nerfs.ray_rendering import render_rays
     from adaptive_city_nerf_b200.distributed import allreduce_grads_
+    from adaptive_city_nerf_b200.nerfs.losses import mse_in_color_space
+    from adaptive_city_nerf_b200.optim import FusedAdam
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -220,21 +222,22 @@ def run_ours(args):
     rays, gt, box = gpu_workload(dev, seed=100 + rank)
     model = make_model(dev, box)
     groups = model.get_param_groups()
-    opt = torch.optim.Adam([{"params": groups["encoding"]["params"], "lr": 1e-2},
-                            {"params": groups["sigma"]["params"], "lr": 2e-3},
-                            {"params": groups["color"]["params"], "lr": 2e-3}], eps=1e-15, fused=True)
+    # reference: common/utils.py get_optimizer (Adam over the encoding / sigma / color groups, configs/train.json lrs)
+    opt = FusedAdam([{"params": groups["encoding"]["params"], "lr": 1e-2},
+                     {"params": groups["sigma"]["params"], "lr": 2e-3},
+                     {"params": groups["color"]["params"], "lr": 2e-3}], eps=1e-15)
     params = [p for g in opt.param_groups for p in g["params"]]
 
     def step(r, g):
         with torch.autocast("cuda", dtype=torch.float16):
             rgb, _, _, _ = render_rays(model, r, ray_samples=SAMPLES, active_module=0, chunk=1 << 30)
-        loss = torch.nn.functional.mse_loss(rgb, g)
+        loss = mse_in_color_space(rgb, g, "linear")               # nerfs/losses.py:29-32, args.py default colour space
         opt.zero_grad(set_to_none=True)
         loss.backward()
         if world > 1:
             allreduce_grads_(params, average=True)
-        opt.step()
-        return loss
+        opt.step(max_norm=1.0)                                    # meta_core.py:181-190 clip_all_grads + Adam, one pass
+        return loss.detach()
 
     def sync():
         if world > 1:
@@ -326,7 +329,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"single Instant-NGP expert (L16 F2 T=2^{LOG2T}, 64-wide MLPs), 2^18 rays/batch x {SAMPLES} "
-                                   "samples, training step = render_rays fwd + MSE + bwd + fused Adam (configs[1])",
+                                   "samples, training step = render_rays fwd + colour-space MSE + bwd + grad clip + Adam (configs[1])",
                        "rays_per_step_per_gpu": N_RAYS, "samples_per_ray": SAMPLES, "parallelism": f"dp{world}",
                        "l2": "inputs > L2: 64 MiB table + 1 GiB fp16 encodings + 2 GiB fp32 dL/denc per step"},
             "samples_per_s": world * N_RAYS * SAMPLES * args.steps / (ms * 1e-3),

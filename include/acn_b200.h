@@ -23,7 +23,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define ACN_VERSION 101 /* major*100 + minor */
+#define ACN_VERSION 102 /* major*100 + minor */
 
 typedef struct acn_ctx acn_ctx;
 typedef void* acn_stream; /* cudaStream_t */
@@ -184,6 +184,50 @@ int acn_blend_add(acn_ctx*, const float* y, const float* w, const int32_t* sel, 
 /* d_y[i] = d_out[sel[i]] * w[i] */
 int acn_blend_bwd(acn_ctx*, const float* d_out, const float* w, const int32_t* sel, int64_t M,
                   float* d_y, acn_stream);
+
+/* ---- around the render: loss epilogue and optimizer tail --------------- */
+enum { ACN_COLOR_LINEAR = 0, ACN_COLOR_SRGB = 1, ACN_COLOR_IDENTITY = 2 };
+#define ACN_LOSS_PARTIALS 1024   /* doubles of workspace acn_color_mse may use */
+#define ACN_ADAM_MAX_TENSORS 48  /* tensors per acn_grad_sqnorm / acn_adam_apply call */
+
+/* nerfs/color_space.py:22-66 color_space_transformer + nerfs/losses.py:32 F.mse_loss in one pass over n = 3N
+ * elements: pred is the rendered LINEAR rgb, gt the sRGB ground truth.  loss_or_null (1): mean (mean != 0) or sum of
+ * the squared errors; elem_or_null (n): the squared errors (reduction="none"); dpred_or_null (n): d loss / d pred
+ * (already divided by n when mean != 0).  partial: ACN_LOSS_PARTIALS doubles of workspace, summed in a fixed order.
+ * In sRGB mode the gradient at pred == 0 is the linear branch's (the reference's is NaN there). */
+int acn_color_mse(acn_ctx*, const float* pred, const float* gt, int64_t n, int color_space, int mean,
+                  float* loss_or_null, float* elem_or_null, float* dpred_or_null, double* partial, acn_stream);
+
+/* One parameter tensor of an optimizer step (host struct, copied into the kernel arguments). */
+typedef struct {
+    float* p;            /* parameter */
+    float* g;            /* gradient, possibly still multiplied by the GradScaler scale */
+    float* m;            /* exp_avg */
+    float* v;            /* exp_avg_sq */
+    int64_t n;
+    double lr;           /* the param group's lr */
+    double weight_decay; /* the param group's weight decay */
+} acn_adam_tensor;
+
+/* Optimizer tail of pipelines/offline_stage/meta_core.py:123-141 maml_meta_update (scaler.unscale_ ->
+ * clip_all_grads :181-190 -> scaler.step) and pipelines/online_stage/runtime_adapt.py:262-268, for
+ * common/utils.py:16-76 get_optimizer's Adam / AdamW, without reading anything back to the host:
+ *   acn_grad_sqnorm : acc2[0] += sum (g / scale)^2, acc2[1] += [any element non-finite]; call once per <= 48 tensors.
+ *   acn_adam_prepare: one thread decides the step.  state8 (doubles, persistent; zero before the first step) =
+ *                     [step, coef = clip / scale, skip, bias_correction1, sqrt(bias_correction2), total_norm, -, -];
+ *                     skip when any gradient (or *found_inf_or_null) is non-finite, as GradScaler.step does;
+ *                     clip = min(1, max_norm / (total_norm + 1e-6)) when max_norm > 0 (torch clip_grad_norm_);
+ *                     acc2 is cleared; found_inf_out_or_null (1 float) is for GradScaler.update().
+ *   acn_adam_apply  : torch.optim.Adam (adamw = 0) / AdamW (adamw = 1) update of <= 48 tensors with the gradient
+ *                     multiplied by coef on the fly; write_grads != 0 also stores the unscaled, clipped gradient
+ *                     back (what the reference leaves in .grad). */
+int acn_grad_sqnorm(acn_ctx*, const acn_adam_tensor* tensors, int count, const float* grad_scale_or_null,
+                    double* acc2, acn_stream);
+int acn_adam_prepare(acn_ctx*, double* acc2, const float* grad_scale_or_null, const float* found_inf_or_null,
+                     float max_norm, double beta1, double beta2, double* state8, float* found_inf_out_or_null,
+                     acn_stream);
+int acn_adam_apply(acn_ctx*, const acn_adam_tensor* tensors, int count, const double* state8, double beta1,
+                   double beta2, double eps, int adamw, int write_grads, acn_stream);
 
 /* ---- diagnostics ---------------------------------------------------------------------------- */
 /* One tcgen05 tile GEMM  D(128,N) = A(128,K) * W(N,K)^T  (fp16 in, fp32 out); validates the

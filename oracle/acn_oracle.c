@@ -764,3 +764,102 @@ ORC_API void orc_blend(const float* y_all, int64_t P, int K, const float* weight
             out[4 * p + c] = acc;
         }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Around the render: loss epilogue and optimizer tail
+ * ---------------------------------------------------------------------------------------- */
+
+static inline float orc_clamp01_nan(float x) { return x != x ? x : clampf(x, 0.0f, 1.0f); }
+
+/* nerfs/color_space.py:13-19 srgb_to_linear.  torch evaluates tensor / python-scalar as a multiplication with the
+ * fp32-rounded reciprocal. */
+static inline float orc_srgb_to_linear(float x)
+{
+    return x <= 0.04045f ? x * (1.0f / 12.92f) : powf((x + 0.055f) * (1.0f / 1.055f), 2.4f);
+}
+
+/* nerfs/color_space.py:22-66 color_space_transformer (cs: 0 linear, 1 srgb, 2 identity) followed by
+ * nerfs/losses.py:32 F.mse_loss.  elem (n): squared errors; dpred (n): d(sum of squared errors)/d pred, i.e. NOT yet
+ * divided by n; returns the sum of the squared errors (double accumulation).  At pred == 0 in sRGB mode autograd
+ * differentiates the unselected pow branch of torch.where (color_space.py:6-10) and returns NaN; this restatement
+ * (like the CUDA kernel) reports the selected linear branch's slope there -- the one documented deviation. */
+ORC_API double orc_color_mse(const float* pred, const float* gt, int64_t n, int cs, float* elem, float* dpred)
+{
+    double sum = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float p = pred[i], g01 = orc_clamp01_nan(gt[i]);
+        float pp, gg, dpp;
+        if (cs == 0) {
+            pp = orc_clamp01_nan(p);
+            dpp = (p >= 0.0f && p <= 1.0f) ? 1.0f : 0.0f;
+            gg = orc_clamp01_nan(orc_srgb_to_linear(g01));
+        } else if (cs == 1) {
+            const float x = orc_clamp01_nan(p), e = (float)(1.0 / 2.4);
+            const int lin = x <= 0.0031308f;
+            const float y = lin ? 12.92f * x : 1.055f * powf(x, e) - 0.055f;
+            const float dy = lin ? 12.92f : 1.055f * e * powf(x, e - 1.0f);
+            pp = orc_clamp01_nan(y);
+            dpp = (p >= 0.0f && p <= 1.0f && y >= 0.0f && y <= 1.0f) ? dy : 0.0f;
+            gg = g01;
+        } else {
+            pp = p; dpp = 1.0f; gg = g01;
+        }
+        const float d = pp - gg, se = d * d;
+        if (elem) elem[i] = se;
+        if (dpred) dpred[i] = 2.0f * d * dpp;
+        sum += (double)se;
+    }
+    return sum;
+}
+
+/* One optimizer step as pipelines/offline_stage/meta_core.py:123-141 maml_meta_update runs it:
+ *   scaler.unscale_  (g *= 1/scale, any non-finite g -> skip the step),
+ *   clip_all_grads   (:181-190 -> torch clip_grad_norm_: coef = min(1, max_norm / (||g||_2 + 1e-6)), g *= coef),
+ *   optimizer.step   (torch.optim.Adam, or AdamW when adamw != 0; common/utils.py:16-76 picks them).
+ * T tensors p/g/m/v of sizes n[], per-tensor lr/wd (the parameter groups).  step_io: number of steps taken so far
+ * (incremented unless skipped).  g is overwritten with the unscaled, clipped gradient.  Returns the total norm;
+ * *skipped is set when a gradient was not finite.  Constants are rounded from doubles exactly where torch rounds. */
+ORC_API float orc_adam_step(int T, float** p, float** g, float** m, float** v, const int64_t* n, const double* lr,
+                            const double* wd, double beta1, double beta2, double eps, int adamw, float grad_scale,
+                            float max_norm, double* step_io, int* skipped)
+{
+    const float inv = grad_scale > 0.0f ? 1.0f / grad_scale : 1.0f;
+    int bad = 0;
+    double sq = 0.0;
+    for (int t = 0; t < T; ++t)
+        for (int64_t i = 0; i < n[t]; ++i) {
+            g[t][i] = g[t][i] * inv;
+            if (!isfinite(g[t][i])) bad = 1;
+            sq += (double)g[t][i] * (double)g[t][i];
+        }
+    const float norm = (float)sqrt(sq);
+    *skipped = bad;
+    if (bad) return norm;
+    if (max_norm > 0.0f) {
+        float coef = max_norm / (norm + 1e-6f);
+        if (coef > 1.0f) coef = 1.0f;
+        for (int t = 0; t < T; ++t)
+            for (int64_t i = 0; i < n[t]; ++i) g[t][i] = g[t][i] * coef;
+    }
+    *step_io += 1.0;
+    const double bc1 = 1.0 - pow(beta1, *step_io), bc2 = 1.0 - pow(beta2, *step_io);
+    const float omb1 = (float)(1.0 - beta1), b2 = (float)beta2, omb2 = (float)(1.0 - beta2);
+    const float bc2s = (float)sqrt(bc2), epsf = (float)eps;
+    for (int t = 0; t < T; ++t) {
+        const float step_size = (float)(lr[t] / bc1), wdf = (float)wd[t], lr_wd = (float)(lr[t] * wd[t]);
+        for (int64_t i = 0; i < n[t]; ++i) {
+            float gi = g[t][i], pi = p[t][i];
+            if (wdf != 0.0f) {
+                if (adamw) pi = pi - lr_wd * pi;
+                else gi = fmaf(wdf, pi, gi);
+            }
+            const float mi = m[t][i] + omb1 * (gi - m[t][i]);
+            const float vi = b2 * v[t][i] + omb2 * gi * gi;
+            const float denom = sqrtf(vi) / bc2s + epsf;
+            p[t][i] = pi - step_size * (mi / denom);
+            m[t][i] = mi;
+            v[t][i] = vi;
+        }
+    }
+    return norm;
+}

@@ -297,3 +297,47 @@ def render_expert(rays, S, ws, table, box_min, extent, L, F, log2T, res, jitter=
     rs = field_fwd(enc, dirs, ws, half=half)
     out = composite_fwd(rs.reshape(rays.shape[0], S, 4), t, bg)
     return out + (dict(t=t, x01=x01, enc=enc, dirs=dirs, rgb_sigma=rs),)
+
+
+COLOR_SPACE = {"linear": 0, "srgb": 1, "identity": 2}
+
+
+def color_mse(pred, gt, color_space="linear", reduction="mean"):
+    """color_space_transformer + F.mse_loss -> (loss or per-element squared errors, d loss / d pred)."""
+    p, g = _f(pred), _f(np.broadcast_to(gt, np.shape(pred)))
+    elem, dpred = np.empty_like(p), np.empty_like(p)
+    fn = lib().orc_color_mse
+    fn.restype = C.c_double
+    s = fn(_p(p), _p(g), C.c_int64(p.size), COLOR_SPACE[color_space], _p(elem), _p(dpred))
+    if reduction == "none":
+        return elem, dpred
+    if reduction == "sum":
+        return F32(s), dpred
+    return F32(s / p.size) if p.size else F32(np.nan), (dpred / F32(p.size)).astype(F32)
+
+
+class AdamState:
+    """Parameters, moments and step count of orc_adam_step (arrays are updated in place)."""
+
+    def __init__(self, params, lrs, wds=None, betas=(0.9, 0.999), eps=1e-8, adamw=False):
+        self.p = [_f(a).copy() for a in params]
+        self.m = [np.zeros_like(a) for a in self.p]
+        self.v = [np.zeros_like(a) for a in self.p]
+        self.lr = np.asarray(lrs, np.float64)
+        self.wd = np.zeros(len(self.p)) if wds is None else np.asarray(wds, np.float64)
+        self.betas, self.eps, self.adamw = betas, eps, adamw
+        self.step = C.c_double(0.0)
+
+    def update(self, grads, grad_scale=1.0, max_norm=0.0):
+        """-> (total_norm, skipped); returns the unscaled, clipped gradients in `self.g`."""
+        T = len(self.p)
+        self.g = [_f(a).copy() for a in grads]
+        arr = lambda xs: (C.c_void_p * T)(*[x.ctypes.data for x in xs])
+        n = (C.c_int64 * T)(*[x.size for x in self.p])
+        skipped = C.c_int(0)
+        fn = lib().orc_adam_step
+        fn.restype = C.c_float
+        norm = fn(T, arr(self.p), arr(self.g), arr(self.m), arr(self.v), n, _p(self.lr), _p(self.wd),
+                  C.c_double(self.betas[0]), C.c_double(self.betas[1]), C.c_double(self.eps), int(self.adamw),
+                  C.c_float(grad_scale), C.c_float(max_norm or 0.0), C.byref(self.step), C.byref(skipped))
+        return float(norm), bool(skipped.value)

@@ -44,7 +44,7 @@ F32 = np.float32
 def save(name, **arrs):
     np.savez_compressed(HERE / name, **{k: np.asarray(v) for k, v in arrs.items()})
     sz = (HERE / name).stat().st_size
-    print(f"  {name}: {sz / 1024:.1f} KiB, keys={list(arrs)}")
+    print(f"  {name}: {sz / 1024:.1f} KiB, keys={list(arrs)[:12]}{' ...' if len(arrs) > 12 else ''}")
 
 
 # --------------------------------------------------------------------------- stage 1
@@ -500,6 +500,65 @@ def gen_train():
     save("train.npz", **out)
 
 
+# --------------------------------------------------------------------------- loss epilogue / optimizer tail
+def gen_loss():
+    """nerfs/color_space.py color_space_transformer + F.mse_loss (nerfs/losses.py:29-32) and autograd's d loss/d pred."""
+    from nerfs.color_space import color_space_transformer
+    pred_np, gt_np = synth.loss_inputs()
+    out = {}
+    for cs in ("linear", "srgb", "identity"):
+        p = T(pred_np).clone().requires_grad_()
+        a, b = color_space_transformer(p, T(gt_np), cs)
+        loss = torch.nn.functional.mse_loss(a, b, reduction="mean")
+        loss.backward()
+        out[f"{cs}_loss"] = loss.detach().numpy()
+        out[f"{cs}_grad"] = p.grad.numpy()          # sRGB: NaN where pred == 0 (0 * inf in the unselected pow branch)
+        out[f"{cs}_elem"] = torch.nn.functional.mse_loss(a, b, reduction="none").detach().numpy()
+    save("loss.npz", **out)
+
+
+def gen_optim():
+    """common/utils.py get_optimizer + pipelines/offline_stage/meta_core.py maml_meta_update (GradScaler.unscale_,
+    clip_all_grads, scaler.step, scaler.update) on CPU, for Adam and AdamW."""
+    from common.utils import get_optimizer
+    from pipelines.offline_stage.meta_core import maml_meta_update
+    import contextlib, io as _io
+    params_np, grads_np = synth.optim_inputs()
+    out = {}
+    for name, wd in (("adam", 0.0), ("adamw", 0.05), ("adam_wd", 0.05)):
+        class Holder(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.ps = torch.nn.ParameterList([torch.nn.Parameter(T(a).clone()) for a in params_np])
+            def get_param_groups(self):
+                g = {}
+                for (grp, _), p in zip(synth.OPTIM_SHAPES, self.ps):
+                    g.setdefault(grp, {"params": []})["params"].append(p)
+                return g
+        m = Holder()
+        P = types.SimpleNamespace(lr=1e-3, encoding_lr=synth.OPTIM_LRS["encoding"], sigma_lr=synth.OPTIM_LRS["sigma"],
+                                  color_lr=synth.OPTIM_LRS["color"], bg_lr=synth.OPTIM_LRS["background"],
+                                  optimizer="adamw" if name == "adamw" else "adam", weight_decay=wd)
+        opt = get_optimizer(P, m)
+        scaler = torch.amp.GradScaler("cpu", init_scale=65536.0, growth_interval=2)
+        scales = []
+        for it, gs in enumerate(grads_np):
+            scales.append(scaler.get_scale())
+            loss = sum((p * T(g)).sum() for p, g in zip(m.ps, gs))
+            with contextlib.redirect_stdout(_io.StringIO()):
+                maml_meta_update(opt, loss, scaler, grad_clip=1.0)
+            if it in synth.OPTIM_KEEP:
+                for k, p in enumerate(m.ps):
+                    out[f"{name}_p{k}_step{it}"] = p.detach().numpy().copy()
+        out[f"{name}_scales"] = np.array(scales + [scaler.get_scale()], np.float64)
+        if name == "adam":
+            for k, p in enumerate(m.ps):
+                out[f"{name}_m{k}"] = opt.state[p]["exp_avg"].numpy().copy()
+                out[f"{name}_v{k}"] = opt.state[p]["exp_avg_sq"].numpy().copy()
+        out[f"{name}_steps"] = np.float64(float(opt.state[m.ps[0]]["step"]))
+    save("optim.npz", **out)
+
+
 if __name__ == "__main__":
     which = set(sys.argv[1:])
     cc = None
@@ -515,3 +574,5 @@ if __name__ == "__main__":
     if want("voronoi"): gen_voronoi(cc)
     if want("render"): gen_render()
     if want("train"): gen_train()
+    if want("loss"): gen_loss()
+    if want("optim"): gen_optim()

@@ -105,3 +105,36 @@ def nadir_rays(seed, n_views, H=64, W=64, f=60.0):
         yaw = rng.uniform(-np.pi, np.pi)
         cams.append(dict(H=H, W=W, fx=f, fy=f, cx=W / 2.0, cy=H / 2.0, c2w=camera_c2w(y, z, yaw)))
     return cams
+
+
+def loss_inputs(seed=61, N=341):
+    """Rendered linear rgb (some outside [0,1], some exactly on the clamp / sRGB thresholds) and sRGB targets."""
+    rng = np.random.default_rng(seed)
+    pred = rng.uniform(-0.15, 1.15, size=(N, 3)).astype(F32)
+    gt = rng.uniform(-0.05, 1.05, size=(N, 3)).astype(F32)
+    pred[:12, 0] = np.array([0.0, 1.0, 0.0031308, 0.0031309, 1e-4, 2e-3, 0.5, -0.0, 1.0000001, 0.99999994, 3e-3, 4e-3], F32)
+    gt[:6, 1] = np.array([0.04045, 0.04046, 0.0, 1.0, 0.04, 0.05], F32)
+    return pred, gt
+
+
+#: parameter tensors of the optimizer fixture: (group name, shape); sizes chosen to hit the kernels' vector and tail paths
+OPTIM_SHAPES = [("encoding", (515, 2)), ("sigma", (32, 16)), ("sigma", (64,)), ("sigma", (1, 64)), ("sigma", (1,)),
+                ("color", (21, 31)), ("color", (3, 64)), ("color", (3,)), ("background", (32, 16)), ("background", (3,))]
+#: steps whose parameters the fixture stores (2: clipped, 3: skipped by the scaler, 5: last)
+OPTIM_KEEP = (2, 3, 5)
+OPTIM_LRS = {"encoding": 1e-2, "sigma": 2e-3, "color": 2e-3, "background": 1e-3}
+
+
+def optim_inputs(seed=67, steps=6):
+    """Initial parameters and one gradient set per step; step 3 (0-based) carries a gradient that overflows under the
+    loss scale, so GradScaler must skip it; step 1 has a tiny norm (no clipping), the others are clipped."""
+    rng = np.random.default_rng(seed)
+    params = [rng.uniform(-0.5, 0.5, size=s).astype(F32) for _, s in OPTIM_SHAPES]
+    grads = []
+    for it in range(steps):
+        scale = 1e-3 if it == 1 else 0.3
+        gs = [(rng.standard_normal(size=s) * scale).astype(F32) for _, s in OPTIM_SHAPES]
+        if it == 3:
+            gs[1][5, 7] = F32(3e35)
+        grads.append(gs)
+    return params, grads

@@ -39,7 +39,7 @@ def test_ctypes_table_matches_header(built_lib):
     from adaptive_city_nerf_b200 import _lib
     assert sorted(_lib.SIGNATURES) == header_symbols()
     l = _lib.lib()
-    assert l.acn_version() == 101
+    assert l.acn_version() == 102
     for name in _lib.SIGNATURES:
         assert getattr(l, name).argtypes == _lib.SIGNATURES[name]
     assert len(_lib.SIGNATURES["acn_hashgrid_fwd"]) == 15 and len(_lib.SIGNATURES["acn_field_bwd"]) == 18
@@ -157,3 +157,44 @@ def test_linspace_table_is_reference_cpu_linspace(golden):
     for S in (2, 3, 16, 17, 64, 65, 96, 255, 256):
         t = torch.linspace(0.0, 1.0, S)
         assert (t.numpy().view(np.uint32) == g[f"linspace_{S}"].view(np.uint32)).all()
+
+
+def test_train_step_host_logic_without_gpu(built_lib):
+    """Loss epilogue / optimizer tail: argument checks and the reference's get_optimizer grouping need no device; the
+    struct the optimizer hands to the C ABI has the header's layout; compute refuses CPU tensors."""
+    import ctypes as C
+    import types
+    from adaptive_city_nerf_b200 import _lib, ops
+    from adaptive_city_nerf_b200.optim import FusedAdam, get_optimizer
+    assert C.sizeof(_lib.AdamTensor) == 56                                 # 4 pointers + int64 + 2 doubles
+    hdr = (ROOT / "include" / "acn_b200.h").read_text()
+    assert f"#define ACN_ADAM_MAX_TENSORS {_lib.ADAM_MAX_TENSORS}" in hdr and f"#define ACN_LOSS_PARTIALS {_lib.LOSS_PARTIALS}" in hdr
+    with pytest.raises(ValueError):
+        ops.color_mse(torch.zeros(2, 3), torch.zeros(2, 3), "hsv")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.color_mse(torch.zeros(2, 3), torch.zeros(2, 3), "linear")
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.t, self.s, self.c, self.b = (torch.nn.Parameter(torch.zeros(n)) for n in (8, 4, 3, 2))
+
+        def get_param_groups(self):
+            return {"background": {"params": [self.b]}, "color": {"params": [self.c]}, "sigma": {"params": [self.s]},
+                    "encoding": {"params": [self.t]}}
+
+    P = types.SimpleNamespace(lr=5e-4, encoding_lr=1e-2, sigma_lr=None, color_lr=2e-3, optimizer="adamw", weight_decay=0.01)
+    opt = get_optimizer(P, Holder())
+    assert [(g["name"], g["lr"], g["weight_decay"]) for g in opt.param_groups] == [
+        ("encoding", 1e-2, 0.01), ("sigma", 5e-4, 0.01), ("color", 2e-3, 0.01), ("background", 5e-4, 0.01)]
+    assert opt.adamw and isinstance(opt, FusedAdam) and FusedAdam._step_supports_amp_scaling
+    P.optimizer = "sgd"
+    with pytest.raises(ValueError):
+        get_optimizer(P, Holder())
+    with pytest.raises(ValueError):
+        FusedAdam([torch.nn.Parameter(torch.zeros(1))], betas=(1.0, 0.999))
+    opt.param_groups[0]["params"][0].grad = torch.zeros(8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        opt.step()
+    opt2 = FusedAdam([torch.nn.Parameter(torch.zeros(1))])
+    opt2.step()                                                             # nothing has a gradient: a no-op, as in torch

@@ -283,3 +283,51 @@ def test_container_blend(orc, golden, tag, margin):
     np.testing.assert_allclose(rgb, g[f"{tag}.rgb"], atol=5e-6, rtol=0)
     np.testing.assert_allclose(dep, g[f"{tag}.depth"], atol=5e-6, rtol=0)
     np.testing.assert_allclose(acc, g[f"{tag}.acc"], atol=5e-6, rtol=0)
+
+
+# ----------------------------------------------------------------------------- loss epilogue / optimizer tail
+@pytest.mark.parametrize("cs", ["linear", "srgb", "identity"])
+def test_color_mse_vs_reference(orc, golden, cs):
+    """color_space_transformer + F.mse_loss and autograd's gradient (nerfs/color_space.py, nerfs/losses.py:29-32)."""
+    g = golden("loss")
+    pred, gt = synth.loss_inputs()
+    loss, dpred = orc.color_mse(pred, gt, cs, "mean")
+    elem, _ = orc.color_mse(pred, gt, cs, "none")
+    np.testing.assert_allclose(elem, g[f"{cs}_elem"], rtol=0, atol=5e-7)     # powf vs torch.pow differ by an ulp; squared
+    np.testing.assert_allclose(loss, g[f"{cs}_loss"], rtol=2e-6)
+    ref = g[f"{cs}_grad"]
+    nan = np.isnan(ref)
+    if cs == "srgb":
+        # the reference's gradient is NaN exactly where pred == 0 (0 * inf in torch.where's unselected pow branch);
+        # the restatement reports the selected linear branch there: 2 (0 - gt) * 12.92 / n
+        assert (nan == (pred == 0.0)).all() and nan.sum() == 2
+        want = 2.0 * (0.0 - np.clip(gt[nan], 0, 1)) * 12.92 / pred.size
+        np.testing.assert_allclose(dpred[nan], want, rtol=1e-6)
+    else:
+        assert not nan.any()
+    np.testing.assert_allclose(dpred[~nan], ref[~nan], rtol=2e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("name,adamw,wd", [("adam", False, 0.0), ("adamw", True, 0.05), ("adam_wd", False, 0.05)])
+def test_adam_step_vs_reference(orc, golden, name, adamw, wd):
+    """get_optimizer + maml_meta_update (unscale_, clip_all_grads at 1.0, scaler.step, scaler.update) on CPU torch."""
+    g = golden("optim")
+    params, grads = synth.optim_inputs()
+    lrs = [synth.OPTIM_LRS[grp] for grp, _ in synth.OPTIM_SHAPES]
+    st = orc.AdamState(params, lrs, [wd] * len(params), adamw=adamw)
+    scales = g[f"{name}_scales"]
+    skipped = []
+    for it, gs in enumerate(grads):
+        with np.errstate(over="ignore"):
+            scaled = [(a * F32(scales[it])).astype(F32) for a in gs]           # what scaler.scale(loss).backward() leaves in .grad
+        norm, skip = st.update(scaled, grad_scale=float(scales[it]), max_norm=1.0)
+        skipped.append(skip)
+        if it in synth.OPTIM_KEEP:
+            for k, p in enumerate(st.p):
+                np.testing.assert_allclose(p, g[f"{name}_p{k}_step{it}"], rtol=2e-6, atol=2e-7, err_msg=f"step {it} tensor {k}")
+    assert skipped == [False, False, False, True, False, False]
+    assert st.step.value == float(g[f"{name}_steps"]) == 5.0
+    if name == "adam":
+        for k in range(len(st.p)):
+            np.testing.assert_allclose(st.m[k], g[f"adam_m{k}"], rtol=2e-6, atol=1e-9)
+            np.testing.assert_allclose(st.v[k], g[f"adam_v{k}"], rtol=2e-6, atol=1e-12)
