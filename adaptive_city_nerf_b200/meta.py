@@ -8,8 +8,9 @@ behind `render_rays` is capture-safe (no host syncs; scratch is chosen at captur
 the whole adaptation once and replays it per task: 0.99 -> 0.30 ms per inner step on a B200 (tools/bench_inner.py),
 with bit-identical adapted weights.
 
-Scope: `algo` in {fomaml, reptile} (first order, `create_graph=False`) and the plain MSE loss
-(nerfs/losses.py:10-32); FIM-weighted losses and second-order MAML stay on the eager path."""
+Scope: `algo` in {fomaml, reptile} (first order, `create_graph=False`) and the MSE loss in `P.color_space`
+(nerfs/losses.py:10-32 compute_mse_loss; one `acn_color_mse` launch); FIM-weighted losses and second-order MAML stay on
+the eager path."""
 from __future__ import annotations
 
 from collections import OrderedDict
@@ -18,20 +19,29 @@ from typing import Callable, List, Optional, Tuple
 import torch
 from torch import Tensor
 
+from .nerfs.losses import mse_in_color_space
 from .nerfs.ray_rendering import render_rays
+
+
+def _loss_of(loss_fn, color_space: str):
+    if loss_fn is not None:
+        return loss_fn
+    return lambda pred, rgbs: mse_in_color_space(pred, rgbs, color_space, "mean")
 
 
 def task_adapt_eager(model, rays: Tensor, rgbs: Tensor, *, active_module: int, ray_samples: int, iterations: int,
                      inner_lr: float, use_amp: bool = True, fast: Optional[OrderedDict] = None,
-                     loss_fn: Callable[[Tensor, Tensor], Tensor] = torch.nn.functional.mse_loss,
+                     loss_fn: Optional[Callable[[Tensor, Tensor], Tensor]] = None, color_space: str = "linear",
                      chunk: int = 1 << 30, detach_updates: bool = False) -> Tuple[OrderedDict, List[Tensor]]:
     """meta_core.py:14-68 for the first-order algorithms, launch by launch (the reference's own control flow).
+    The loss is compute_mse_loss's (colour-space transform + MSE, `color_space` = P.color_space) unless `loss_fn` is given.
     detach_updates=True applies each SGD step as one multi-tensor kernel outside autograd (the adapted weights then
     carry no history back to theta -- what a captured graph returns anyway)."""
     base = model.submodules[active_module]
     if fast is None:
         fast = OrderedDict((n, p) for n, p in base.meta_named_parameters())
     losses = []
+    loss_fn = _loss_of(loss_fn, color_space)
     for _ in range(int(iterations)):
         with torch.autocast("cuda", enabled=use_amp, dtype=torch.float16):
             pred, *_ = render_rays(model, rays, ray_samples=ray_samples, params=fast, active_module=active_module, chunk=chunk)
@@ -60,8 +70,8 @@ class GraphedTaskAdapt:
     """
 
     def __init__(self, model, *, active_module: int, n_rays: int, ray_samples: int, iterations: int, inner_lr: float,
-                 use_amp: bool = True, loss_fn: Callable[[Tensor, Tensor], Tensor] = torch.nn.functional.mse_loss,
-                 warmup: int = 3):
+                 use_amp: bool = True, loss_fn: Optional[Callable[[Tensor, Tensor], Tensor]] = None,
+                 color_space: str = "linear", warmup: int = 3):
         self.model, self.cid = model, int(active_module)
         self.expert = model.submodules[self.cid]
         dev = next(self.expert.parameters()).device
@@ -74,7 +84,7 @@ class GraphedTaskAdapt:
         self.rgbs = torch.zeros(n_rays, 3, dtype=torch.float32, device=dev)
         self._w = OrderedDict((n, p.detach().clone().requires_grad_(True)) for n, p in self.expert.meta_named_parameters())
         kw = dict(active_module=self.cid, ray_samples=int(ray_samples), iterations=int(iterations), inner_lr=float(inner_lr),
-                  use_amp=bool(use_amp), loss_fn=loss_fn, detach_updates=True)
+                  use_amp=bool(use_amp), loss_fn=loss_fn, color_space=color_space, detach_updates=True)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                       # warm-up off the capture: lazy tables, cuda attributes, allocator

@@ -176,15 +176,18 @@ def test_training_psnr_matches_reference(golden):
     assert abs(final - float(g["final_eval_psnr"])) < 0.1
 
 
-def test_graphed_task_adapt_matches_eager(golden):
+@pytest.mark.parametrize("loss", ["linear", "srgb", "plain"])
+def test_graphed_task_adapt_matches_eager(golden, loss):
     """The inner loop (meta_core.py:14-68, first order) replayed as one CUDA graph gives the weights the launch-by-launch
-    loop gives, task after task, and its fast weights drive a first-order outer gradient."""
+    loop gives, task after task, and its fast weights drive a first-order outer gradient.  Loss: compute_mse_loss in
+    P.color_space (the fused epilogue) or a caller-supplied function."""
     from adaptive_city_nerf_b200.meta import GraphedTaskAdapt, accumulate_first_order_grads, task_adapt_eager
     from adaptive_city_nerf_b200.nerfs.ray_rendering import render_rays
     m = make_container(1, np.zeros((1, 3), F32), [synth.AABB_GLOBAL], 1.0, False, seed0=500).eval()   # eval: no jitter
     ex = m.submodules[0]
     N, S = 1500, 24
     kw = dict(active_module=0, ray_samples=S, iterations=4, inner_lr=5e-2)
+    kw.update(dict(loss_fn=torch.nn.functional.mse_loss) if loss == "plain" else dict(color_space=loss))
     adapt = GraphedTaskAdapt(m, n_rays=N, **kw)
     for task in range(3):
         o, d = synth.random_rays_in_box(600 + task, N)
