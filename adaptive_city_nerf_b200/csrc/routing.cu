@@ -7,6 +7,8 @@
 #include "acn_common.cuh"
 
 #define FULL 0xffffffffu
+static constexpr int ROUTE_THREADS = 512;    // points per block of the routing / bucketing kernels
+static constexpr int ROUTE_WARPS = ROUTE_THREADS / 32;
 
 template <int DIMS>
 __device__ __forceinline__ float cdist_mm(const float* x, const float* __restrict__ c) {
@@ -24,21 +26,60 @@ __device__ __forceinline__ float cdist_mm(const float* x, const float* __restric
     return __fsqrt_rn(fmaxf(acc, 0.0f));
 }
 
-template <int DIMS>
-__global__ void __launch_bounds__(256) k_route_points(
+// Per-expert counts are aggregated per block in shared memory (one global atomic per expert per block): with a warp
+// per atomic, a 1080p frame issued ~35 M atomics onto the two or three counters a view touches and the kernel ran at
+// the L2's same-address atomic rate instead of memory bandwidth.
+template <int DIMS, int KT>
+__global__ void __launch_bounds__(ROUTE_THREADS) k_route_points(
     const float* __restrict__ pts, int64_t P, int stride, const float* __restrict__ cen, int K, float margin,
     float* __restrict__ weights, int32_t* __restrict__ hard, int32_t* __restrict__ counts)
 {
+    extern __shared__ int s_cnt[];   // K ints (only when counts != nullptr)
     constexpr int OFF = DIMS == 2 ? 1 : 0;
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = p < P;
     const int lane = threadIdx.x & 31;
+    if (counts) {
+        for (int k = threadIdx.x; k < K; k += blockDim.x) s_cnt[k] = 0;
+        __syncthreads();
+    }
     float x[3] = { 0.f, 0.f, 0.f };
     if (on) {
 #pragma unroll
         for (int k = 0; k < DIMS; ++k) x[k] = pts[p * stride + OFF + k];
     }
-    if (weights) {
+    if (weights && KT > 0) {
+        // K == KT experts: distances computed once and kept in registers, weights stored as float4s
+        float d[KT > 0 ? KT : 1];
+        float mind = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            d[k] = fmaxf(cdist_mm<DIMS>(x, cen + 3 * k + OFF), 1e-6f);
+            mind = fminf(mind, d[k]);
+        }
+        const float thr = __fmul_rn(margin, mind);
+        float denom = 0.0f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            d[k] = d[k] <= thr ? __fdiv_rn(1.0f, d[k]) : 0.0f;      // d[k] > 0, so 1/d > 0 marks "in"
+            denom = __fadd_rn(denom, d[k]);
+        }
+        denom = fmaxf(denom, 1e-6f);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const bool in = on && d[k] > 0.0f;
+            d[k] = in ? __fdiv_rn(d[k], denom) : 0.0f;
+            if (counts) {
+                unsigned m = __ballot_sync(FULL, in);
+                if (lane == 0 && m) atomicAdd_block(s_cnt + k, __popc(m));
+            }
+        }
+        if (on) {
+            float4* dst = reinterpret_cast<float4*>(weights + p * KT);
+#pragma unroll
+            for (int q = 0; q < KT / 4; ++q) dst[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+        }
+    } else if (weights) {
         // pass 1: min distance (after the 1e-6 floor); pass 2: masked 1/d sum; pass 3: normalise
         float mind = __int_as_float(0x7f800000);
         for (int k = 0; k < K; ++k) mind = fminf(mind, fmaxf(cdist_mm<DIMS>(x, cen + 3 * k + OFF), 1e-6f));
@@ -56,7 +97,7 @@ __global__ void __launch_bounds__(256) k_route_points(
             if (on) weights[p * K + k] = in ? __fdiv_rn(__fdiv_rn(1.0f, d), denom) : 0.0f;
             if (counts) {
                 unsigned m = __ballot_sync(FULL, in);
-                if (lane == 0 && m) atomicAdd(counts + k, __popc(m));
+                if (lane == 0 && m) atomicAdd_block(s_cnt + k, __popc(m));
             }
         }
     } else {
@@ -70,9 +111,14 @@ __global__ void __launch_bounds__(256) k_route_points(
         if (counts) {
             for (int k = 0; k < K; ++k) {
                 unsigned m = __ballot_sync(FULL, on && best == k);
-                if (lane == 0 && m) atomicAdd(counts + k, __popc(m));
+                if (lane == 0 && m) atomicAdd_block(s_cnt + k, __popc(m));
             }
         }
+    }
+    if (counts) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += blockDim.x)
+            if (s_cnt[k]) atomicAdd(counts + k, s_cnt[k]);
     }
 }
 
@@ -119,35 +165,68 @@ __global__ void __launch_bounds__(128) k_route_rays(
     }
 }
 
-// Device-side bucket: warp-aggregated cursor claim per expert.
-__global__ void __launch_bounds__(256) k_bucket_points(
+// Device-side bucket.  Each block claims ONE contiguous range per expert (one global atomic per expert per block, see
+// k_route_points): warps publish their per-expert counts, one thread per expert scans them and claims the range, then
+// every lane derives its slot from block base + warp prefix + lane prefix.
+template <bool DISPATCH>
+__device__ __forceinline__ void bucket_body(
+    const float* __restrict__ id6, int64_t P, const float* __restrict__ weights, const int32_t* __restrict__ hard,
+    int K, const int32_t* __restrict__ offsets, int32_t* __restrict__ cursor, int32_t* __restrict__ sel,
+    float* __restrict__ xd_out, float* __restrict__ w_out, const unsigned long long* __restrict__ row_base,
+    const int32_t* __restrict__ row_off)
+{
+    extern __shared__ int s_base[];   // ROUTE_WARPS * K ints: per-warp count, then per-warp first index within the expert
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = p < P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = (on && hard) ? hard[p] : -1;
+    for (int k = 0; k < K; ++k) {
+        const float w = weights ? (on ? weights[p * K + k] : 0.0f) : (h == k ? 1.0f : 0.0f);
+        const unsigned m = __ballot_sync(FULL, on && w > 0.0f);
+        if (lane == 0) s_base[warp * K + k] = __popc(m);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        int total = 0;
+        for (int wi = 0; wi < ROUTE_WARPS; ++wi) total += s_base[wi * K + k];
+        int run = total ? atomicAdd(cursor + k, total) : 0;
+        for (int wi = 0; wi < ROUTE_WARPS; ++wi) {
+            const int c = s_base[wi * K + k];
+            s_base[wi * K + k] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    float2 r0 = make_float2(0.f, 0.f), r1 = r0, r2 = r0;
+    if (on && (DISPATCH || xd_out)) {
+        const float2* src = reinterpret_cast<const float2*>(id6 + p * 6);
+        r0 = __ldg(src); r1 = __ldg(src + 1); r2 = __ldg(src + 2);
+    }
+    for (int k = 0; k < K; ++k) {
+        const float w = weights ? (on ? weights[p * K + k] : 0.0f) : (h == k ? 1.0f : 0.0f);
+        const bool in = on && w > 0.0f;
+        const unsigned m = __ballot_sync(FULL, in);
+        if (!in) continue;
+        const int idx = s_base[warp * K + k] + __popc(m & ((1u << lane) - 1u));
+        const int slot = __ldg(offsets + k) + idx;
+        sel[slot] = (int32_t)p;
+        if (w_out) w_out[slot] = w;
+        if (DISPATCH) {
+            float2* dst = reinterpret_cast<float2*>(__ldg(row_base + k)) + ((size_t)__ldg(row_off + k) + idx) * 3;
+            dst[0] = r0; dst[1] = r1; dst[2] = r2;
+        } else if (xd_out) {
+            float2* dst = reinterpret_cast<float2*>(xd_out) + (size_t)slot * 3;
+            dst[0] = r0; dst[1] = r1; dst[2] = r2;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ROUTE_THREADS) k_bucket_points(
     const float* __restrict__ id6, int64_t P, const float* __restrict__ weights, const int32_t* __restrict__ hard,
     int K, const int32_t* __restrict__ offsets, int32_t* __restrict__ cursor, int32_t* __restrict__ sel,
     float* __restrict__ xd_out, float* __restrict__ w_out)
 {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool on = p < P;
-    const int lane = threadIdx.x & 31;
-    const int h = (on && hard) ? hard[p] : -1;
-    for (int k = 0; k < K; ++k) {
-        float w = weights ? (on ? weights[p * K + k] : 0.0f) : (h == k ? 1.0f : 0.0f);
-        bool in = on && w > 0.0f;
-        unsigned m = __ballot_sync(FULL, in);
-        if (!m) continue;
-        int base = 0;
-        int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(cursor + k, __popc(m));
-        base = __shfl_sync(FULL, base, leader);
-        if (in) {
-            int slot = __ldg(offsets + k) + base + __popc(m & ((1u << lane) - 1u));
-            sel[slot] = (int32_t)p;
-            if (w_out) w_out[slot] = w;
-            if (xd_out) {
-#pragma unroll
-                for (int c = 0; c < 6; ++c) xd_out[(size_t)slot * 6 + c] = id6[p * 6 + c];
-            }
-        }
-    }
+    bucket_body<false>(id6, P, weights, hard, K, offsets, cursor, sel, xd_out, w_out, nullptr, nullptr);
 }
 
 // Fused dispatch for expert sharding: the same bucketing, but the routed [xyz, dir] row of expert k is stored straight
@@ -155,36 +234,133 @@ __global__ void __launch_bounds__(256) k_bucket_points(
 // (NVLink peer memory, or local memory for the experts this rank owns), row_off[k] the first row reserved there for
 // (this source rank, expert k).  sel / w_out stay local.  The dispatch half of the all-to-all is therefore the
 // kernel's own store stream; no staging copy, no NCCL send.
-__global__ void __launch_bounds__(256) k_dispatch_points(
+__global__ void __launch_bounds__(ROUTE_THREADS) k_dispatch_points(
     const float* __restrict__ id6, int64_t P, const float* __restrict__ weights, const int32_t* __restrict__ hard,
     int K, const int32_t* __restrict__ offsets, int32_t* __restrict__ cursor, int32_t* __restrict__ sel,
     float* __restrict__ w_out, const unsigned long long* __restrict__ row_base, const int32_t* __restrict__ row_off)
 {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool on = p < P;
-    const int lane = threadIdx.x & 31;
-    const int h = (on && hard) ? hard[p] : -1;
-    float2 r0 = make_float2(0.f, 0.f), r1 = r0, r2 = r0;
-    if (on) {
-        const float2* src = reinterpret_cast<const float2*>(id6 + p * 6);
-        r0 = __ldg(src); r1 = __ldg(src + 1); r2 = __ldg(src + 2);
+    bucket_body<true>(id6, P, weights, hard, K, offsets, cursor, sel, nullptr, w_out, row_base, row_off);
+}
+
+// Routing + bucketing straight from (rays, t): the container's render path without the (P,6) point matrix and the
+// (P,K) weight matrix in HBM (a 1080p frame: 3.2 GB + 4.2 GB written and read back).  Two launches of the same body:
+// COUNT computes every sample's support set (one bit per expert), stores it (2 bytes per sample) and adds up the
+// per-expert row counts -- the one host read that sizes the buckets; BUCKET reads the set back, evaluates distances
+// and weights only for the experts in it (one for all but the few % of samples near a cell boundary), claims one
+// contiguous range per expert per block and writes sel / w / [xyz, dir] rows.  Same arithmetic as k_points +
+// k_route_points (terms outside the set contribute an exact +0 to the normaliser), so rows and weights are
+// bit-identical to the unfused path.
+template <int DIMS, int MAXK>
+__device__ __forceinline__ unsigned support_bits(const float* pos, const float* __restrict__ cen, int K, float margin) {
+    constexpr int OFF = DIMS == 2 ? 1 : 0;
+    unsigned bits = 0;
+    if (margin > 1.0f) {
+        float d[MAXK];
+        float mind = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) {
+            d[k] = 0.0f;
+            if (k < K) { d[k] = fmaxf(cdist_mm<DIMS>(pos + OFF, cen + 3 * k + OFF), 1e-6f); mind = fminf(mind, d[k]); }
+        }
+        const float thr = __fmul_rn(margin, mind);
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+            if (k < K && d[k] <= thr) bits |= 1u << k;
+    } else {                                                // hard: first minimum wins, like argmin
+        int best = 0;
+        float bd = cdist_mm<DIMS>(pos + OFF, cen + OFF);
+#pragma unroll
+        for (int k = 1; k < MAXK; ++k) {
+            if (k < K) { float d = cdist_mm<DIMS>(pos + OFF, cen + 3 * k + OFF); if (d < bd) { bd = d; best = k; } }
+        }
+        bits = 1u << best;
     }
-    for (int k = 0; k < K; ++k) {
-        float w = weights ? (on ? weights[p * K + k] : 0.0f) : (h == k ? 1.0f : 0.0f);
-        bool in = on && w > 0.0f;
-        unsigned m = __ballot_sync(FULL, in);
-        if (!m) continue;
-        int base = 0;
-        int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(cursor + k, __popc(m));
-        base = __shfl_sync(FULL, base, leader);
-        if (in) {
-            const int idx = base + __popc(m & ((1u << lane) - 1u));
-            const int slot = __ldg(offsets + k) + idx;
-            sel[slot] = (int32_t)p;
-            w_out[slot] = w;
-            float2* dst = reinterpret_cast<float2*>(__ldg(row_base + k)) + ((size_t)__ldg(row_off + k) + idx) * 3;
-            dst[0] = r0; dst[1] = r1; dst[2] = r2;
+    return bits;
+}
+
+template <int DIMS, int MAXK, bool BUCKET>
+__global__ void __launch_bounds__(ROUTE_THREADS) k_route_samples(
+    const float* __restrict__ rays8, const float* __restrict__ t_vals, int64_t P, int S, const float* __restrict__ cen,
+    int K, float margin, uint16_t* __restrict__ support, int32_t* __restrict__ counts, const int32_t* __restrict__ offsets,
+    int32_t* __restrict__ cursor, int32_t* __restrict__ sel, float* __restrict__ xd_out, float* __restrict__ w_out)
+{
+    extern __shared__ int s_k[];      // COUNT: K ints; BUCKET: ROUTE_WARPS * K ints
+    constexpr int OFF = DIMS == 2 ? 1 : 0;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = p < P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!BUCKET) {
+        for (int k = threadIdx.x; k < K; k += blockDim.x) s_k[k] = 0;
+        __syncthreads();
+    }
+    float pos[3] = { 0.f, 0.f, 0.f }, dir[3] = { 0.f, 0.f, 0.f };
+    if (on) {
+        const int64_t r = p / S;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * r));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * r) + 1);
+        const float t = t_vals[p];
+        dir[0] = a.w; dir[1] = b.x; dir[2] = b.y;
+        pos[0] = __fadd_rn(a.x, __fmul_rn(dir[0], t));      // k_points
+        pos[1] = __fadd_rn(a.y, __fmul_rn(dir[1], t));
+        pos[2] = __fadd_rn(a.z, __fmul_rn(dir[2], t));
+    }
+    unsigned bits = 0;
+    if (on) bits = (BUCKET && support) ? (unsigned)support[p] : support_bits<DIMS, MAXK>(pos, cen, K, margin);
+    if (!BUCKET && support && on) support[p] = (uint16_t)bits;
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) {
+        if (k < K) {
+            const unsigned m = __ballot_sync(FULL, (bits >> k) & 1u);
+            if (lane == 0) {
+                if (BUCKET) s_k[warp * K + k] = __popc(m);
+                else if (m) atomicAdd_block(s_k + k, __popc(m));
+            }
+        }
+    }
+    __syncthreads();
+    if (!BUCKET) {
+        for (int k = threadIdx.x; k < K; k += blockDim.x)
+            if (s_k[k]) atomicAdd(counts + k, s_k[k]);
+        return;
+    }
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        int total = 0;
+        for (int wi = 0; wi < ROUTE_WARPS; ++wi) total += s_k[wi * K + k];
+        int run = total ? atomicAdd(cursor + k, total) : 0;
+        for (int wi = 0; wi < ROUTE_WARPS; ++wi) {
+            const int c = s_k[wi * K + k];
+            s_k[wi * K + k] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // blend weights of the experts in the set: w_k = (1/d_k) / max(sum over the set of 1/d, 1e-6), summed in expert order
+    float inv[MAXK];
+    float denom = 0.0f;
+    const bool soft = margin > 1.0f;
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) {
+        inv[k] = 0.0f;
+        if (soft && ((bits >> k) & 1u)) {
+            inv[k] = __fdiv_rn(1.0f, fmaxf(cdist_mm<DIMS>(pos + OFF, cen + 3 * k + OFF), 1e-6f));
+            denom = __fadd_rn(denom, inv[k]);
+        }
+    }
+    denom = fmaxf(denom, 1e-6f);
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) {
+        if (k < K) {
+            const bool in = (bits >> k) & 1u;
+            const unsigned m = __ballot_sync(FULL, in);
+            if (in) {
+                const int slot = __ldg(offsets + k) + s_k[warp * K + k] + __popc(m & ((1u << lane) - 1u));
+                sel[slot] = (int32_t)p;
+                w_out[slot] = soft ? __fdiv_rn(inv[k], denom) : 1.0f;
+                float2* dst = reinterpret_cast<float2*>(xd_out) + (size_t)slot * 3;
+                dst[0] = make_float2(pos[0], pos[1]);
+                dst[1] = make_float2(pos[2], dir[0]);
+                dst[2] = make_float2(dir[1], dir[2]);
+            }
         }
     }
 }
@@ -223,11 +399,16 @@ extern "C" int acn_route_points(acn_ctx* ctx, const float* pts, int64_t P, int s
                 "acn_route_points: margin %s needs the %s output", soft ? "> 1" : "== 1", soft ? "weights" : "hard");
     if (P == 0) return ACN_OK;
     ACN_REQUIRE(pts, ACN_EINVAL, "acn_route_points: null points");
-    const int grid = acn_grid_1d(P, 256);
+    ACN_REQUIRE(K <= 4096, ACN_EUNSUPPORTED, "acn_route_points: K=%d > 4096", K);
+    const int grid = acn_grid_1d(P, ROUTE_THREADS);
+    const size_t smem = counts_or_null ? (size_t)K * sizeof(int) : 0;
     cudaStream_t st = (cudaStream_t)stream;
     float* w = soft ? weights_or_null : nullptr;
-    if (dims == 2) k_route_points<2><<<grid, 256, 0, st>>>(pts, P, stride, centroids, K, margin, w, hard_or_null, counts_or_null);
-    else k_route_points<3><<<grid, 256, 0, st>>>(pts, P, stride, centroids, K, margin, w, hard_or_null, counts_or_null);
+#define RP(D, KT) k_route_points<D, KT><<<grid, ROUTE_THREADS, smem, st>>>(pts, P, stride, centroids, K, margin, w, hard_or_null, counts_or_null)
+    const bool vec = w && ((uintptr_t)w & 15) == 0;
+    if (dims == 2) { if (vec && K == 8) RP(2, 8); else if (vec && K == 4) RP(2, 4); else RP(2, 0); }
+    else           { if (vec && K == 8) RP(3, 8); else if (vec && K == 4) RP(3, 4); else RP(3, 0); }
+#undef RP
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }
@@ -259,10 +440,12 @@ extern "C" int acn_bucket_points(acn_ctx* ctx, const float* id6, int64_t P, cons
     ACN_REQUIRE(P >= 0 && K >= 1 && offsets && cursor && sel, ACN_EINVAL, "acn_bucket_points: bad arguments");
     ACN_REQUIRE((weights_or_null != nullptr) != (hard_or_null != nullptr), ACN_EINVAL,
                 "acn_bucket_points: give exactly one of weights / hard");
-    ACN_REQUIRE(!xd_out || id6, ACN_EINVAL, "acn_bucket_points: xd_out needs id6");
+    ACN_REQUIRE(!xd_out || (id6 && ((uintptr_t)id6 & 7) == 0 && ((uintptr_t)xd_out & 7) == 0), ACN_EINVAL,
+                "acn_bucket_points: xd_out needs id6, both 8-byte aligned");
+    ACN_REQUIRE(K <= 512, ACN_EUNSUPPORTED, "acn_bucket_points: K=%d > 512", K);
     if (P == 0) return ACN_OK;
-    k_bucket_points<<<acn_grid_1d(P, 256), 256, 0, (cudaStream_t)stream>>>(id6, P, weights_or_null, hard_or_null, K, offsets,
-                                                                           cursor, sel, xd_out, w_out);
+    k_bucket_points<<<acn_grid_1d(P, ROUTE_THREADS), ROUTE_THREADS, (size_t)ROUTE_WARPS * K * sizeof(int), (cudaStream_t)stream>>>(
+        id6, P, weights_or_null, hard_or_null, K, offsets, cursor, sel, xd_out, w_out);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }
@@ -277,8 +460,65 @@ extern "C" int acn_dispatch_points(acn_ctx* ctx, const float* id6, int64_t P, co
     ACN_REQUIRE(offsets && cursor && sel && w_out && row_base && row_off, ACN_EINVAL, "acn_dispatch_points: null buffer");
     if (P == 0) return ACN_OK;
     ACN_REQUIRE(id6 && ((uintptr_t)id6 & 7) == 0, ACN_EINVAL, "acn_dispatch_points: id6 null or not 8-byte aligned");
-    k_dispatch_points<<<acn_grid_1d(P, 256), 256, 0, (cudaStream_t)stream>>>(id6, P, weights_or_null, hard_or_null, K, offsets, cursor,
-                                                                             sel, w_out, (const unsigned long long*)row_base, row_off);
+    ACN_REQUIRE(K <= 512, ACN_EUNSUPPORTED, "acn_dispatch_points: K=%d > 512", K);
+    k_dispatch_points<<<acn_grid_1d(P, ROUTE_THREADS), ROUTE_THREADS, (size_t)ROUTE_WARPS * K * sizeof(int), (cudaStream_t)stream>>>(
+        id6, P, weights_or_null, hard_or_null, K, offsets, cursor, sel, w_out, (const unsigned long long*)row_base, row_off);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
+
+template <bool BUCKET>
+static int launch_route_samples(const float* rays8, const float* t_vals, int64_t N, int S, const float* cen, int K, int dims,
+                                float margin, uint16_t* support, int32_t* counts, const int32_t* offsets, int32_t* cursor,
+                                int32_t* sel, float* xd_out, float* w_out, cudaStream_t st) {
+    const int64_t P = N * S;
+    const int grid = acn_grid_1d(P, ROUTE_THREADS);
+    const size_t smem = (size_t)(BUCKET ? ROUTE_WARPS : 1) * K * sizeof(int);
+#define RS(D, MK) k_route_samples<D, MK, BUCKET><<<grid, ROUTE_THREADS, smem, st>>>(rays8, t_vals, P, S, cen, K, margin, support, \
+                                                                                  counts, offsets, cursor, sel, xd_out, w_out)
+    if (dims == 2) { if (K <= 4) RS(2, 4); else if (K <= 8) RS(2, 8); else RS(2, 16); }
+    else           { if (K <= 4) RS(3, 4); else if (K <= 8) RS(3, 8); else RS(3, 16); }
+#undef RS
+    return 0;
+}
+
+static int check_route_samples(const char* who, const float* rays8, const float* t_vals, int64_t N, int S, const float* cen,
+                               int K, int dims, float margin) {
+    ACN_REQUIRE(N >= 0 && S >= 1 && cen, ACN_EINVAL, "%s: bad arguments", who);
+    ACN_REQUIRE(K >= 1 && K <= 16, ACN_EUNSUPPORTED, "%s: K=%d outside [1,16] (use acn_route_points + acn_bucket_points)", who, K);
+    ACN_REQUIRE(dims == 2 || dims == 3, ACN_EINVAL, "%s: dims must be 2 (cluster_2d) or 3", who);
+    ACN_REQUIRE(margin >= 1.0f, ACN_EINVAL, "%s: boundary_margin must be >= 1", who);
+    ACN_REQUIRE(N == 0 || (rays8 && t_vals && ((uintptr_t)rays8 & 15) == 0), ACN_EINVAL, "%s: rays8 / t_vals null or rays8 not 16-byte aligned", who);
+    ACN_REQUIRE(N * (int64_t)S < ((int64_t)1 << 31), ACN_EUNSUPPORTED, "%s: more than 2^31 samples per call", who);
+    return ACN_OK;
+}
+
+extern "C" int acn_route_count_rays(acn_ctx* ctx, const float* rays8, const float* t_vals, int64_t N, int S,
+                                    const float* centroids, int K, int dims, float margin, uint16_t* support_or_null,
+                                    int32_t* counts, acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    int rc = check_route_samples("acn_route_count_rays", rays8, t_vals, N, S, centroids, K, dims, margin);
+    if (rc) return rc;
+    ACN_REQUIRE(counts, ACN_EINVAL, "acn_route_count_rays: null counts");
+    if (N == 0) return ACN_OK;
+    launch_route_samples<false>(rays8, t_vals, N, S, centroids, K, dims, margin, support_or_null, counts, nullptr, nullptr, nullptr,
+                                nullptr, nullptr, (cudaStream_t)stream);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
+
+extern "C" int acn_route_bucket_rays(acn_ctx* ctx, const float* rays8, const float* t_vals, int64_t N, int S,
+                                     const float* centroids, int K, int dims, float margin,
+                                     const uint16_t* support_or_null, const int32_t* offsets, int32_t* cursor, int32_t* sel,
+                                     float* xd_out, float* w_out, acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    int rc = check_route_samples("acn_route_bucket_rays", rays8, t_vals, N, S, centroids, K, dims, margin);
+    if (rc) return rc;
+    ACN_REQUIRE(offsets && cursor, ACN_EINVAL, "acn_route_bucket_rays: null offsets / cursor");
+    if (N == 0) return ACN_OK;
+    ACN_REQUIRE(sel && xd_out && w_out && ((uintptr_t)xd_out & 7) == 0, ACN_EINVAL, "acn_route_bucket_rays: null or misaligned output");
+    launch_route_samples<true>(rays8, t_vals, N, S, centroids, K, dims, margin, const_cast<uint16_t*>(support_or_null), nullptr,
+                               offsets, cursor, sel, xd_out, w_out, (cudaStream_t)stream);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }

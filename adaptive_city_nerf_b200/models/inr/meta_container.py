@@ -101,6 +101,27 @@ class MetaContainer(MetaModule):
             return self.submodules[active_module](x, params=sub_params[active_module])
         return self._routed(x, sub_params)
 
+    #: the fused route-from-rays kernels keep one weight per expert in registers
+    FUSED_ROUTE_MAX_EXPERTS = 16
+
+    def forward_rays(self, rays: torch.Tensor, t: torch.Tensor, params: Optional[OrderedDict] = None) -> torch.Tensor:
+        """rays (N,8), t (N,S) -> (N,S,4): `forward(points(rays, t))` without materialising the (N*S,6) points or the
+        (N*S,K) routing weights -- routing and bucketing run straight from the rays (render path of
+        nerfs/ray_rendering.py:317-323 + meta_container.py:275-343)."""
+        N, S = t.shape
+        K = len(self.submodules)
+        if K > self.FUSED_ROUTE_MAX_EXPERTS:
+            return self.forward(ops.points(rays, t), params=params).view(N, S, -1)
+        dims = 2 if self.cluster_2d else 3
+        with torch.no_grad():
+            counts, support = ops.route_count_rays(rays, t, self.centroids, dims, self.boundary_margin, want_support=True)
+            cnt = counts.cpu()                                                   # the one host read: K ints
+            offsets = torch.zeros(K, dtype=torch.int32)
+            offsets[1:] = torch.cumsum(cnt, 0)[:-1].to(torch.int32)
+            sel, xd, wsel = ops.route_bucket_rays(rays, t, self.centroids, dims, self.boundary_margin,
+                                                  offsets.to(rays.device), int(cnt.sum()), support=support)
+        return self._evaluate_buckets(N * S, cnt, offsets, sel, xd, wsel, self._sub_params(params), rays.device).view(N, S, -1)
+
     def _routed(self, x: torch.Tensor, sub_params: List) -> torch.Tensor:
         N, K = x.shape[0], len(self.submodules)
         id6 = ops.dev_f32(x[:, :6], "points")
@@ -112,7 +133,10 @@ class MetaContainer(MetaModule):
             offsets[1:] = torch.cumsum(cnt, 0)[:-1].to(torch.int32)
             total = int(cnt.sum())
             sel, xd, wsel = ops.bucket_points(id6, w, hard, K, offsets.to(x.device), total)
-        out = torch.zeros(N, self.dim_out, dtype=torch.float32, device=x.device)
+        return self._evaluate_buckets(N, cnt, offsets, sel, xd, wsel, sub_params, x.device)
+
+    def _evaluate_buckets(self, N: int, cnt, offsets, sel, xd, wsel, sub_params: List, device) -> torch.Tensor:
+        out = torch.zeros(N, self.dim_out, dtype=torch.float32, device=device)
         off = offsets.tolist()
         for k, sub in enumerate(self.submodules):
             m = int(cnt[k])

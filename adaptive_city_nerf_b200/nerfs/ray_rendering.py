@@ -8,7 +8,8 @@ pipeline of hand-written kernels:
     stratified bins (csrc/rays.cu)  ->  per-sample field
         active_module set : hash encode + fused MLP straight from (rays, t) -- the reference's
                             (N*S,6) point tensor is never materialised
-        container         : points -> route -> bucket -> experts -> blend (csrc/routing.cu)
+        container         : route + bucket straight from (rays, t) -> experts -> blend (csrc/routing.cu);
+                            neither the point matrix nor the (P,K) routing weights are materialised
     ->  alpha compositing (csrc/composite.cu, warp-per-ray prefix product)
 
 `chunk` keeps its meaning (an upper bound on points per field launch, i.e. on temporary
@@ -114,6 +115,8 @@ def render_rays_stratified(model, rays: Tensor, ray_samples: int, params=None, a
         if active_module is not None:
             sub = model.submodules[active_module]
             outs.append(sub.forward_rays(rays[r0:r1], t_vals[r0:r1], params=params))
+        elif hasattr(model, "forward_rays"):                   # MetaContainer: routing + bucketing straight from the rays
+            outs.append(model.forward_rays(rays[r0:r1], t_vals[r0:r1], params=params))
         else:
             id6 = ops.points(rays[r0:r1], t_vals[r0:r1])
             outs.append(model(id6, params=params).view(r1 - r0, S, 4))

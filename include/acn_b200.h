@@ -23,7 +23,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define ACN_VERSION 102 /* major*100 + minor */
+#define ACN_VERSION 103 /* major*100 + minor */
 
 typedef struct acn_ctx acn_ctx;
 typedef void* acn_stream; /* cudaStream_t */
@@ -184,6 +184,22 @@ int acn_blend_add(acn_ctx*, const float* y, const float* w, const int32_t* sel, 
 /* d_y[i] = d_out[sel[i]] * w[i] */
 int acn_blend_bwd(acn_ctx*, const float* d_out, const float* w, const int32_t* sel, int64_t M,
                   float* d_y, acn_stream);
+
+/* The container's render path without the point and weight matrices: routing (meta_container.py:97-134) of the samples
+ * o + d*t of packed rays (nerfs/ray_rendering.py:317-319) and their bucketing (:306-337), straight from (rays8, t_vals).
+ *   acn_route_count_rays : counts (K) int32 += rows per expert (the one host read that sizes the buckets)
+ *   acn_route_bucket_rays: sel (total) = sample index r*S+s, w_out (total) = blend weight (1 when margin == 1),
+ *                          xd_out (total,6) = [xyz, dir] rows, expert k's in [offsets[k], offsets[k]+counts[k]);
+ *                          cursor (K) int32 must be zero on entry.
+ * support (N*S) uint16: bit k set = expert k is in the sample's support set; written by the count pass and, when handed to
+ * the bucket pass, saves it the routing (distances are then evaluated only for the experts in the set).
+ * Same arithmetic as acn_points + acn_route_points + acn_bucket_points (rows and weights are bit-identical); K <= 16. */
+int acn_route_count_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
+                         const float* centroids, int K, int dims, float margin, uint16_t* support_or_null,
+                         int32_t* counts, acn_stream);
+int acn_route_bucket_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
+                          const float* centroids, int K, int dims, float margin, const uint16_t* support_or_null,
+                          const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out, acn_stream);
 
 /* ---- around the render: loss epilogue and optimizer tail --------------- */
 enum { ACN_COLOR_LINEAR = 0, ACN_COLOR_SRGB = 1, ACN_COLOR_IDENTITY = 2 };

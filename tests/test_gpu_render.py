@@ -272,3 +272,28 @@ def test_allow_tf32_selects_the_tensor_core_path(golden):
         if p.grad is not None:
             a, b = p.grad.double(), g32[n].double()
             assert float((a - b).norm() / (b.norm() + 1e-30)) < 3e-2, n
+
+@pytest.mark.parametrize("margin", [1.0, 1.05])
+def test_container_forward_rays_equals_forward_of_points(margin):
+    """The container's render path routes and buckets straight from the rays; it must give exactly what
+    `model(points(rays, t))` gives (forward bit for bit; gradients up to the order of the table atomics)."""
+    from adaptive_city_nerf_b200 import ops
+    m = make_container(4, synth.CENTROIDS_G22, synth.EXPERT_BOXES_G22, margin, False, seed0=530).eval()
+    N, S = 777, 20
+    o, d = synth.random_rays_in_box(81, N)
+    rays = torch.cat([cu(o), cu(d), torch.zeros(N, 1, device="cuda"), torch.full((N, 1), 0.5, device="cuda")], dim=1)
+    t = ops.sample_stratified(rays, S, None)
+    grads = []
+    outs = []
+    for fused in (True, False):
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            y = m.forward_rays(rays, t) if fused else m(ops.points(rays, t)).view(N, S, 4)
+        (y[..., :3].sum() + 0.1 * y[..., 3].clamp(max=50).sum()).backward()
+        outs.append(y.detach())
+        grads.append({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    assert torch.equal(outs[0], outs[1])
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 0
+    for n in grads[0]:
+        a, b = grads[0][n].double(), grads[1][n].double()
+        assert float((a - b).norm() / (b.norm() + 1e-30)) < 1e-4, n

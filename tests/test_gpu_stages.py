@@ -369,6 +369,50 @@ def test_bucket_and_blend(ops, orc):
         np.testing.assert_allclose(npy(out), ref, atol=1e-6)
 
 
+@pytest.mark.parametrize("K,margin,dims", [(4, 1.05, 2), (4, 1.0, 2), (8, 1.1, 2), (3, 1.05, 3), (13, 1.05, 2)])
+def test_route_and_bucket_straight_from_rays(ops, orc, golden, K, margin, dims):
+    """acn_route_count_rays / acn_route_bucket_rays == acn_points + acn_route_points + acn_bucket_points, bit for bit
+    (rows, weights, per-expert sets), and the counts equal the oracle's routing of the oracle's points."""
+    rng = np.random.default_rng(40 + K)
+    N, S = 1531, 24                                                      # N*S not a multiple of the block size
+    o, d = synth.random_rays_in_box(50 + K, N)
+    rays_np = np.concatenate([o, d, np.zeros((N, 1), F32), rng.uniform(0.2, 0.6, (N, 1)).astype(F32)], 1).astype(F32)
+    rays = cu(rays_np)
+    t = ops.sample_stratified(rays, S, cu(rng.uniform(0, 1, (N, S)).astype(F32)))
+    cen_np = synth.CENTROIDS_G22[:K] if K <= 4 else np.concatenate(
+        [np.zeros((K, 1)), rng.uniform(-1, 1, (K, 2))], 1).astype(F32)
+    cen = cu(cen_np)
+    id6 = ops.points(rays, t)
+    w, h, counts = ops.route_points(id6, cen, dims, margin, want_counts=True)
+    cnt_f = ops.route_count_rays(rays, t, cen, dims, margin)
+    assert (npy(cnt_f) == npy(counts)).all()
+    ow, oh = orc.route_points(npy(id6)[:, :3], cen_np, margin, cluster_2d=dims == 2)
+    o_cnt = (ow > 0).sum(0) if margin > 1 else np.bincount(oh, minlength=K)
+    assert (npy(cnt_f).astype(np.int64) == o_cnt).all()                  # bit-exact support sets vs the CPU oracle
+    cnt = npy(counts).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int32)
+    sel_a, xd_a, w_a = ops.bucket_points(id6, w, h, K, cu(off), int(cnt.sum()))
+    cnt_s, support = ops.route_count_rays(rays, t, cen, dims, margin, want_support=True)
+    assert (npy(cnt_s) == npy(counts)).all()
+    wn = npy(w) > 0 if w is not None else np.eye(K, dtype=bool)[npy(h).astype(np.int64)]
+    assert (support.cpu().numpy().astype(np.int64) == (wn * (1 << np.arange(K))).sum(1)).all()     # one bit per expert in the set
+    for sup in (None, support):                                          # bucket pass: routing recomputed / read back
+        sel_b, xd_b, w_b = ops.route_bucket_rays(rays, t, cen, dims, margin, cu(off), int(cnt.sum()), support=sup)
+        _compare_buckets(K, off, cnt, (sel_a, xd_a, w_a), (sel_b, xd_b, w_b))
+    empty = ops.route_count_rays(rays[:0], t[:0], cen, dims, margin)
+    assert int(empty.sum()) == 0
+
+
+def _compare_buckets(K, off, cnt, a, b):
+    (sel_a, xd_a, w_a), (sel_b, xd_b, w_b) = a, b
+    for k in range(K):
+        sl = slice(int(off[k]), int(off[k] + cnt[k]))
+        oa, ob = np.argsort(npy(sel_a[sl]).astype(np.int64)), np.argsort(npy(sel_b[sl]).astype(np.int64))
+        assert (npy(sel_a[sl])[oa] == npy(sel_b[sl])[ob]).all()
+        assert_bitexact(npy(xd_a[sl])[oa], npy(xd_b[sl])[ob], f"rows of expert {k}")
+        assert_bitexact(npy(w_a[sl])[oa], npy(w_b[sl])[ob], f"weights of expert {k}")
+
+
 def test_hashgrid_bwd_march_vs_generic(ops):
     """The ray-marching scatter (run-length aggregation, rotated start) must equal the generic
     per-(point,level) scatter: same sums, different order -> fp32 tolerance."""

@@ -14,6 +14,8 @@ sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests" / "golden")
 import synth
 from adaptive_city_nerf_b200.models.inr import MetaContainer
 from adaptive_city_nerf_b200.nerfs.ray_rendering import render_rays
+from adaptive_city_nerf_b200.nerfs.losses import mse_in_color_space
+from adaptive_city_nerf_b200.optim import FusedAdam
 from adaptive_city_nerf_b200.nerfs.ray_sampling import clamp_rays_near_far, get_ray_directions, get_rays
 from adaptive_city_nerf_b200.nerfs.scene_box import SceneBox
 
@@ -80,17 +82,17 @@ N = 1 << (16 if quick else 18)
 rays = torch.cat([view_rays(box, 64, 64, 60.0, seed=s)[0] for s in range(N // 4096)])
 gt = torch.rand(N, 3, device=dev)
 groups = m.get_param_groups()
-opt = torch.optim.Adam([{"params": groups["encoding"]["params"], "lr": 1e-2}, {"params": groups["sigma"]["params"], "lr": 2e-3},
-                        {"params": groups["color"]["params"], "lr": 2e-3}], eps=1e-15, fused=True)
+opt = FusedAdam([{"params": groups["encoding"]["params"], "lr": 1e-2}, {"params": groups["sigma"]["params"], "lr": 2e-3},
+                 {"params": groups["color"]["params"], "lr": 2e-3}], eps=1e-15)
 
 
 def step3():
     with torch.autocast("cuda", dtype=torch.float16):
         rgb, *_ = render_rays(m, rays, ray_samples=64, active_module=None, chunk=1 << 24)
-    loss = torch.nn.functional.mse_loss(rgb, gt)
+    loss = mse_in_color_space(rgb, gt, "linear")
     opt.zero_grad(set_to_none=True)
     loss.backward()
-    opt.step()
+    opt.step(max_norm=1.0)
 
 
 ms = timed(step3, 3, warm=2)
@@ -105,25 +107,32 @@ m.train()
 rays = view_rays(box, 64, 64, 60.0, seed=3)[0][:4000].contiguous()
 gt = torch.rand(rays.shape[0], 3, device=dev)
 groups = m.get_param_groups()
-opt = torch.optim.Adam([{"params": groups["encoding"]["params"], "lr": 1e-2}, {"params": groups["sigma"]["params"], "lr": 2e-3},
-                        {"params": groups["color"]["params"], "lr": 2e-3}, {"params": groups["background"]["params"], "lr": 1e-3}],
-                       eps=1e-15, fused=True)
-scaler = torch.amp.GradScaler("cuda")
-all_params = [p for g in opt.param_groups for p in g["params"]]
+pg = [{"params": groups["encoding"]["params"], "lr": 1e-2}, {"params": groups["sigma"]["params"], "lr": 2e-3},
+      {"params": groups["color"]["params"], "lr": 2e-3}, {"params": groups["background"]["params"], "lr": 1e-3}]
+all_params = [p for g in pg for p in g["params"]]
+res5 = {}
+for tail in ("torch", "fused"):
+    opt = torch.optim.Adam(pg, eps=1e-15, fused=True) if tail == "torch" else FusedAdam(pg, eps=1e-15)
+    scaler = torch.amp.GradScaler("cuda")
 
+    def step5():
+        with torch.autocast("cuda", dtype=torch.float16):
+            rgb, *_ = render_rays(m, rays, ray_samples=96, active_module=None, chunk=1 << 24)
+            loss = torch.nn.functional.mse_loss(rgb.float(), gt) if tail == "torch" else mse_in_color_space(rgb, gt, "linear")
+        opt.zero_grad(set_to_none=True)
+        scaler.scale(loss).backward()
+        if tail == "torch":                                  # runtime_adapt.py:262-268 as written
+            scaler.unscale_(opt)
+            torch.nn.utils.clip_grad_norm_(all_params, 1.0)
+            scaler.step(opt)
+            scaler.update()
+        else:
+            opt.step_scaled(scaler, max_norm=1.0)
 
-def step5():
-    with torch.autocast("cuda", dtype=torch.float16):
-        rgb, *_ = render_rays(m, rays, ray_samples=96, active_module=None, chunk=1 << 24)
-        loss = torch.nn.functional.mse_loss(rgb.float(), gt)
-    opt.zero_grad(set_to_none=True)
-    scaler.scale(loss).backward()
-    scaler.unscale_(opt)
-    torch.nn.utils.clip_grad_norm_(all_params, 1.0)
-    scaler.step(opt)
-    scaler.update()
-
-
-ms = timed(step5, 8, warm=3)
+    res5[tail] = timed(step5, 8, warm=3)
+    del opt
+    torch.cuda.empty_cache()
+ms = res5["fused"]
 print(json.dumps({"config": "cfg5: 8 experts, 4000 support rays x 96 samples, Adam + GradScaler + clip 1.0, whole container",
-                  "ms_per_step": round(ms, 2), "rays_per_s": rays.shape[0] / (ms * 1e-3)}))
+                  "ms_per_step": round(ms, 2), "rays_per_s": rays.shape[0] / (ms * 1e-3),
+                  "ms_per_step_with_pytorch_loss_and_optimizer": round(res5["torch"], 2)}))
