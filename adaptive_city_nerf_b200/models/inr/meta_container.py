@@ -113,13 +113,18 @@ class MetaContainer(MetaModule):
         if K > self.FUSED_ROUTE_MAX_EXPERTS:
             return self.forward(ops.points(rays, t), params=params).view(N, S, -1)
         dims = 2 if self.cluster_2d else 3
+        # Inference renders frames (consecutive rays = adjacent pixels): order the buckets so that a warp of the experts'
+        # gathers sees one sample of 32 neighbouring pixels.  Training batches are unrelated rays: keep a ray's samples together.
+        ray_major = not torch.is_grad_enabled()
         with torch.no_grad():
-            counts, support = ops.route_count_rays(rays, t, self.centroids, dims, self.boundary_margin, want_support=True)
+            counts, support = ops.route_count_rays(rays, t, self.centroids, dims, self.boundary_margin, want_support=True,
+                                                   ray_major=ray_major)
             cnt = counts.cpu()                                                   # the one host read: K ints
             offsets = torch.zeros(K, dtype=torch.int32)
             offsets[1:] = torch.cumsum(cnt, 0)[:-1].to(torch.int32)
             sel, xd, wsel = ops.route_bucket_rays(rays, t, self.centroids, dims, self.boundary_margin,
-                                                  offsets.to(rays.device), int(cnt.sum()), support=support)
+                                                  offsets.to(rays.device), int(cnt.sum()), support=support,
+                                                  ray_major=ray_major)
         return self._evaluate_buckets(N * S, cnt, offsets, sel, xd, wsel, self._sub_params(params), rays.device).view(N, S, -1)
 
     def _routed(self, x: torch.Tensor, sub_params: List) -> torch.Tensor:

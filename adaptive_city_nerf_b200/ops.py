@@ -446,7 +446,8 @@ def bucket_points(id6: Tensor, weights: Optional[Tensor], hard: Optional[Tensor]
     return sel, xd, w
 
 
-def route_count_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, margin: float, want_support: bool = False):
+def route_count_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, margin: float, want_support: bool = False,
+                     ray_major: bool = False):
     """Rows per expert for the samples o + d*t of `rays` -> (K,) int32 (device) [, support sets (N*S,) uint16]."""
     rays, t = dev_f32(rays, "rays"), dev_f32(t, "t_vals")
     cen = dev_f32(centroids.to(rays.device), "centroids")
@@ -454,12 +455,12 @@ def route_count_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, marg
     counts = torch.zeros(cen.shape[0], dtype=torch.int32, device=rays.device)
     support = torch.empty(N * S, dtype=torch.uint16, device=rays.device) if want_support else None
     check(lib().acn_route_count_rays(ctx(rays.device), ptr(rays), ptr(t), N, S, ptr(cen), cen.shape[0], dims, float(margin),
-                                     ptr(support), ptr(counts), stream(rays.device)))
+                                     int(ray_major), ptr(support), ptr(counts), stream(rays.device)))
     return (counts, support) if want_support else counts
 
 
 def route_bucket_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, margin: float, offsets: Tensor, total: int,
-                      support: Optional[Tensor] = None):
+                      support: Optional[Tensor] = None, ray_major: bool = False):
     """-> sel (total,) int32 sample index, xd (total,6) [xyz, dir] rows, w (total,) blend weights; expert k's rows lie in
     [offsets[k], offsets[k] + counts[k])."""
     rays, t = dev_f32(rays, "rays"), dev_f32(t, "t_vals")
@@ -470,8 +471,8 @@ def route_bucket_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, mar
     xd = torch.empty(total, 6, dtype=torch.float32, device=dev)
     w = torch.empty(total, dtype=torch.float32, device=dev)
     cursor = torch.zeros(K, dtype=torch.int32, device=dev)
-    check(lib().acn_route_bucket_rays(ctx(dev), ptr(rays), ptr(t), N, S, ptr(cen), K, dims, float(margin), ptr(support),
-                                      ptr(offsets), ptr(cursor), ptr(sel), ptr(xd), ptr(w), stream(dev)))
+    check(lib().acn_route_bucket_rays(ctx(dev), ptr(rays), ptr(t), N, S, ptr(cen), K, dims, float(margin), int(ray_major),
+                                      ptr(support), ptr(offsets), ptr(cursor), ptr(sel), ptr(xd), ptr(w), stream(dev)))
     return sel, xd, w
 
 

@@ -193,13 +193,16 @@ int acn_blend_bwd(acn_ctx*, const float* d_out, const float* w, const int32_t* s
  *                          cursor (K) int32 must be zero on entry.
  * support (N*S) uint16: bit k set = expert k is in the sample's support set; written by the count pass and, when handed to
  * the bucket pass, saves it the routing (distances are then evaluated only for the experts in the set).
+ * ray_major != 0 orders the rows of a bucket as (sample, 32 adjacent rays) instead of (ray, 32 consecutive samples): for
+ * frames, where consecutive rays are adjacent pixels, a warp of the experts' gather kernels then works on neighbouring
+ * cells.  The set of rows per expert does not depend on it.
  * Same arithmetic as acn_points + acn_route_points + acn_bucket_points (rows and weights are bit-identical); K <= 16. */
 int acn_route_count_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
-                         const float* centroids, int K, int dims, float margin, uint16_t* support_or_null,
-                         int32_t* counts, acn_stream);
+                         const float* centroids, int K, int dims, float margin, int ray_major,
+                         uint16_t* support_or_null, int32_t* counts, acn_stream);
 int acn_route_bucket_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
-                          const float* centroids, int K, int dims, float margin, const uint16_t* support_or_null,
-                          const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out, acn_stream);
+                          const float* centroids, int K, int dims, float margin, int ray_major,
+                          const uint16_t* support_or_null, const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out, acn_stream);
 
 /* ---- around the render: loss epilogue and optimizer tail --------------- */
 enum { ACN_COLOR_LINEAR = 0, ACN_COLOR_SRGB = 1, ACN_COLOR_IDENTITY = 2 };

@@ -293,6 +293,8 @@ def test_container_forward_rays_equals_forward_of_points(margin):
         outs.append(y.detach())
         grads.append({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
     assert torch.equal(outs[0], outs[1])
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):       # inference orders the buckets ray-major
+        assert torch.equal(m.forward_rays(rays, t), outs[0])
     assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 0
     for n in grads[0]:
         a, b = grads[0][n].double(), grads[1][n].double()

@@ -397,8 +397,12 @@ def test_route_and_bucket_straight_from_rays(ops, orc, golden, K, margin, dims):
     wn = npy(w) > 0 if w is not None else np.eye(K, dtype=bool)[npy(h).astype(np.int64)]
     assert (support.cpu().numpy().astype(np.int64) == (wn * (1 << np.arange(K))).sum(1)).all()     # one bit per expert in the set
     for sup in (None, support):                                          # bucket pass: routing recomputed / read back
-        sel_b, xd_b, w_b = ops.route_bucket_rays(rays, t, cen, dims, margin, cu(off), int(cnt.sum()), support=sup)
-        _compare_buckets(K, off, cnt, (sel_a, xd_a, w_a), (sel_b, xd_b, w_b))
+        for ray_major in (False, True):                                  # row order inside a bucket; the sets are the same
+            sel_b, xd_b, w_b = ops.route_bucket_rays(rays, t, cen, dims, margin, cu(off), int(cnt.sum()), support=sup,
+                                                     ray_major=ray_major)
+            _compare_buckets(K, off, cnt, (sel_a, xd_a, w_a), (sel_b, xd_b, w_b))
+    cnt_r, support_r = ops.route_count_rays(rays, t, cen, dims, margin, want_support=True, ray_major=True)
+    assert (npy(cnt_r) == npy(counts)).all() and torch.equal(support_r, support)
     empty = ops.route_count_rays(rays[:0], t[:0], cen, dims, margin)
     assert int(empty.sum()) == 0
 
