@@ -104,7 +104,8 @@ class MetaContainer(MetaModule):
     #: the fused route-from-rays kernels keep one weight per expert in registers
     FUSED_ROUTE_MAX_EXPERTS = 16
 
-    def forward_rays(self, rays: torch.Tensor, t: torch.Tensor, params: Optional[OrderedDict] = None) -> torch.Tensor:
+    def forward_rays(self, rays: torch.Tensor, t: torch.Tensor, params: Optional[OrderedDict] = None,
+                     ray_major: bool = False) -> torch.Tensor:
         """rays (N,8), t (N,S) -> (N,S,4): `forward(points(rays, t))` without materialising the (N*S,6) points or the
         (N*S,K) routing weights -- routing and bucketing run straight from the rays (render path of
         nerfs/ray_rendering.py:317-323 + meta_container.py:275-343)."""
@@ -113,9 +114,9 @@ class MetaContainer(MetaModule):
         if K > self.FUSED_ROUTE_MAX_EXPERTS:
             return self.forward(ops.points(rays, t), params=params).view(N, S, -1)
         dims = 2 if self.cluster_2d else 3
-        # Inference renders frames (consecutive rays = adjacent pixels): order the buckets so that a warp of the experts'
-        # gathers sees one sample of 32 neighbouring pixels.  Training batches are unrelated rays: keep a ray's samples together.
-        ray_major = not torch.is_grad_enabled()
+        # ray_major (frames: consecutive rays = adjacent pixels) orders the buckets so that a warp of the experts' gathers
+        # sees one sample of 32 neighbouring pixels; otherwise a ray's samples stay together (shuffled training rays).
+        ray_major = bool(ray_major)
         with torch.no_grad():
             counts, support = ops.route_count_rays(rays, t, self.centroids, dims, self.boundary_margin, want_support=True,
                                                    ray_major=ray_major)

@@ -99,10 +99,14 @@ def stratified_t_vals(near: Tensor, far: Tensor, ray_samples: int, randomized: b
 # ------------------------------------------------------------------ the renderer
 def render_rays_stratified(model, rays: Tensor, ray_samples: int, params=None, active_module: Optional[int] = None,
                            bg_color_default: str = "white", chunk: int = 1_000_000, sigma_scale=1.0,
-                           jitter: Optional[Tensor] = None, **kwargs):
-    """Stratified renderer (reference :290-345)."""
+                           jitter: Optional[Tensor] = None, coherent_rays: Optional[bool] = None, **kwargs):
+    """Stratified renderer (reference :290-345).  `coherent_rays`: consecutive rays are adjacent pixels of a frame (the
+    gather kernels then work on one sample of 32 neighbouring rays per warp); None = find out from the rays themselves
+    when rendering without autograd (one small host read), never for training batches."""
     rays = ops.dev_f32(rays, "rays")
     N, S = rays.shape[0], int(ray_samples)
+    if coherent_rays is None:
+        coherent_rays = (not torch.is_grad_enabled()) and ops.rays_are_coherent(rays, S)
     with torch.no_grad():
         if model.training and jitter is None:
             jitter = torch.rand(N, S, device=rays.device, dtype=torch.float32)   # rand_like(low), reference :286
@@ -114,9 +118,9 @@ def render_rays_stratified(model, rays: Tensor, ray_samples: int, params=None, a
         r1 = min(N, r0 + rays_per_chunk)
         if active_module is not None:
             sub = model.submodules[active_module]
-            outs.append(sub.forward_rays(rays[r0:r1], t_vals[r0:r1], params=params))
+            outs.append(sub.forward_rays(rays[r0:r1], t_vals[r0:r1], params=params, ray_major=coherent_rays))
         elif hasattr(model, "forward_rays"):                   # MetaContainer: routing + bucketing straight from the rays
-            outs.append(model.forward_rays(rays[r0:r1], t_vals[r0:r1], params=params))
+            outs.append(model.forward_rays(rays[r0:r1], t_vals[r0:r1], params=params, ray_major=coherent_rays))
         else:
             id6 = ops.points(rays[r0:r1], t_vals[r0:r1])
             outs.append(model(id6, params=params).view(r1 - r0, S, 4))

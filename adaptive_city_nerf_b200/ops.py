@@ -102,6 +102,23 @@ def points(rays: Tensor, t: Tensor) -> Tensor:
     return id6
 
 
+def rays_are_coherent(rays: Tensor, S: int, threshold: float = 0.25) -> bool:
+    """True when consecutive rays are neighbouring pixels of a frame: the gap between ray r and r+1 at mid depth is well
+    below the spacing of the samples along a ray.  Then the gather kernels should give a warp one sample of 32 adjacent
+    rays (`ray_major`) rather than 32 samples of one ray.  Looks at the first 65 rays; one small host read (inference
+    only -- training batches are shuffled rays and never ask)."""
+    n = min(int(rays.shape[0]), 65)
+    if n < 33:
+        return False
+    a = rays[:n].float()
+    tm = 0.5 * (a[:-1, 6] + a[:-1, 7])
+    gap = ((a[1:, :3] - a[:-1, :3]) + (a[1:, 3:6] - a[:-1, 3:6]) * tm[:, None]).norm(dim=1)
+    step = (a[:-1, 7] - a[:-1, 6]).abs() / max(int(S), 1)
+    ok = torch.isfinite(gap) & torch.isfinite(step) & (step > 0)
+    ratio = torch.where(ok, gap / step.clamp_min(1e-30), torch.full_like(gap, float("inf"))).median()
+    return bool(ratio < threshold)
+
+
 # ------------------------------------------------------------------------------------------ stage 2
 class GridSpec:
     """Static description of one hash grid (device-resident resolution table)."""
@@ -149,12 +166,13 @@ def hashgrid_bwd(x: Tensor, dout: Tensor, spec: GridSpec, box6: Optional[Tensor]
                                  ptr(_grid_res(spec, dev)), spec.interp, ptr(dout), _dt(dout), ptr(dtable), stream(dev)))
 
 
-def hashgrid_fwd_rays(rays: Tensor, t: Tensor, table: Tensor, spec: GridSpec, box6: Optional[Tensor], out_dtype) -> Tensor:
+def hashgrid_fwd_rays(rays: Tensor, t: Tensor, table: Tensor, spec: GridSpec, box6: Optional[Tensor], out_dtype,
+                      ray_major: bool = False) -> Tensor:
     N, S = t.shape
     dev = rays.device
     out = torch.empty(N * S, spec.L * spec.F, dtype=out_dtype, device=dev)
     check(lib().acn_hashgrid_fwd_rays(ctx(dev), ptr(rays), ptr(t), N, S, ptr(box6), ptr(table), spec.L, spec.F, spec.log2T,
-                                      ptr(_grid_res(spec, dev)), spec.interp, ptr(out), _dt(out), stream(dev)))
+                                      ptr(_grid_res(spec, dev)), spec.interp, ptr(out), _dt(out), int(ray_major), stream(dev)))
     return out
 
 
@@ -254,14 +272,14 @@ class ExpertFieldFn(torch.autograd.Function):
     fast weights).  The backward recomputes the MLP activations from the saved encoding."""
 
     @staticmethod
-    def forward(ctx_, x6, rays, t, table, spec, box6, half, table_node, *ws):
+    def forward(ctx_, x6, rays, t, table, spec, box6, half, ray_major, table_node, *ws):
         ws = [dev_f32(w, "MLP weight") for w in ws]
         table_c = dev_f32(table, "hash_table")
         enc_dtype = torch.float16 if half else torch.float32
         if rays is not None:
             rays = dev_f32(rays, "rays")
             t = dev_f32(t, "t_vals")
-            enc = hashgrid_fwd_rays(rays, t, table_c, spec, box6, enc_dtype)
+            enc = hashgrid_fwd_rays(rays, t, table_c, spec, box6, enc_dtype, ray_major)
             dirs, dstride, dgroup = rays[:, 3:], 8, t.shape[1]
             pos = (rays, t)
         else:
@@ -288,7 +306,7 @@ class ExpertFieldFn(torch.autograd.Function):
         # asks torch.autograd.grad for the 14 fast weights only (meta_core.py:54-59) and must not pay for d_enc and the
         # table scatter -- the reference's un-fused graph gets that pruning from the engine for free.
         need_table = ctx_.needs_input_grad[3] and engine_wants(ctx_.table_node)
-        need_w = ctx_.needs_input_grad[8:]
+        need_w = ctx_.needs_input_grad[9:]
         dirs = pos[0][:, 3:]
         g = g.contiguous().float()
         grads, d_enc = field_bwd(enc, dirs, dstride, dgroup, ws, half, g, need_table, need_w)
@@ -299,7 +317,7 @@ class ExpertFieldFn(torch.autograd.Function):
                 hashgrid_bwd_rays(pos[0], pos[1], d_enc, spec, box6, dtable)
             else:
                 hashgrid_bwd(pos[0], d_enc, spec, box6, dtable)
-        return (None, None, None, dtable, None, None, None, None, *grads)
+        return (None, None, None, dtable, None, None, None, None, None, *grads)
 
 
 def grad_node_of(t: Optional[Tensor]):

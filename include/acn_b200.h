@@ -23,7 +23,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define ACN_VERSION 103 /* major*100 + minor */
+#define ACN_VERSION 104 /* major*100 + minor */
 
 typedef struct acn_ctx acn_ctx;
 typedef void* acn_stream; /* cudaStream_t */
@@ -98,10 +98,12 @@ int acn_hashgrid_bwd(acn_ctx*, const float* x, int64_t P, int x_stride, const fl
 
 /* Same, with the points formed on the fly from rays (N,8) and t_vals (N,S): p = o + d*t
  * (nerfs/ray_rendering.py:317); the reference's (N*S,6) id6 tensor is never materialised.
- * out / dout are (N*S, L*F). */
+ * out / dout are (N*S, L*F).  ray_major != 0 (forward): a warp encodes one sample of 32 consecutive rays instead of 32
+ * consecutive samples of one ray -- same output, fewer distinct cache lines per gather when consecutive rays are
+ * adjacent pixels of a frame. */
 int acn_hashgrid_fwd_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
                           const float* box6_or_null, const float* table, int L, int F, int log2T,
-                          const int32_t* res, int interp, void* out, int out_dtype, acn_stream);
+                          const int32_t* res, int interp, void* out, int out_dtype, int ray_major, acn_stream);
 int acn_hashgrid_bwd_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
                           const float* box6_or_null, int L, int F, int log2T, const int32_t* res,
                           int interp, const void* dout, int dout_dtype, float* dtable, acn_stream);

@@ -293,9 +293,36 @@ def test_container_forward_rays_equals_forward_of_points(margin):
         outs.append(y.detach())
         grads.append({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
     assert torch.equal(outs[0], outs[1])
-    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):       # inference orders the buckets ray-major
-        assert torch.equal(m.forward_rays(rays, t), outs[0])
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):       # frames order the buckets ray-major
+        assert torch.equal(m.forward_rays(rays, t, ray_major=True), outs[0])
     assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 0
     for n in grads[0]:
         a, b = grads[0][n].double(), grads[1][n].double()
         assert float((a - b).norm() / (b.norm() + 1e-30)) < 1e-4, n
+
+def test_coherent_frames_are_detected_and_render_identically():
+    """Consecutive rays of a frame are adjacent pixels: render_rays finds that out (inference only) and switches the
+    gather kernels to one-sample-of-32-rays warps; shuffled rays do not trigger it; the image is the same bit for bit."""
+    from adaptive_city_nerf_b200 import _lib, ops
+    from adaptive_city_nerf_b200.nerfs.ray_rendering import render_rays
+    from adaptive_city_nerf_b200.nerfs.ray_sampling import clamp_rays_near_far, get_ray_directions, get_rays
+    from adaptive_city_nerf_b200.nerfs.scene_box import SceneBox
+    box = SceneBox(cu(synth.AABB_GLOBAL))
+    cam = synth.nadir_rays(9, 1, H=40, W=72, f=900.0)[0]
+    dirs = get_ray_directions(40, 72, cam["fx"], cam["fy"], cam["cx"], cam["cy"], True, torch.device("cuda"))
+    rays, _ = clamp_rays_near_far(get_rays(dirs, cu(cam["c2w"]), scene_box=box).view(-1, 8), (None, None))
+    shuffled = rays[torch.randperm(rays.shape[0], device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))]
+    assert ops.rays_are_coherent(rays, 32) and not ops.rays_are_coherent(shuffled, 32)
+    assert not ops.rays_are_coherent(rays[:20], 32)
+    for K in (1, 4):
+        if K == 1:
+            m = make_container(1, np.zeros((1, 3), F32), [synth.AABB_GLOBAL], 1.0, False, seed0=540).eval()
+        else:
+            m = make_container(4, synth.CENTROIDS_G22, synth.EXPERT_BOXES_G22, 1.05, True, seed0=541).eval()
+        kw = dict(ray_samples=32, active_module=0 if K == 1 else None)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            auto = render_rays(m, rays, **kw)
+            plain = render_rays(m, rays, coherent_rays=False, **kw)
+            forced = render_rays(m, rays, coherent_rays=True, **kw)
+        for a, b, c in zip(auto, plain, forced):
+            assert torch.equal(a, b) and torch.equal(a, c)

@@ -417,6 +417,25 @@ def _compare_buckets(K, off, cnt, a, b):
         assert_bitexact(npy(w_a[sl])[oa], npy(w_b[sl])[ob], f"weights of expert {k}")
 
 
+def test_hashgrid_fwd_rays_ray_major_is_the_same_encoding(ops):
+    """ray_major only changes which thread encodes which sample (frames: a warp = one sample of 32 adjacent pixels)."""
+    from adaptive_city_nerf_b200.nerfs.ray_sampling import get_rays, get_ray_directions
+    from adaptive_city_nerf_b200.nerfs.scene_box import SceneBox
+    box = SceneBox(cu(synth.AABB_GLOBAL))
+    cam = synth.nadir_rays(5, 1, H=37, W=53, f=400.0)[0]                   # N = 1961 rays: not a multiple of 32
+    dirs = get_ray_directions(37, 53, cam["fx"], cam["fy"], cam["cx"], cam["cy"], True, torch.device("cuda"))
+    rays = get_rays(dirs, cu(cam["c2w"]), scene_box=box).view(-1, 8).contiguous()
+    spec = ops.GridSpec(16, 2, 14, _encoder(14).level_resolutions.clone(), 1)
+    table = (torch.rand(16 << 14, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4)) - 0.5)
+    box6 = torch.cat([box.min, box.extent]).contiguous()
+    for S in (13, 64):                                                     # S not a multiple of 8 / a multiple
+        t = ops.sample_stratified(rays, S, None)
+        for dt in (torch.float16, torch.float32):
+            a = ops.hashgrid_fwd_rays(rays, t, table, spec, box6, dt, ray_major=False)
+            b = ops.hashgrid_fwd_rays(rays, t, table, spec, box6, dt, ray_major=True)
+            assert torch.equal(a, b)
+
+
 def test_hashgrid_bwd_march_vs_generic(ops):
     """The ray-marching scatter (run-length aggregation, rotated start) must equal the generic
     per-(point,level) scatter: same sums, different order -> fp32 tolerance."""
