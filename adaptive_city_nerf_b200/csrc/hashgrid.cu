@@ -11,7 +11,7 @@
 // Where a point's position comes from: an explicit (P,>=3) array, or rays (N,8) + t (N,S), in
 // which case p = o + d*t is formed here (un-fused, nerfs/ray_rendering.py:317) and the
 // reference's (N*S,6) id6 tensor is never materialised.
-struct PosSrc { const float* x; int xs; const float* rays; const float* t; int S; int ray_major; };
+struct PosSrc { const float* x; int xs; const float* rays; const float* t; int S; int ray_major; const int32_t* ray_major_dev; };
 
 __device__ __forceinline__ void load_pos(const PosSrc& s, int64_t p, float& px, float& py, float& pz) {
     if (s.rays) {
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_hashgrid_fwd(
     OutT* __restrict__ out, int32_t* __restrict__ idx_out)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos.ray_major) {
+    if (pos.ray_major_dev ? (__ldg(pos.ray_major_dev) != 0) : (pos.ray_major != 0)) {
         // frames (consecutive rays = adjacent pixels): a warp takes ONE sample of 32 neighbouring rays, so its lanes
         // sit in the same or neighbouring cells up to the levels whose cells are as small as a pixel footprint
         const int sgroups = (pos.S + 7) / 8;
@@ -326,7 +326,8 @@ static int hashgrid_fwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P
     ACN_REQUIRE((pos.x || (pos.rays && pos.t && pos.S >= 1)) && table && out, ACN_EINVAL, "%s: null buffer", fn);
     ACN_REQUIRE(((uintptr_t)table & 15) == 0 && ((uintptr_t)out & 7) == 0, ACN_EINVAL, "%s: misaligned table/out", fn);
     const int block = 256;
-    const int grid = pos.ray_major ? (int)(((P / pos.S + 31) / 32) * ((pos.S + 7) / 8)) : acn_grid_1d(P, block);
+    // the ray-major grid covers the sample-major one too, so a launch whose mapping is decided on the device uses it
+    const int grid = (pos.ray_major || pos.ray_major_dev) ? (int)(((P / pos.S + 31) / 32) * ((pos.S + 7) / 8)) : acn_grid_1d(P, block);
     cudaStream_t st = (cudaStream_t)stream;
     if (out_dtype == ACN_F32) {
         DISPATCH_F(F, (k_hashgrid_fwd<FF, float><<<grid, block, 0, st>>>(pos, P, box6_or_null, table, L, log2T, res,
@@ -366,7 +367,7 @@ static int hashgrid_bwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P
 extern "C" int acn_hashgrid_fwd(acn_ctx* ctx, const float* x, int64_t P, int x_stride, const float* box6_or_null,
                                 const float* table, int L, int F, int log2T, const int32_t* res, int interp,
                                 void* out, int out_dtype, int32_t* idx_out_or_null, acn_stream stream) {
-    PosSrc pos{ x, x_stride, nullptr, nullptr, 0, 0 };
+    PosSrc pos{ x, x_stride, nullptr, nullptr, 0, 0, nullptr };
     return hashgrid_fwd_impl(ctx, "acn_hashgrid_fwd", pos, P, box6_or_null, table, L, F, log2T, res, interp, out, out_dtype,
                              idx_out_or_null, stream);
 }
@@ -374,16 +375,16 @@ extern "C" int acn_hashgrid_fwd(acn_ctx* ctx, const float* x, int64_t P, int x_s
 extern "C" int acn_hashgrid_bwd(acn_ctx* ctx, const float* x, int64_t P, int x_stride, const float* box6_or_null, int L,
                                 int F, int log2T, const int32_t* res, int interp, const void* dout, int dout_dtype,
                                 float* dtable, acn_stream stream) {
-    PosSrc pos{ x, x_stride, nullptr, nullptr, 0, 0 };
+    PosSrc pos{ x, x_stride, nullptr, nullptr, 0, 0, nullptr };
     return hashgrid_bwd_impl(ctx, "acn_hashgrid_bwd", pos, P, box6_or_null, L, F, log2T, res, interp, dout, dout_dtype, dtable, stream);
 }
 
 extern "C" int acn_hashgrid_fwd_rays(acn_ctx* ctx, const float* rays8, const float* t_vals, int64_t N, int S,
                                      const float* box6_or_null, const float* table, int L, int F, int log2T,
                                      const int32_t* res, int interp, void* out, int out_dtype, int ray_major,
-                                     acn_stream stream) {
+                                     const int32_t* ray_major_dev_or_null, acn_stream stream) {
     ACN_REQUIRE(N >= 0 && S >= 1, ACN_EINVAL, "acn_hashgrid_fwd_rays: bad N / S");
-    PosSrc pos{ nullptr, 0, rays8, t_vals, S, ray_major ? 1 : 0 };
+    PosSrc pos{ nullptr, 0, rays8, t_vals, S, ray_major ? 1 : 0, ray_major_dev_or_null };
     return hashgrid_fwd_impl(ctx, "acn_hashgrid_fwd_rays", pos, N * S, box6_or_null, table, L, F, log2T, res, interp, out,
                              out_dtype, nullptr, stream);
 }
@@ -411,7 +412,7 @@ extern "C" int acn_hashgrid_bwd_rays(acn_ctx* ctx, const float* rays8, const flo
         ACN_CHECK_LAUNCH();
         return ACN_OK;
     }
-    PosSrc pos{ nullptr, 0, rays8, t_vals, S, 0 };
+    PosSrc pos{ nullptr, 0, rays8, t_vals, S, 0, nullptr };
     return hashgrid_bwd_impl(ctx, "acn_hashgrid_bwd_rays", pos, N * S, box6_or_null, L, F, log2T, res, interp, dout, dout_dtype,
                              dtable, stream);
 }

@@ -142,6 +142,32 @@ __global__ void k_points(const float* __restrict__ rays8, int64_t N, int S, cons
     }
 }
 
+// Are consecutive rays neighbouring pixels of a frame?  One warp looks at the first 65 rays: the gap between ray r and
+// r+1 at mid depth against the spacing of the samples along the ray; *flag = 1 when more than half of the usable pairs
+// (i.e. the median) fall below threshold.  A performance hint for the gather kernels' warp mapping -- never changes results.
+__global__ void k_rays_coherent(const float* __restrict__ rays8, int64_t N, int S, float threshold, int32_t* __restrict__ flag) {
+    const int lane = threadIdx.x;
+    const int pairs = (int)(N < 65 ? N : 65) - 1;
+    int valid = 0, good = 0;
+    for (int i = lane; i < pairs; i += 32) {
+        const float* a = rays8 + 8 * (int64_t)i;
+        const float* b = a + 8;
+        const float tm = 0.5f * (a[6] + a[7]);
+        const float gx = (b[0] - a[0]) + (b[3] - a[3]) * tm, gy = (b[1] - a[1]) + (b[4] - a[4]) * tm,
+                    gz = (b[2] - a[2]) + (b[5] - a[5]) * tm;
+        const float gap = sqrtf(gx * gx + gy * gy + gz * gz);
+        const float step = fabsf(a[7] - a[6]) / (float)S;
+        const bool ok = isfinite(gap) && isfinite(step) && step > 0.0f;
+        valid += ok;
+        good += ok && gap < threshold * step;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        valid += __shfl_xor_sync(0xffffffffu, valid, d);
+        good += __shfl_xor_sync(0xffffffffu, good, d);
+    }
+    if (lane == 0) *flag = (N >= 33 && valid > 0 && 2 * good > valid) ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" int acn_ray_directions(acn_ctx* ctx, int H, int W, float fx, float fy, float cx, float cy,
                                   int center_pixels, float* dirs, acn_stream stream) {
@@ -210,6 +236,15 @@ extern "C" int acn_points(acn_ctx* ctx, const float* rays8, int64_t N, int S, co
     if (N == 0) return ACN_OK;
     ACN_REQUIRE(rays8 && t_vals && id6, ACN_EINVAL, "acn_points: null buffer");
     k_points<<<acn_grid_1d(N * S, 256), 256, 0, (cudaStream_t)stream>>>(rays8, N, S, t_vals, id6);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
+
+extern "C" int acn_rays_coherent(acn_ctx* ctx, const float* rays8, int64_t N, int S, float threshold, int32_t* flag,
+                                 acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    ACN_REQUIRE(N >= 0 && S >= 1 && flag && (N == 0 || rays8), ACN_EINVAL, "acn_rays_coherent: bad arguments");
+    k_rays_coherent<<<1, 32, 0, (cudaStream_t)stream>>>(rays8, N, S, threshold, flag);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }

@@ -281,7 +281,8 @@ __device__ __forceinline__ unsigned support_bits(const float* pos, const float* 
 template <int DIMS, int MAXK, bool BUCKET>
 __global__ void __launch_bounds__(ROUTE_THREADS) k_route_samples(
     const float* __restrict__ rays8, const float* __restrict__ t_vals, int64_t P, int S, const float* __restrict__ cen,
-    int K, float margin, int ray_major, uint16_t* __restrict__ support, int32_t* __restrict__ counts,
+    int K, float margin, int ray_major, const int32_t* __restrict__ ray_major_dev, uint16_t* __restrict__ support,
+    int32_t* __restrict__ counts,
     const int32_t* __restrict__ offsets, int32_t* __restrict__ cursor, int32_t* __restrict__ sel, float* __restrict__ xd_out,
     float* __restrict__ w_out)
 {
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route_samples(
     // per gather instruction on a 1080p view.
     int64_t p;
     bool on;
-    if (ray_major) {
+    if (ray_major_dev ? (__ldg(ray_major_dev) != 0) : (ray_major != 0)) {
         const int sgroups = (S + ROUTE_WARPS - 1) / ROUTE_WARPS;
         const int64_t r = (int64_t)(blockIdx.x / sgroups) * 32 + lane;
         const int si = (blockIdx.x % sgroups) * ROUTE_WARPS + warp;
@@ -485,12 +486,13 @@ extern "C" int acn_dispatch_points(acn_ctx* ctx, const float* id6, int64_t P, co
 
 template <bool BUCKET>
 static int launch_route_samples(const float* rays8, const float* t_vals, int64_t N, int S, const float* cen, int K, int dims,
-                                float margin, int ray_major, uint16_t* support, int32_t* counts, const int32_t* offsets,
-                                int32_t* cursor, int32_t* sel, float* xd_out, float* w_out, cudaStream_t st) {
+                                float margin, int ray_major, const int32_t* ray_major_dev, uint16_t* support, int32_t* counts,
+                                const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out, cudaStream_t st) {
     const int64_t P = N * S;
-    const int grid = ray_major ? (int)(((N + 31) / 32) * ((S + ROUTE_WARPS - 1) / ROUTE_WARPS)) : acn_grid_1d(P, ROUTE_THREADS);
+    const int grid = (ray_major || ray_major_dev) ? (int)(((N + 31) / 32) * ((S + ROUTE_WARPS - 1) / ROUTE_WARPS)) : acn_grid_1d(P, ROUTE_THREADS);
     const size_t smem = (size_t)(BUCKET ? ROUTE_WARPS : 1) * K * sizeof(int);
-#define RS(D, MK) k_route_samples<D, MK, BUCKET><<<grid, ROUTE_THREADS, smem, st>>>(rays8, t_vals, P, S, cen, K, margin, ray_major, support, \
+#define RS(D, MK) k_route_samples<D, MK, BUCKET><<<grid, ROUTE_THREADS, smem, st>>>(rays8, t_vals, P, S, cen, K, margin, ray_major, ray_major_dev, \
+                                                                                  support, \
                                                                                   counts, offsets, cursor, sel, xd_out, w_out)
     if (dims == 2) { if (K <= 4) RS(2, 4); else if (K <= 8) RS(2, 8); else RS(2, 16); }
     else           { if (K <= 4) RS(3, 4); else if (K <= 8) RS(3, 8); else RS(3, 16); }
@@ -511,13 +513,14 @@ static int check_route_samples(const char* who, const float* rays8, const float*
 
 extern "C" int acn_route_count_rays(acn_ctx* ctx, const float* rays8, const float* t_vals, int64_t N, int S,
                                     const float* centroids, int K, int dims, float margin, int ray_major,
-                                    uint16_t* support_or_null, int32_t* counts, acn_stream stream) {
+                                    const int32_t* ray_major_dev_or_null, uint16_t* support_or_null, int32_t* counts,
+                                    acn_stream stream) {
     ACN_CHECK_CTX(ctx);
     int rc = check_route_samples("acn_route_count_rays", rays8, t_vals, N, S, centroids, K, dims, margin);
     if (rc) return rc;
     ACN_REQUIRE(counts, ACN_EINVAL, "acn_route_count_rays: null counts");
     if (N == 0) return ACN_OK;
-    launch_route_samples<false>(rays8, t_vals, N, S, centroids, K, dims, margin, ray_major, support_or_null, counts, nullptr, nullptr, nullptr,
+    launch_route_samples<false>(rays8, t_vals, N, S, centroids, K, dims, margin, ray_major, ray_major_dev_or_null, support_or_null, counts, nullptr, nullptr, nullptr,
                                 nullptr, nullptr, (cudaStream_t)stream);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
@@ -525,7 +528,7 @@ extern "C" int acn_route_count_rays(acn_ctx* ctx, const float* rays8, const floa
 
 extern "C" int acn_route_bucket_rays(acn_ctx* ctx, const float* rays8, const float* t_vals, int64_t N, int S,
                                      const float* centroids, int K, int dims, float margin, int ray_major,
-                                     const uint16_t* support_or_null, const int32_t* offsets, int32_t* cursor, int32_t* sel,
+                                     const int32_t* ray_major_dev_or_null, const uint16_t* support_or_null, const int32_t* offsets, int32_t* cursor, int32_t* sel,
                                      float* xd_out, float* w_out, acn_stream stream) {
     ACN_CHECK_CTX(ctx);
     int rc = check_route_samples("acn_route_bucket_rays", rays8, t_vals, N, S, centroids, K, dims, margin);
@@ -533,7 +536,8 @@ extern "C" int acn_route_bucket_rays(acn_ctx* ctx, const float* rays8, const flo
     ACN_REQUIRE(offsets && cursor, ACN_EINVAL, "acn_route_bucket_rays: null offsets / cursor");
     if (N == 0) return ACN_OK;
     ACN_REQUIRE(sel && xd_out && w_out && ((uintptr_t)xd_out & 7) == 0, ACN_EINVAL, "acn_route_bucket_rays: null or misaligned output");
-    launch_route_samples<true>(rays8, t_vals, N, S, centroids, K, dims, margin, ray_major, const_cast<uint16_t*>(support_or_null), nullptr,
+    launch_route_samples<true>(rays8, t_vals, N, S, centroids, K, dims, margin, ray_major, ray_major_dev_or_null,
+                               const_cast<uint16_t*>(support_or_null), nullptr,
                                offsets, cursor, sel, xd_out, w_out, (cudaStream_t)stream);
     ACN_CHECK_LAUNCH();
     return ACN_OK;

@@ -105,7 +105,7 @@ class MetaContainer(MetaModule):
     FUSED_ROUTE_MAX_EXPERTS = 16
 
     def forward_rays(self, rays: torch.Tensor, t: torch.Tensor, params: Optional[OrderedDict] = None,
-                     ray_major: bool = False) -> torch.Tensor:
+                     ray_major=False) -> torch.Tensor:
         """rays (N,8), t (N,S) -> (N,S,4): `forward(points(rays, t))` without materialising the (N*S,6) points or the
         (N*S,K) routing weights -- routing and bucketing run straight from the rays (render path of
         nerfs/ray_rendering.py:317-323 + meta_container.py:275-343)."""
@@ -116,7 +116,7 @@ class MetaContainer(MetaModule):
         dims = 2 if self.cluster_2d else 3
         # ray_major (frames: consecutive rays = adjacent pixels) orders the buckets so that a warp of the experts' gathers
         # sees one sample of 32 neighbouring pixels; otherwise a ray's samples stay together (shuffled training rays).
-        ray_major = bool(ray_major)
+        # bool, or a device flag from ops.rays_coherent_flag.
         with torch.no_grad():
             counts, support = ops.route_count_rays(rays, t, self.centroids, dims, self.boundary_margin, want_support=True,
                                                    ray_major=ray_major)

@@ -190,14 +190,15 @@ class MetaNGP(MetaModule):
                                       *self.fused_weights(params))
         return out.view(*x_d.shape[:-1], 4)
 
-    def forward_rays(self, rays: Tensor, t_vals: Tensor, params=None, ray_major: bool = False) -> Tensor:
+    def forward_rays(self, rays: Tensor, t_vals: Tensor, params=None, ray_major=False) -> Tensor:
         """Same field evaluated at the samples o + d*t of packed rays without materialising the
-        (N*S,6) point tensor (nerfs/ray_rendering.py:317-319) -> (N,S,4).  `ray_major` (forward only): a warp of the
-        encoder takes one sample of 32 consecutive rays -- for frames, where those are adjacent pixels."""
+        (N*S,6) point tensor (nerfs/ray_rendering.py:317-319) -> (N,S,4).  `ray_major` (forward only; bool, or a device flag
+        from `ops.rays_coherent_flag`): a warp of the encoder takes one sample of 32 consecutive rays -- for frames,
+        where those are adjacent pixels."""
         self._check_fused()
         table = self.xyz_encoder.hash_table
         out = ops.ExpertFieldFn.apply(None, rays, t_vals, table, self.xyz_encoder.grid_spec(),
-                                      self.box6(), self._use_half(rays.device), bool(ray_major), ops.grad_node_of(table),
+                                      self.box6(), self._use_half(rays.device), ray_major, ops.grad_node_of(table),
                                       *self.fused_weights(params))
         return out.view(t_vals.shape[0], t_vals.shape[1], 4)
 

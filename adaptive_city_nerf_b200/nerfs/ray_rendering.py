@@ -102,11 +102,11 @@ def render_rays_stratified(model, rays: Tensor, ray_samples: int, params=None, a
                            jitter: Optional[Tensor] = None, coherent_rays: Optional[bool] = None, **kwargs):
     """Stratified renderer (reference :290-345).  `coherent_rays`: consecutive rays are adjacent pixels of a frame (the
     gather kernels then work on one sample of 32 neighbouring rays per warp); None = find out from the rays themselves
-    when rendering without autograd (one small host read), never for training batches."""
+    when rendering without autograd (a one-warp kernel whose verdict stays on the device), never for training batches."""
     rays = ops.dev_f32(rays, "rays")
     N, S = rays.shape[0], int(ray_samples)
     if coherent_rays is None:
-        coherent_rays = (not torch.is_grad_enabled()) and ops.rays_are_coherent(rays, S)
+        coherent_rays = False if torch.is_grad_enabled() else ops.rays_coherent_flag(rays, S)
     with torch.no_grad():
         if model.training and jitter is None:
             jitter = torch.rand(N, S, device=rays.device, dtype=torch.float32)   # rand_like(low), reference :286

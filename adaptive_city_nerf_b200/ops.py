@@ -102,21 +102,28 @@ def points(rays: Tensor, t: Tensor) -> Tensor:
     return id6
 
 
+def rays_coherent_flag(rays: Tensor, S: int, threshold: float = 0.25) -> Tensor:
+    """Device int32 flag: 1 when consecutive rays are neighbouring pixels of a frame (the gap between ray r and r+1 at mid
+    depth is well below the spacing of the samples along a ray).  The gather kernels then give a warp one sample of 32
+    adjacent rays (`ray_major`) instead of 32 samples of one ray; handing them this tensor keeps the choice on the
+    device (no host read).  A performance hint only: results do not depend on it."""
+    rays = dev_f32(rays, "rays")
+    flag = torch.empty(1, dtype=torch.int32, device=rays.device)
+    check(lib().acn_rays_coherent(ctx(rays.device), ptr(rays), rays.shape[0], int(S), float(threshold), ptr(flag),
+                                  stream(rays.device)))
+    return flag
+
+
 def rays_are_coherent(rays: Tensor, S: int, threshold: float = 0.25) -> bool:
-    """True when consecutive rays are neighbouring pixels of a frame: the gap between ray r and r+1 at mid depth is well
-    below the spacing of the samples along a ray.  Then the gather kernels should give a warp one sample of 32 adjacent
-    rays (`ray_major`) rather than 32 samples of one ray.  Looks at the first 65 rays; one small host read (inference
-    only -- training batches are shuffled rays and never ask)."""
-    n = min(int(rays.shape[0]), 65)
-    if n < 33:
-        return False
-    a = rays[:n].float()
-    tm = 0.5 * (a[:-1, 6] + a[:-1, 7])
-    gap = ((a[1:, :3] - a[:-1, :3]) + (a[1:, 3:6] - a[:-1, 3:6]) * tm[:, None]).norm(dim=1)
-    step = (a[:-1, 7] - a[:-1, 6]).abs() / max(int(S), 1)
-    ok = torch.isfinite(gap) & torch.isfinite(step) & (step > 0)
-    ratio = torch.where(ok, gap / step.clamp_min(1e-30), torch.full_like(gap, float("inf"))).median()
-    return bool(ratio < threshold)
+    """`rays_coherent_flag` read back to the host."""
+    return bool(rays_coherent_flag(rays, S, threshold).item())
+
+
+def _ray_major_args(ray_major):
+    """(int, device pointer) for the `ray_major` / `ray_major_dev_or_null` pair of the C ABI."""
+    if isinstance(ray_major, Tensor):
+        return 0, ptr(ray_major)
+    return int(bool(ray_major)), None
 
 
 # ------------------------------------------------------------------------------------------ stage 2
@@ -167,12 +174,12 @@ def hashgrid_bwd(x: Tensor, dout: Tensor, spec: GridSpec, box6: Optional[Tensor]
 
 
 def hashgrid_fwd_rays(rays: Tensor, t: Tensor, table: Tensor, spec: GridSpec, box6: Optional[Tensor], out_dtype,
-                      ray_major: bool = False) -> Tensor:
+                      ray_major=False) -> Tensor:
     N, S = t.shape
     dev = rays.device
     out = torch.empty(N * S, spec.L * spec.F, dtype=out_dtype, device=dev)
     check(lib().acn_hashgrid_fwd_rays(ctx(dev), ptr(rays), ptr(t), N, S, ptr(box6), ptr(table), spec.L, spec.F, spec.log2T,
-                                      ptr(_grid_res(spec, dev)), spec.interp, ptr(out), _dt(out), int(ray_major), stream(dev)))
+                                      ptr(_grid_res(spec, dev)), spec.interp, ptr(out), _dt(out), *_ray_major_args(ray_major), stream(dev)))
     return out
 
 
@@ -465,7 +472,7 @@ def bucket_points(id6: Tensor, weights: Optional[Tensor], hard: Optional[Tensor]
 
 
 def route_count_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, margin: float, want_support: bool = False,
-                     ray_major: bool = False):
+                     ray_major=False):
     """Rows per expert for the samples o + d*t of `rays` -> (K,) int32 (device) [, support sets (N*S,) uint16]."""
     rays, t = dev_f32(rays, "rays"), dev_f32(t, "t_vals")
     cen = dev_f32(centroids.to(rays.device), "centroids")
@@ -473,12 +480,12 @@ def route_count_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, marg
     counts = torch.zeros(cen.shape[0], dtype=torch.int32, device=rays.device)
     support = torch.empty(N * S, dtype=torch.uint16, device=rays.device) if want_support else None
     check(lib().acn_route_count_rays(ctx(rays.device), ptr(rays), ptr(t), N, S, ptr(cen), cen.shape[0], dims, float(margin),
-                                     int(ray_major), ptr(support), ptr(counts), stream(rays.device)))
+                                     *_ray_major_args(ray_major), ptr(support), ptr(counts), stream(rays.device)))
     return (counts, support) if want_support else counts
 
 
 def route_bucket_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, margin: float, offsets: Tensor, total: int,
-                      support: Optional[Tensor] = None, ray_major: bool = False):
+                      support: Optional[Tensor] = None, ray_major=False):
     """-> sel (total,) int32 sample index, xd (total,6) [xyz, dir] rows, w (total,) blend weights; expert k's rows lie in
     [offsets[k], offsets[k] + counts[k])."""
     rays, t = dev_f32(rays, "rays"), dev_f32(t, "t_vals")
@@ -489,7 +496,7 @@ def route_bucket_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, mar
     xd = torch.empty(total, 6, dtype=torch.float32, device=dev)
     w = torch.empty(total, dtype=torch.float32, device=dev)
     cursor = torch.zeros(K, dtype=torch.int32, device=dev)
-    check(lib().acn_route_bucket_rays(ctx(dev), ptr(rays), ptr(t), N, S, ptr(cen), K, dims, float(margin), int(ray_major),
+    check(lib().acn_route_bucket_rays(ctx(dev), ptr(rays), ptr(t), N, S, ptr(cen), K, dims, float(margin), *_ray_major_args(ray_major),
                                       ptr(support), ptr(offsets), ptr(cursor), ptr(sel), ptr(xd), ptr(w), stream(dev)))
     return sel, xd, w
 

@@ -23,7 +23,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define ACN_VERSION 104 /* major*100 + minor */
+#define ACN_VERSION 105 /* major*100 + minor */
 
 typedef struct acn_ctx acn_ctx;
 typedef void* acn_stream; /* cudaStream_t */
@@ -81,6 +81,10 @@ int acn_sample_stratified(acn_ctx*, const float* rays8, int64_t N, int S, const 
 int acn_points(acn_ctx*, const float* rays8, int64_t N, int S, const float* t_vals, float* id6,
                acn_stream);
 
+/* Performance hint, not part of the reference: *flag (device int32) = 1 when consecutive rays look like adjacent pixels
+ * of a frame (median gap between rays r, r+1 at mid depth < threshold x sample spacing, over the first 65 rays). */
+int acn_rays_coherent(acn_ctx*, const float* rays8, int64_t N, int S, float threshold, int32_t* flag, acn_stream);
+
 /* ---- stage 2: multiresolution hash grid (models/encodings.py:160-381, torch branch) --------- */
 
 /* x: (P,>=3) with row stride x_stride floats.  box6_or_null = [min xyz, extent xyz] (device):
@@ -100,10 +104,12 @@ int acn_hashgrid_bwd(acn_ctx*, const float* x, int64_t P, int x_stride, const fl
  * (nerfs/ray_rendering.py:317); the reference's (N*S,6) id6 tensor is never materialised.
  * out / dout are (N*S, L*F).  ray_major != 0 (forward): a warp encodes one sample of 32 consecutive rays instead of 32
  * consecutive samples of one ray -- same output, fewer distinct cache lines per gather when consecutive rays are
- * adjacent pixels of a frame. */
+ * adjacent pixels of a frame.  ray_major_dev_or_null (device, 1 int32, e.g. from acn_rays_coherent) overrides
+ * ray_major when given, so the choice needs no host read. */
 int acn_hashgrid_fwd_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
                           const float* box6_or_null, const float* table, int L, int F, int log2T,
-                          const int32_t* res, int interp, void* out, int out_dtype, int ray_major, acn_stream);
+                          const int32_t* res, int interp, void* out, int out_dtype, int ray_major,
+                          const int32_t* ray_major_dev_or_null, acn_stream);
 int acn_hashgrid_bwd_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
                           const float* box6_or_null, int L, int F, int log2T, const int32_t* res,
                           int interp, const void* dout, int dout_dtype, float* dtable, acn_stream);
@@ -197,14 +203,14 @@ int acn_blend_bwd(acn_ctx*, const float* d_out, const float* w, const int32_t* s
  * the bucket pass, saves it the routing (distances are then evaluated only for the experts in the set).
  * ray_major != 0 orders the rows of a bucket as (sample, 32 adjacent rays) instead of (ray, 32 consecutive samples): for
  * frames, where consecutive rays are adjacent pixels, a warp of the experts' gather kernels then works on neighbouring
- * cells.  The set of rows per expert does not depend on it.
+ * cells.  The set of rows per expert does not depend on it.  ray_major_dev_or_null (device, 1 int32) overrides it.
  * Same arithmetic as acn_points + acn_route_points + acn_bucket_points (rows and weights are bit-identical); K <= 16. */
 int acn_route_count_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
                          const float* centroids, int K, int dims, float margin, int ray_major,
-                         uint16_t* support_or_null, int32_t* counts, acn_stream);
+                         const int32_t* ray_major_dev_or_null, uint16_t* support_or_null, int32_t* counts, acn_stream);
 int acn_route_bucket_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
                           const float* centroids, int K, int dims, float margin, int ray_major,
-                          const uint16_t* support_or_null, const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out, acn_stream);
+                          const int32_t* ray_major_dev_or_null, const uint16_t* support_or_null, const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out, acn_stream);
 
 /* ---- around the render: loss epilogue and optimizer tail --------------- */
 enum { ACN_COLOR_LINEAR = 0, ACN_COLOR_SRGB = 1, ACN_COLOR_IDENTITY = 2 };
