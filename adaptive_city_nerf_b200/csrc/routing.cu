@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route_samples(
     int K, float margin, int ray_major, const int32_t* __restrict__ ray_major_dev, uint16_t* __restrict__ support,
     int32_t* __restrict__ counts,
     const int32_t* __restrict__ offsets, int32_t* __restrict__ cursor, int32_t* __restrict__ sel, float* __restrict__ xd_out,
-    float* __restrict__ w_out)
+    float* __restrict__ w_out, const unsigned long long* __restrict__ row_base, const int32_t* __restrict__ row_off)
 {
     extern __shared__ int s_k[];      // COUNT: K ints; BUCKET: ROUTE_WARPS * K ints
     constexpr int OFF = DIMS == 2 ? 1 : 0;
@@ -370,10 +370,14 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route_samples(
             const bool in = (bits >> k) & 1u;
             const unsigned m = __ballot_sync(FULL, in);
             if (in) {
-                const int slot = __ldg(offsets + k) + s_k[warp * K + k] + __popc(m & ((1u << lane) - 1u));
+                const int idx = s_k[warp * K + k] + __popc(m & ((1u << lane) - 1u));
+                const int slot = __ldg(offsets + k) + idx;
                 sel[slot] = (int32_t)p;
                 w_out[slot] = soft ? __fdiv_rn(inv[k], denom) : 1.0f;
-                float2* dst = reinterpret_cast<float2*>(xd_out) + (size_t)slot * 3;
+                // expert sharding: the row goes straight into the receive buffer of the GPU that owns expert k (see
+                // k_dispatch_points); otherwise into this rank's bucket
+                float2* dst = row_base ? reinterpret_cast<float2*>(__ldg(row_base + k)) + ((size_t)__ldg(row_off + k) + idx) * 3
+                                       : reinterpret_cast<float2*>(xd_out) + (size_t)slot * 3;
                 dst[0] = make_float2(pos[0], pos[1]);
                 dst[1] = make_float2(pos[2], dir[0]);
                 dst[2] = make_float2(dir[1], dir[2]);
@@ -487,13 +491,14 @@ extern "C" int acn_dispatch_points(acn_ctx* ctx, const float* id6, int64_t P, co
 template <bool BUCKET>
 static int launch_route_samples(const float* rays8, const float* t_vals, int64_t N, int S, const float* cen, int K, int dims,
                                 float margin, int ray_major, const int32_t* ray_major_dev, uint16_t* support, int32_t* counts,
-                                const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out, cudaStream_t st) {
+                                const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out,
+                                const unsigned long long* row_base, const int32_t* row_off, cudaStream_t st) {
     const int64_t P = N * S;
     const int grid = (ray_major || ray_major_dev) ? (int)(((N + 31) / 32) * ((S + ROUTE_WARPS - 1) / ROUTE_WARPS)) : acn_grid_1d(P, ROUTE_THREADS);
     const size_t smem = (size_t)(BUCKET ? ROUTE_WARPS : 1) * K * sizeof(int);
 #define RS(D, MK) k_route_samples<D, MK, BUCKET><<<grid, ROUTE_THREADS, smem, st>>>(rays8, t_vals, P, S, cen, K, margin, ray_major, ray_major_dev, \
                                                                                   support, \
-                                                                                  counts, offsets, cursor, sel, xd_out, w_out)
+                                                                                  counts, offsets, cursor, sel, xd_out, w_out, row_base, row_off)
     if (dims == 2) { if (K <= 4) RS(2, 4); else if (K <= 8) RS(2, 8); else RS(2, 16); }
     else           { if (K <= 4) RS(3, 4); else if (K <= 8) RS(3, 8); else RS(3, 16); }
 #undef RS
@@ -521,24 +526,29 @@ extern "C" int acn_route_count_rays(acn_ctx* ctx, const float* rays8, const floa
     ACN_REQUIRE(counts, ACN_EINVAL, "acn_route_count_rays: null counts");
     if (N == 0) return ACN_OK;
     launch_route_samples<false>(rays8, t_vals, N, S, centroids, K, dims, margin, ray_major, ray_major_dev_or_null, support_or_null, counts, nullptr, nullptr, nullptr,
-                                nullptr, nullptr, (cudaStream_t)stream);
+                                nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }
 
 extern "C" int acn_route_bucket_rays(acn_ctx* ctx, const float* rays8, const float* t_vals, int64_t N, int S,
                                      const float* centroids, int K, int dims, float margin, int ray_major,
-                                     const int32_t* ray_major_dev_or_null, const uint16_t* support_or_null, const int32_t* offsets, int32_t* cursor, int32_t* sel,
-                                     float* xd_out, float* w_out, acn_stream stream) {
+                                     const int32_t* ray_major_dev_or_null, const uint16_t* support_or_null,
+                                     const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out,
+                                     const uint64_t* row_base_or_null, const int32_t* row_off_or_null, acn_stream stream) {
     ACN_CHECK_CTX(ctx);
     int rc = check_route_samples("acn_route_bucket_rays", rays8, t_vals, N, S, centroids, K, dims, margin);
     if (rc) return rc;
     ACN_REQUIRE(offsets && cursor, ACN_EINVAL, "acn_route_bucket_rays: null offsets / cursor");
     if (N == 0) return ACN_OK;
-    ACN_REQUIRE(sel && xd_out && w_out && ((uintptr_t)xd_out & 7) == 0, ACN_EINVAL, "acn_route_bucket_rays: null or misaligned output");
+    ACN_REQUIRE(sel && w_out, ACN_EINVAL, "acn_route_bucket_rays: null sel / w_out");
+    ACN_REQUIRE((row_base_or_null != nullptr) == (row_off_or_null != nullptr), ACN_EINVAL, "acn_route_bucket_rays: row_base and row_off go together");
+    ACN_REQUIRE(row_base_or_null || (xd_out && ((uintptr_t)xd_out & 7) == 0), ACN_EINVAL,
+                "acn_route_bucket_rays: xd_out (8-byte aligned) or per-expert destination buffers are needed");
     launch_route_samples<true>(rays8, t_vals, N, S, centroids, K, dims, margin, ray_major, ray_major_dev_or_null,
                                const_cast<uint16_t*>(support_or_null), nullptr,
-                               offsets, cursor, sel, xd_out, w_out, (cudaStream_t)stream);
+                               offsets, cursor, sel, xd_out, w_out, (const unsigned long long*)row_base_or_null, row_off_or_null,
+                               (cudaStream_t)stream);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }

@@ -235,11 +235,44 @@ class ExpertShardedContainer(torch.nn.Module):
                 raise RuntimeError(f"expert {active_module} is owned by rank {active_module % self.world}, not {self.rank}")
             return self.inner(x, params=params, active_module=active_module)
         c = self.inner
-        N = x.shape[0]
         id6 = ops.dev_f32(x[:, :6], "points")
-        sub_params = c._sub_params(params)
         with torch.no_grad():
             w, hard, counts = ops.route_points(id6, c.centroids, 2 if c.cluster_2d else 3, c.boundary_margin, want_counts=True)
+        return self._exchange_and_blend(
+            x.shape[0], counts, params,
+            bucket=lambda offsets, total: ops.bucket_points(id6, w, hard, self.K, offsets, total),
+            dispatch=lambda offsets, total, row_base, row_off: ops.dispatch_points(id6, w, hard, self.K, offsets, total, row_base, row_off))
+
+    def forward_rays(self, rays: Tensor, t: Tensor, params=None, ray_major=False) -> Tensor:
+        """rays (N,8), t (N,S) -> (N,S,4): the routed, blended field at the samples o + d*t, routed and bucketed (or
+        dispatched into the owners' peer buffers) straight from the rays -- no (N*S,6) points, no (N*S,K) weights.
+        `ray_major`: see MetaContainer.forward_rays."""
+        c = self.inner
+        if self.K > c.FUSED_ROUTE_MAX_EXPERTS:
+            return self.forward(ops.points(rays, t), params=params).view(t.shape[0], t.shape[1], -1)
+        N, S = t.shape
+        dims = 2 if c.cluster_2d else 3
+        with torch.no_grad():
+            counts, support = ops.route_count_rays(rays, t, c.centroids, dims, c.boundary_margin, want_support=True, ray_major=ray_major)
+        kw = dict(support=support, ray_major=ray_major)
+
+        def bucket(offsets, total):
+            return ops.route_bucket_rays(rays, t, c.centroids, dims, c.boundary_margin, offsets, total, **kw)
+
+        def dispatch(offsets, total, row_base, row_off):
+            sel, _, wsel = ops.route_bucket_rays(rays, t, c.centroids, dims, c.boundary_margin, offsets, total,
+                                                 row_base=row_base, row_off=row_off, **kw)
+            return sel, wsel
+
+        return self._exchange_and_blend(N * S, counts, params, bucket, dispatch).view(N, S, -1)
+
+    def _exchange_and_blend(self, N: int, counts: Tensor, params, bucket, dispatch) -> Tensor:
+        """counts (K,) rows per expert on this rank; bucket(offsets, total) -> (sel, xd, w) builds the local buckets,
+        dispatch(offsets, total, row_base, row_off) -> (sel, w) stores the rows into the owners' peer buffers."""
+        c = self.inner
+        dev = counts.device
+        sub_params = c._sub_params(params)
+        with torch.no_grad():
             all_counts = gather_counts(counts, self.group)              # the step's one host read
             cnt = all_counts[self.rank]
             offsets = torch.zeros(self.K, dtype=torch.int32)
@@ -249,12 +282,12 @@ class ExpertShardedContainer(torch.nn.Module):
                 pos += int(cnt[k])
             use_peer = self._peer_rows > 0 and int(all_counts.sum(0).reshape(self.m, self.world).sum(0).max()) <= self._peer_rows
             if not use_peer:
-                sel, xd, wsel = ops.bucket_points(id6, w, hard, self.K, offsets.to(x.device), pos)
+                sel, xd, wsel = bucket(offsets.to(dev), pos)
         fields = [(lambda rows, k=k: c.submodules[k](rows, params=sub_params[k])) for k in self.local_ids]
         if use_peer:
-            return self._forward_peer(id6, w, hard, all_counts, cnt, offsets, pos, fields, N)
+            return self._forward_peer(dispatch, dev, all_counts, cnt, offsets, pos, fields, N)
         y = routed_exchange(xd, all_counts, fields, self.group)
-        out = torch.zeros(N, 4, dtype=torch.float32, device=x.device) + 0.0 * y.sum()   # ties y in even if unused
+        out = torch.zeros(N, 4, dtype=torch.float32, device=dev) + 0.0 * y.sum()   # ties y in even if unused
         off = offsets.tolist()
         for k in range(self.K):                               # blend in expert order, like the reference
             n = int(cnt[k])
@@ -263,9 +296,8 @@ class ExpertShardedContainer(torch.nn.Module):
                 out = ops.BlendFn.apply(out, y[sl], wsel[sl], sel[sl])
         return out
 
-    def _forward_peer(self, id6, w, hard, all_counts, cnt, offsets, total, fields, N):
+    def _forward_peer(self, dispatch, dev, all_counts, cnt, offsets, total, fields, N):
         """The routed step over peer memory: dispatch kernel -> barrier -> owners' fields -> barrier -> blend from peers."""
-        dev = id6.device
         if self._px is None:
             self._px = PeerExchange(self._peer_rows, dev, self.group)
         px, W, m = self._px, self.world, self.m
@@ -279,7 +311,7 @@ class ExpertShardedContainer(torch.nn.Module):
             row_base = torch.tensor([px.rows_ptrs[k % W] for k in range(self.K)], dtype=torch.int64, device=dev)
             row_off = torch.tensor([p[3] for p in plan], dtype=torch.int32, device=dev)
             px.h_rows.barrier()                               # the owners are done with the previous contents of `rows`
-            sel, wsel = ops.dispatch_points(id6, w, hard, self.K, offsets.to(dev), total, row_base, row_off)
+            sel, wsel = dispatch(offsets.to(dev), total, row_base, row_off)
             px.h_rows.barrier()                               # every rank's rows have landed in every owner
             _, recv_splits, segs = exchange_segments(all_counts, self.rank)
             M = sum(recv_splits)

@@ -485,7 +485,8 @@ def route_count_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, marg
 
 
 def route_bucket_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, margin: float, offsets: Tensor, total: int,
-                      support: Optional[Tensor] = None, ray_major=False):
+                      support: Optional[Tensor] = None, ray_major=False, row_base: Optional[Tensor] = None,
+                      row_off: Optional[Tensor] = None):
     """-> sel (total,) int32 sample index, xd (total,6) [xyz, dir] rows, w (total,) blend weights; expert k's rows lie in
     [offsets[k], offsets[k] + counts[k])."""
     rays, t = dev_f32(rays, "rays"), dev_f32(t, "t_vals")
@@ -493,11 +494,13 @@ def route_bucket_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, mar
     dev, K = rays.device, cen.shape[0]
     N, S = t.shape
     sel = torch.empty(total, dtype=torch.int32, device=dev)
-    xd = torch.empty(total, 6, dtype=torch.float32, device=dev)
+    xd = torch.empty(total, 6, dtype=torch.float32, device=dev) if row_base is None else None   # else: rows go to row_base[k]
     w = torch.empty(total, dtype=torch.float32, device=dev)
     cursor = torch.zeros(K, dtype=torch.int32, device=dev)
+    assert row_base is None or (row_base.dtype == torch.int64 and row_off.dtype == torch.int32 and row_base.numel() == K == row_off.numel())
     check(lib().acn_route_bucket_rays(ctx(dev), ptr(rays), ptr(t), N, S, ptr(cen), K, dims, float(margin), *_ray_major_args(ray_major),
-                                      ptr(support), ptr(offsets), ptr(cursor), ptr(sel), ptr(xd), ptr(w), stream(dev)))
+                                      ptr(support), ptr(offsets), ptr(cursor), ptr(sel), ptr(xd), ptr(w), ptr(row_base), ptr(row_off),
+                                      stream(dev)))
     return sel, xd, w
 
 

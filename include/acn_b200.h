@@ -23,7 +23,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define ACN_VERSION 105 /* major*100 + minor */
+#define ACN_VERSION 106 /* major*100 + minor */
 
 typedef struct acn_ctx acn_ctx;
 typedef void* acn_stream; /* cudaStream_t */
@@ -204,13 +204,17 @@ int acn_blend_bwd(acn_ctx*, const float* d_out, const float* w, const int32_t* s
  * ray_major != 0 orders the rows of a bucket as (sample, 32 adjacent rays) instead of (ray, 32 consecutive samples): for
  * frames, where consecutive rays are adjacent pixels, a warp of the experts' gather kernels then works on neighbouring
  * cells.  The set of rows per expert does not depend on it.  ray_major_dev_or_null (device, 1 int32) overrides it.
+ * row_base / row_off (K each, as in acn_dispatch_points): when given, expert k's [xyz, dir] rows are stored into that
+ * buffer (peer memory of the GPU that owns k) instead of xd_out.
  * Same arithmetic as acn_points + acn_route_points + acn_bucket_points (rows and weights are bit-identical); K <= 16. */
 int acn_route_count_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
                          const float* centroids, int K, int dims, float margin, int ray_major,
                          const int32_t* ray_major_dev_or_null, uint16_t* support_or_null, int32_t* counts, acn_stream);
 int acn_route_bucket_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
                           const float* centroids, int K, int dims, float margin, int ray_major,
-                          const int32_t* ray_major_dev_or_null, const uint16_t* support_or_null, const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out, acn_stream);
+                          const int32_t* ray_major_dev_or_null, const uint16_t* support_or_null,
+                          const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out,
+                          const uint64_t* row_base_or_null, const int32_t* row_off_or_null, acn_stream);
 
 /* ---- around the render: loss epilogue and optimizer tail --------------- */
 enum { ACN_COLOR_LINEAR = 0, ACN_COLOR_SRGB = 1, ACN_COLOR_IDENTITY = 2 };

@@ -73,7 +73,14 @@ def _worker(rank, world, port, margin, peer_rows, ret):
         n_owned = sum(1 for k in model.local_ids for _ in model.submodules[k].parameters())
         total = sharded_clip_grad_norm_(model.local_parameters(), model.shared_parameters(), 1e9)
         ref_total = float(torch.sqrt(sum(g.double().pow(2).sum() for g in ref_grads.values())))
-        ret[rank] = (err, gerr, n_owned, float(total), ref_total)
+        # the (N,>=6) point interface of the reference and the frame mode of the ray interface give the same field
+        from adaptive_city_nerf_b200 import ops
+        with torch.no_grad():
+            t = ops.sample_stratified(mine, S, None)
+            y_pts = model(ops.points(mine, t)).view(-1, S, 4)
+            y_rays = model.forward_rays(mine, t, ray_major=True)
+        perr = float((y_pts - y_rays).abs().max())
+        ret[rank] = (err, gerr, n_owned, float(total), ref_total, perr)
     finally:
         dist.destroy_process_group()
 
@@ -88,7 +95,8 @@ def test_expert_sharded_container_matches_single_process(margin, peer_rows):
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), margin, peer_rows, ret), nprocs=2, join=True)
     for rank in range(2):
-        err, gerr, n_owned, total, ref_total = ret[rank]
+        err, gerr, n_owned, total, ref_total, perr = ret[rank]
+        assert perr == 0.0, (rank, perr)                    # points path == rays path (ray-major buckets), bit for bit
         assert err < 1e-5, (rank, err)                      # same kernels, same order of blending
         assert gerr < 1e-4, (rank, gerr)                    # float atomics reorder sums; nothing else differs
         assert n_owned == 2 * 15                            # two experts' 14 MLP tensors + table each (experts r and r + 2)

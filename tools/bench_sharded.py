@@ -71,11 +71,11 @@ def step():
 
 fn = step if train else frame
 model.train() if train else model.eval()
-for _ in range(2):
+for _ in range(3):
     fn()
 dist.barrier(); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-K = 4
+K = 6
 e0.record()
 for _ in range(K):
     fn()
