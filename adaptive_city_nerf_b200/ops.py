@@ -504,6 +504,18 @@ def route_bucket_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, mar
     return sel, xd, w
 
 
+def bin_indices(hard: Tensor, K: int, offsets: Tensor, total: int) -> Tensor:
+    """Indices i grouped by hard[i] (int32, -1 = skip): group k occupies [offsets[k], offsets[k] + count_k) -> (total,) int32."""
+    dev = hard.device
+    sel = torch.empty(total, dtype=torch.int32, device=dev)
+    if total == 0 or hard.shape[0] == 0:
+        return sel
+    cursor = torch.zeros(K, dtype=torch.int32, device=dev)
+    check(lib().acn_bucket_points(ctx(dev), None, hard.shape[0], None, ptr(hard), K, ptr(offsets), ptr(cursor), ptr(sel), None,
+                                  None, stream(dev)))
+    return sel
+
+
 def dispatch_points(id6: Tensor, weights: Optional[Tensor], hard: Optional[Tensor], K: int, offsets: Tensor, total: int,
                     row_base: Tensor, row_off: Tensor):
     """bucket_points whose [xyz,dir] rows are stored into per-expert destination buffers (peer memory): row_base (K,)

@@ -23,7 +23,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define ACN_VERSION 106 /* major*100 + minor */
+#define ACN_VERSION 107 /* major*100 + minor */
 
 typedef struct acn_ctx acn_ctx;
 typedef void* acn_stream; /* cudaStream_t */
@@ -259,6 +259,18 @@ int acn_adam_prepare(acn_ctx*, double* acc2, const float* grad_scale_or_null, co
                      acn_stream);
 int acn_adam_apply(acn_ctx*, const acn_adam_tensor* tensors, int count, const double* state8, double beta1,
                    double beta2, double eps, int adamw, int write_grads, acn_stream);
+
+/* ---- ray-batch producer ------------------------------------------------------ */
+/* data/task_dataset.py:544-627 TaskDataset._route_and_bin with routing_policy="dda" (nerf_runner.py:207), per ray:
+ * clip to the region box and (near, far) (:155-172), walk the nx*ny*nz task grid for at most max_steps voxels keeping the
+ * cell with the longest in-cell parametric length (:239-351), drop the ray when its overlap with that cell is below
+ * tol[cell] (:590-603).  aabb6 = region [lo, hi]; cell3 = clamp((hi-lo)/cells, 1e-12) (3 floats), cell_bounds (C,2,3) and
+ * tol (C) are the small tensors the reference builds on the host (:174-197, :241-245, :595-597), all on the device.
+ * cid_out (N) int32 = cell or -1; best_len_or_null (N); counts_or_null (C) int32 is ADDED to.  Bins: feed cid_out to
+ * acn_bucket_points as `hard`. */
+int acn_dda_route_rays(acn_ctx*, const float* rays8, int64_t N, const float* aabb6, int nx, int ny, int nz,
+                       const float* cell3, const float* cell_bounds, const float* tol, int max_steps,
+                       int32_t* cid_out, float* best_len_or_null, int32_t* counts_or_null, acn_stream);
 
 /* ---- diagnostics ---------------------------------------------------------------------------- */
 /* One tcgen05 tile GEMM  D(128,N) = A(128,K) * W(N,K)^T  (fp16 in, fp32 out); validates the

@@ -863,3 +863,112 @@ ORC_API float orc_adam_step(int T, float** p, float** g, float** m, float** v, c
     }
     return norm;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Ray-batch producer: DDA max-overlap binning of rays into the task grid
+ * ---------------------------------------------------------------------------------------- */
+
+/* torch.minimum / torch.maximum / Tensor.max(dim) propagate NaN; fminf / fmaxf do not. */
+static inline float orc_min_nan(float a, float b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
+static inline float orc_max_nan(float a, float b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
+static inline float orc_nan_to_big(float x) { return (x != x || isinf(x)) ? 1e30f : x; }  /* nan_to_num_(nan=posinf=neginf=1e30) */
+
+/* data/task_dataset.py:125-152 _aabb_intersect (eps = 1e-12) for one ray and one box. */
+static inline int orc_slab(const float* o, const float* d, const float* lo, const float* hi, float* t_entry, float* t_exit)
+{
+    float te = -INFINITY, tx = INFINITY;
+    int miss_parallel = 0, first = 1;
+    for (int a = 0; a < 3; ++a) {
+        const int parallel = fabsf(d[a]) < 1e-12f;
+        const float inv_d = 1.0f / d[a];
+        const float t0 = (lo[a] - o[a]) * inv_d, t1 = (hi[a] - o[a]) * inv_d;
+        const float tmin = orc_min_nan(t0, t1), tmax = orc_max_nan(t0, t1);
+        if (parallel && !(o[a] >= lo[a] && o[a] <= hi[a])) miss_parallel = 1;
+        te = first ? tmin : orc_max_nan(te, tmin);
+        tx = first ? tmax : orc_min_nan(tx, tmax);
+        first = 0;
+    }
+    *t_entry = te; *t_exit = tx;
+    return (tx >= te) && !miss_parallel;
+}
+
+/* The "dda" routing policy of data/task_dataset.py:544-627 _route_and_bin (nerf_runner.py:207 selects it), per ray:
+ *   :155-172 _region_segment        clip to the region box and (near, far); invalid rays get cell -1
+ *   :239-297 _dda_transform/_dda_init  grid coordinates, first voxel at t0 + 1e-6, tMax / tDelta with nan/inf -> 1e30
+ *   :299-351 _dda_maxoverlap        up to max_steps voxel steps, the cell with the longest in-cell parametric length wins
+ *                                   (tMax is measured from the entry point but compared with absolute t: kept as is)
+ *   :212-228, 590-603               overlap of the ray with the chosen cell must reach tol[cell], else the ray is dropped
+ * aabb6 = [lo, hi]; cell3 = clamp((hi-lo)/cells, 1e-12) and cell_bounds (C,2,3), tol (C) are the tensors the reference
+ * builds on the host (:174-197, :595-597).  cid_out (N): chosen cell or -1; counts (C) are ADDED to. */
+ORC_API void orc_dda_route_rays(const float* rays8, int64_t N, const float* aabb6, const int* cells, const float* cell3,
+                                const float* cell_bounds, const float* tol, int max_steps, int32_t* cid_out,
+                                float* best_len_out, int64_t* counts)
+{
+    const int nx = cells[0], ny = cells[1], nz = cells[2], nyz = ny * nz;
+    const float* lo = aabb6;
+    const float* hi = aabb6 + 3;
+    for (int64_t r = 0; r < N; ++r) {
+        const float* ray = rays8 + 8 * r;
+        const float* o = ray;
+        const float* d = ray + 3;
+        const float near = ray[6], far = ray[7];
+        cid_out[r] = -1;
+        if (best_len_out) best_len_out[r] = 0.0f;
+        float te, tx;
+        const int hit = orc_slab(o, d, lo, hi, &te, &tx);
+        float t0 = orc_max_nan(orc_max_nan(te, 0.0f), near);
+        float t1 = orc_min_nan(tx, far);
+        const float seg = t1 - t0;
+        if (!(hit && seg > 0.0f)) continue;
+        /* grid transform + init */
+        float p[3], gd[3], tmax[3], tdelta[3];
+        int64_t idx[3], step[3];
+        const int64_t ncell[3] = { nx, ny, nz };
+        const float tstart = t0 + 1e-6f;
+        for (int a = 0; a < 3; ++a) {
+            const float go = (o[a] - lo[a]) / cell3[a];
+            gd[a] = d[a] / cell3[a];
+            p[a] = go + gd[a] * tstart;
+            idx[a] = (int64_t)floorf(p[a]);
+            step[a] = gd[a] > 0.0f ? 1 : (gd[a] < 0.0f ? -1 : 0);
+            const float nb = step[a] > 0 ? floorf(p[a]) + 1.0f : ceilf(p[a]) - 1.0f;
+            const float inv = 1.0f / gd[a];
+            tmax[a] = orc_nan_to_big((nb - p[a]) * inv);
+            tdelta[a] = orc_nan_to_big((float)step[a] * inv);
+            if (idx[a] < 0) idx[a] = 0;
+            if (idx[a] > ncell[a] - 1) idx[a] = ncell[a] - 1;
+        }
+        float t = t0, best_len = 0.0f;
+        int64_t best_cid = idx[0] * nyz + idx[1] * nz + idx[2];
+        for (int it = 0; it < max_steps; ++it) {
+            const float m = orc_min_nan(orc_min_nan(tmax[0], tmax[1]), tmax[2]);
+            const float t_next = orc_min_nan(m, t1);
+            float dt = t_next - t;
+            if (dt < 0.0f) dt = 0.0f;
+            const int64_t cid = idx[0] * nyz + idx[1] * nz + idx[2];
+            if (dt > best_len) { best_len = dt; best_cid = cid; }
+            if (t_next >= t1) break;
+            const int adv_x = (tmax[0] <= tmax[1]) && (tmax[0] <= tmax[2]);
+            const int adv_y = !(tmax[0] <= tmax[1]) && (tmax[1] <= tmax[2]);
+            const int a = adv_x ? 0 : (adv_y ? 1 : 2);
+            idx[a] += step[a];
+            if (idx[a] < 0) idx[a] = 0;
+            if (idx[a] > ncell[a] - 1) idx[a] = ncell[a] - 1;
+            tmax[a] = tmax[a] + tdelta[a];
+            t = t_next;
+        }
+        /* overlap with the chosen cell */
+        const float* cb = cell_bounds + 6 * best_cid;
+        float ce, cx;
+        const int chit = orc_slab(o, d, cb, cb + 3, &ce, &cx);
+        const float c0 = orc_max_nan(orc_max_nan(ce, 0.0f), near), c1 = orc_min_nan(cx, far);
+        float len = c1 - c0;
+        if (len < 0.0f) len = 0.0f;                 /* clamp_min(0.0) keeps NaN; NaN >= tol is false either way */
+        if (!chit) len = 0.0f;
+        if (best_len_out) best_len_out[r] = best_len;
+        if (len >= tol[best_cid]) {
+            cid_out[r] = (int32_t)best_cid;
+            if (counts) counts[best_cid] += 1;
+        }
+    }
+}

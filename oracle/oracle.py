@@ -341,3 +341,17 @@ class AdamState:
                   C.c_double(self.betas[0]), C.c_double(self.betas[1]), C.c_double(self.eps), int(self.adamw),
                   C.c_float(grad_scale), C.c_float(max_norm or 0.0), C.byref(self.step), C.byref(skipped))
         return float(norm), bool(skipped.value)
+
+
+def dda_route_rays(rays, aabb, cells, cell3, cell_bounds, tol, max_steps=64):
+    """data/task_dataset.py _route_and_bin, "dda" policy -> (cell id per ray or -1, best in-cell length, counts (C,))."""
+    rays = _f(rays)
+    N = rays.shape[0]
+    C_ = int(np.prod(cells))
+    cid = np.empty(N, np.int32)
+    blen = np.empty(N, F32)
+    counts = np.zeros(C_, np.int64)
+    cells_a = np.asarray(cells, np.int32)
+    lib().orc_dda_route_rays(_p(rays), C.c_int64(N), _p(_f(aabb).reshape(-1)), _p(cells_a), _p(_f(cell3)),
+                             _p(_f(cell_bounds).reshape(-1)), _p(_f(tol)), int(max_steps), _p(cid), _p(blen), _p(counts))
+    return cid, blen, counts

@@ -559,6 +559,35 @@ def gen_optim():
     save("optim.npz", **out)
 
 
+def gen_taskgrid():
+    """data/task_dataset.py TaskDataset "dda" routing (nerf_runner.py:201-209): per-ray task cell, the bins, the region
+    box inferred from the near points, and the host-side tensors (cell bounds, tolerances) the binning uses."""
+    from data.task_dataset import TaskDataset
+    rays = T(synth.task_rays())
+    ram = types.SimpleNamespace(_rays=rays, _rgbs=torch.zeros(rays.shape[0], 3), _img_indices=torch.arange(rays.shape[0]) // 1600)
+    out = {}
+    for tag, cells, region in (("auto", (1, 6, 6), None),
+                               ("box", (2, 3, 4), tuple(map(tuple, synth.EXPERT_BOXES_G22[0].tolist())))):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ds = TaskDataset(ram_ds=ram, cell_id=0, S_target=64, Q_target=32, min_rays_cell=10, image_cap=0.4,
+                             assignment_checkpoint=0.7, routing_policy="dda", cells=cells, region_bounds=region)
+        bins = ds._route_and_bin(ds.rays, ds.aabb, ds.cells, 0.7)
+        cid = np.full(rays.shape[0], -1, np.int32)
+        for c, b in enumerate(bins):
+            cid[b.numpy()] = c
+        valid, t0, t1, seg = ds._region_segment(ds.rays, ds.aabb)
+        best = np.zeros(rays.shape[0], F32)
+        _, bl = ds._dda_maxoverlap(ds.rays[valid], t0[valid], t1[valid], max_steps=64)
+        best[valid.numpy()] = bl.numpy()
+        out[f"{tag}_cid"], out[f"{tag}_best_len"], out[f"{tag}_valid"] = cid, best, valid.numpy()
+        out[f"{tag}_aabb"], out[f"{tag}_cell_bounds"] = ds.aabb.numpy(), ds.cell_bounds.numpy()
+        out[f"{tag}_counts"] = np.array([b.numel() for b in bins], np.int64)
+        print(f"  taskgrid[{tag}]: {int(valid.sum())} valid of {rays.shape[0]}, {int((cid >= 0).sum())} binned, "
+              f"cells used {int((out[f'{tag}_counts'] > 0).sum())}/{len(bins)}")
+    save("taskgrid.npz", **out)
+
+
 if __name__ == "__main__":
     which = set(sys.argv[1:])
     cc = None
@@ -576,3 +605,4 @@ if __name__ == "__main__":
     if want("train"): gen_train()
     if want("loss"): gen_loss()
     if want("optim"): gen_optim()
+    if want("taskgrid"): gen_taskgrid()

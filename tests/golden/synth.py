@@ -138,3 +138,30 @@ def optim_inputs(seed=67, steps=6):
             gs[1][5, 7] = F32(3e35)
         grads.append(gs)
     return params, grads
+
+
+def task_rays(seed=83, n_soup=3000, aabb=AABB_GLOBAL):
+    """Packed (N,8) rays for the task-grid binning fixture: pixels of four oblique nadir views (near / far = scene-box
+    slab) plus a ray soup with degenerate directions; some miss the region, some have near >= far."""
+    rng = np.random.default_rng(seed)
+    lo, hi = aabb[0].astype(np.float64), aabb[1].astype(np.float64)
+    rays = []
+    for cam in nadir_rays(seed, 4, H=40, W=40, f=32.0):
+        j, i = np.meshgrid(np.arange(40), np.arange(40), indexing="ij")
+        dc = np.stack([(i + 0.5 - cam["cx"]) / cam["fx"], -(j + 0.5 - cam["cy"]) / cam["fy"], -np.ones_like(i, float)], -1)
+        dc /= np.linalg.norm(dc, axis=-1, keepdims=True)
+        dw = dc.reshape(-1, 3) @ cam["c2w"][:, :3].astype(np.float64).T
+        ow = np.broadcast_to(cam["c2w"][:, 3].astype(np.float64), dw.shape)
+        rays.append(np.concatenate([ow, dw], 1))
+    o, d = random_rays_in_box(seed + 1, n_soup, aabb)
+    rays.append(np.concatenate([o, d], 1).astype(np.float64))
+    od = np.concatenate(rays, 0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t0, t1 = (lo - od[:, :3]) / od[:, 3:], (hi - od[:, :3]) / od[:, 3:]
+    with np.errstate(invalid="ignore"):
+        near = np.nan_to_num(np.nanmax(np.minimum(t0, t1), 1), nan=0.0, posinf=0.0, neginf=0.0).clip(0)
+        far = np.nan_to_num(np.nanmin(np.maximum(t0, t1), 1), nan=1.0, posinf=5.0, neginf=0.0)
+    miss = ~(far > near) | (near > 10.0)              # rays that miss the scene box keep a short dummy segment
+    near[miss], far[miss] = 0.0, 0.5
+    far[::97] = near[::97] - 0.01                     # empty segments
+    return np.concatenate([od, near[:, None], far[:, None]], 1).astype(F32)

@@ -322,3 +322,54 @@ def test_get_optimizer_groups_and_training_step():
         losses[which] = hist
     assert losses["fused"][-1] < losses["fused"][0]
     np.testing.assert_allclose(losses["fused"], losses["torch"], rtol=2e-3)
+
+
+# ----------------------------------------------------------------------------- task-grid binning (ray-batch producer)
+@pytest.mark.parametrize("tag,cells,region", [("auto", (1, 6, 6), None), ("box", (2, 3, 4), "expert0")])
+def test_dda_task_binning(orc, golden, tag, cells, region):
+    """TaskDataset._route_and_bin, "dda" policy: cell per ray, counts and bins -- bit-exact vs the reference's fixture and
+    the oracle; the host-side grid tensors equal the reference's."""
+    from adaptive_city_nerf_b200.data import TaskGrid, route_and_bin
+    from adaptive_city_nerf_b200.data.task_binning import dda_route_rays
+    g = golden("taskgrid")
+    rays_np = synth.task_rays()
+    rays = cu(rays_np)
+    reg = None if region is None else tuple(map(tuple, synth.EXPERT_BOXES_G22[0].tolist()))
+    grid = TaskGrid(rays, cells, reg)
+    np.testing.assert_allclose(npy(grid.aabb), g[f"{tag}_aabb"], rtol=0, atol=0)
+    np.testing.assert_allclose(npy(grid.cell_bounds), g[f"{tag}_cell_bounds"], rtol=0, atol=1e-7)
+    cid, counts, blen = dda_route_rays(rays, grid, want_len=True)
+    o_cid, o_len, o_counts = orc.dda_route_rays(rays_np, npy(grid.aabb), cells, npy(grid.cell3), npy(grid.cell_bounds), npy(grid.tol))
+    assert (cid.cpu().numpy() == o_cid).all() and (counts.cpu().numpy() == o_counts).all()
+    assert_bitexact(npy(blen), o_len, "in-cell length vs oracle")
+    assert (cid.cpu().numpy() == g[f"{tag}_cid"]).all(), int((cid.cpu().numpy() != g[f"{tag}_cid"]).sum())
+    assert (counts.cpu().numpy() == g[f"{tag}_counts"]).all()
+    assert_bitexact(npy(blen), g[f"{tag}_best_len"], "in-cell length vs reference")
+    bins, _ = route_and_bin(rays, cells, reg)
+    assert len(bins) == int(np.prod(cells))
+    for c, b in enumerate(bins):
+        assert b.dtype == torch.int64
+        assert sorted(b.tolist()) == np.nonzero(g[f"{tag}_cid"] == c)[0].tolist()
+
+
+def test_dda_task_binning_large_and_edge_cases(orc):
+    """An expert's worth of rays (2^20) against the oracle; empty input; a grid the rays never reach."""
+    from adaptive_city_nerf_b200.data import TaskGrid, route_and_bin
+    from adaptive_city_nerf_b200.data.task_binning import dda_route_rays
+    base = synth.task_rays(seed=91, n_soup=60000)
+    rng = np.random.default_rng(2)
+    rays_np = base[rng.integers(0, base.shape[0], 1 << 20)]
+    rays_np[:, :3] += rng.normal(0, 1e-3, (rays_np.shape[0], 3)).astype(F32)
+    rays = cu(rays_np)
+    grid = TaskGrid(rays, (1, 12, 12), tuple(map(tuple, synth.AABB_GLOBAL.tolist())))
+    cid, counts = dda_route_rays(rays, grid)
+    o_cid, _, o_counts = orc.dda_route_rays(rays_np, npy(grid.aabb), grid.cells, npy(grid.cell3), npy(grid.cell_bounds), npy(grid.tol))
+    assert (cid.cpu().numpy() == o_cid).all() and (counts.cpu().numpy() == o_counts).all()
+    assert int(counts.sum()) > (1 << 19)
+    bins, _ = route_and_bin(rays[:0], (1, 2, 2), tuple(map(tuple, synth.AABB_GLOBAL.tolist())))
+    assert [b.numel() for b in bins] == [0, 0, 0, 0]
+    far_away = ((10.0, 10.0, 10.0), (11.0, 11.0, 11.0))
+    bins, _ = route_and_bin(rays[:5000], (1, 3, 3), far_away)
+    assert sum(b.numel() for b in bins) == 0
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        route_and_bin(rays[:10].cpu(), (1, 2, 2))

@@ -331,3 +331,42 @@ def test_adam_step_vs_reference(orc, golden, name, adamw, wd):
         for k in range(len(st.p)):
             np.testing.assert_allclose(st.m[k], g[f"adam_m{k}"], rtol=2e-6, atol=1e-9)
             np.testing.assert_allclose(st.v[k], g[f"adam_v{k}"], rtol=2e-6, atol=1e-12)
+
+
+# ----------------------------------------------------------------------------- task-grid binning (ray-batch producer)
+def taskgrid_host_tensors(rays, cells, region=None):
+    """The small host-side tensors of data/task_dataset.py: region box (:230-237 inferred from the near points when not
+    given), clamped cell size (:241-245), per-cell bounds (:174-197) and tolerances (:595-597) -- torch ops, as there."""
+    import torch
+    r = torch.from_numpy(np.ascontiguousarray(rays, F32))
+    if region is None:
+        pts = r[:, 0:3] + r[:, 3:6] * r[:, 6:7]
+        aabb = torch.stack([pts.min(dim=0).values, pts.max(dim=0).values], dim=0)
+    else:
+        aabb = torch.tensor(region, dtype=torch.float32)
+    lo, hi = aabb[0], aabb[1]
+    cell3 = torch.clamp((hi - lo) / torch.tensor(cells, dtype=torch.float32), min=1e-12)
+    size = (hi - lo).clamp(min=1e-9)
+    axes = [torch.linspace(0, 1, steps=n + 1) for n in cells]
+    X0, Y0, Z0 = torch.meshgrid(*[a[:-1] for a in axes], indexing="ij")
+    X1, Y1, Z1 = torch.meshgrid(*[a[1:] for a in axes], indexing="ij")
+    lo_n = torch.stack([X0, Y0, Z0], dim=-1).reshape(-1, 3)
+    hi_n = torch.stack([X1, Y1, Z1], dim=-1).reshape(-1, 3)
+    bounds = torch.stack([lo + size * lo_n, lo + size * hi_n], dim=1)
+    tol = torch.maximum(1e-6 * (bounds[:, 1] - bounds[:, 0]).norm(dim=1), torch.tensor(1e-9))
+    return aabb.numpy(), cell3.numpy(), bounds.numpy(), tol.numpy()
+
+
+@pytest.mark.parametrize("tag,cells,region", [("auto", (1, 6, 6), None), ("box", (2, 3, 4), "expert0")])
+def test_dda_task_binning_vs_reference(orc, golden, tag, cells, region):
+    """TaskDataset's "dda" routing (the policy nerf_runner.py:207 selects): the cell of every ray, bit for bit."""
+    g = golden("taskgrid")
+    rays = synth.task_rays()
+    reg = None if region is None else tuple(map(tuple, synth.EXPERT_BOXES_G22[0].tolist()))
+    aabb, cell3, bounds, tol = taskgrid_host_tensors(rays, cells, reg)
+    assert_bitexact(aabb, g[f"{tag}_aabb"], "region box")
+    assert_bitexact(bounds, g[f"{tag}_cell_bounds"], "cell bounds")
+    cid, best_len, counts = orc.dda_route_rays(rays, aabb, cells, cell3, bounds, tol)
+    assert (cid == g[f"{tag}_cid"]).all(), int((cid != g[f"{tag}_cid"]).sum())
+    assert (counts == g[f"{tag}_counts"]).all()
+    assert_bitexact(best_len, g[f"{tag}_best_len"], "in-cell length of the winning cell")
