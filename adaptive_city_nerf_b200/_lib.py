@@ -94,7 +94,7 @@ class _Profile:
         return {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in cls.events.items()}
 
 
-_NOT_KERNELS = {"acn_version", "acn_last_error", "acn_create", "acn_destroy", "acn_device_info"}
+_NOT_KERNELS = {"acn_version", "acn_last_error", "acn_create", "acn_destroy", "acn_device_info", "acn_debug_generic_scatter"}
 
 
 class _Bound:

@@ -296,6 +296,76 @@ __global__ void __launch_bounds__(256) k_hashgrid_bwd_march(
     if (have) flush();
 }
 
+// The same run-length scatter for an arbitrary (P,>=3) point list -- the routed path, where an expert's rows are
+// bucketed in (block of rays, ray, sample) order, so consecutive rows are mostly consecutive samples of one ray.  A
+// 16-lane group walks SEG consecutive rows from a rotated start; nothing depends on ray structure: a row in a different
+// cell simply flushes the accumulators.  (The per-(point, level) kernel above stays for F != 2, "Nearest" and as the
+// cross-check; measured on the 4-expert routed step: 11.6 ms -> see DESIGN.md.)
+template <typename InT>
+__global__ void __launch_bounds__(256) k_hashgrid_bwd_march_pts(
+    const float* __restrict__ x, int xs, int64_t P, int seg,
+    const float* __restrict__ box6, int L, int log2T, const int32_t* __restrict__ res, int interp,
+    const InT* __restrict__ dout, float* __restrict__ dtable)
+{
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t grp = gid >> 4;
+    const int l = (int)(gid & 15);
+    const int64_t row0 = grp * seg;
+    const int n = row0 < P ? (int)((P - row0) < seg ? (P - row0) : seg) : 0;   // uniform over the 16-lane group
+    const bool on = l < L;
+    const uint32_t mask = (1u << log2T) - 1u;
+    const float resf = (float)__ldg(res + (l < L ? l : 0));
+    float2* lt = reinterpret_cast<float2*>(dtable) + ((size_t)(l < L ? l : 0) << log2T);
+    const int comp = l < 3 ? l : 0;
+    const float mn_c = box6 ? __ldg(box6 + comp) : 0.0f, ex_c = box6 ? __ldg(box6 + 3 + comp) : 1.0f;
+    const int start = n > 0 ? (int)(((uint32_t)grp * 2654435761u) >> 8) % n : 0;
+
+    uint32_t cx = 0, cy = 0, cz = 0;
+    bool have = false;
+    float2 acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
+
+    // the two 16-lane groups of a warp may own segments of different length: iterate to the longer one so the
+    // shuffles below stay convergent
+    const int n_other = __shfl_xor_sync(0xffffffffu, n, 16);
+    const int n_iter = n > n_other ? n : n_other;
+    for (int it = 0; it < n_iter; ++it) {
+        const bool live = it < n;
+        int sidx = it + start; if (sidx >= n) sidx -= n;
+        const int64_t prow = row0 + (live ? sidx : 0);
+        float pc = (live || n > 0) ? __ldg(x + (row0 < P ? prow : 0) * xs + comp) : 0.0f;
+        if (box6) pc = world_to_unit1(pc, mn_c, ex_c);
+        const float px = __shfl_sync(0xffffffffu, pc, 0, 16);
+        const float py = __shfl_sync(0xffffffffu, pc, 1, 16);
+        const float pz = __shfl_sync(0xffffffffu, pc, 2, 16);
+        if (!on || !live) continue;
+        float2 g;
+        if constexpr (sizeof(InT) == 4) g = __ldg(reinterpret_cast<const float2*>(dout) + prow * L + l);
+        else g = __half22float2(__ldg(reinterpret_cast<const __half2*>(dout) + prow * L + l));
+        if (g.x == 0.0f && g.y == 0.0f) continue;
+        GridCell c = grid_cell(px, py, pz, resf, interp);
+        if (!(have && c.x0 == cx && c.y0 == cy && c.z0 == cz)) {
+            if (have) {
+                scatter_cell_f2(lt, cx, cy, cz, mask, acc);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
+            }
+            cx = c.x0; cy = c.y0; cz = c.z0; have = true;
+        }
+        const float wx[2] = { 1.0f - c.wx, c.wx }, wy[2] = { 1.0f - c.wy, c.wy }, wz[2] = { 1.0f - c.wz, c.wz };
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float w = wz[k & 1] * wy[(k >> 1) & 1] * wx[(k >> 2) & 1];
+            acc[k].x = fmaf(g.x, w, acc[k].x);
+            acc[k].y = fmaf(g.y, w, acc[k].y);
+        }
+    }
+    if (have) scatter_cell_f2(lt, cx, cy, cz, mask, acc);
+}
+
+static int g_force_generic_scatter = 0;   // acn_debug_generic_scatter: tests cross-check the march kernels against the plain one
+
 // ------------------------------------------------------------------------------------------ C ABI
 static int check_grid_args(const char* fn, int64_t P, int xs, int L, int F, int log2T, const void* res, int interp) {
     ACN_REQUIRE(P >= 0 && xs >= 3, ACN_EINVAL, "%s: bad P / x_stride", fn);
@@ -350,9 +420,22 @@ static int hashgrid_bwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P
     if (P == 0) return ACN_OK;
     ACN_REQUIRE((pos.x || (pos.rays && pos.t && pos.S >= 1)) && dout && dtable, ACN_EINVAL, "%s: null buffer", fn);
     ACN_REQUIRE(((uintptr_t)dtable & 15) == 0, ACN_EINVAL, "%s: misaligned dtable", fn);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pos.x && F == 2 && L <= 16 && interp != ACN_INTERP_NEAREST && !g_force_generic_scatter) {
+        ACN_REQUIRE(((uintptr_t)dout & 7) == 0, ACN_EINVAL, "%s: misaligned dout", fn);
+        const int seg = 64;
+        const int grid_m = acn_grid_1d(((P + seg - 1) / seg) * 16, 256);
+        if (dout_dtype == ACN_F32)
+            k_hashgrid_bwd_march_pts<float><<<grid_m, 256, 0, st>>>(pos.x, pos.xs, P, seg, box6_or_null, L, log2T, res, interp,
+                                                                   (const float*)dout, dtable);
+        else
+            k_hashgrid_bwd_march_pts<__half><<<grid_m, 256, 0, st>>>(pos.x, pos.xs, P, seg, box6_or_null, L, log2T, res, interp,
+                                                                    (const __half*)dout, dtable);
+        ACN_CHECK_LAUNCH();
+        return ACN_OK;
+    }
     const int block = 256;
     const int grid = acn_grid_1d(P * L, block);
-    cudaStream_t st = (cudaStream_t)stream;
     if (dout_dtype == ACN_F32) {
         DISPATCH_F(F, (k_hashgrid_bwd<FF, float><<<grid, block, 0, st>>>(pos, P, box6_or_null, L, log2T, res, interp,
                                                                         (const float*)dout, dtable)));
@@ -415,4 +498,9 @@ extern "C" int acn_hashgrid_bwd_rays(acn_ctx* ctx, const float* rays8, const flo
     PosSrc pos{ nullptr, 0, rays8, t_vals, S, 0, nullptr };
     return hashgrid_bwd_impl(ctx, "acn_hashgrid_bwd_rays", pos, N * S, box6_or_null, L, F, log2T, res, interp, dout, dout_dtype,
                              dtable, stream);
+}
+
+extern "C" int acn_debug_generic_scatter(int on) {
+    g_force_generic_scatter = on ? 1 : 0;
+    return ACN_OK;
 }

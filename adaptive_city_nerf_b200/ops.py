@@ -553,6 +553,11 @@ class BlendFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------ diagnostics
+def debug_generic_scatter(on: bool) -> None:
+    """Cross-check switch: acn_hashgrid_bwd falls back to the plain per-(point, level) scatter while on."""
+    check(lib().acn_debug_generic_scatter(int(bool(on))))
+
+
 def debug_umma_gemm(a: Tensor, w: Tensor) -> Tensor:
     """D = A @ W^T on one tcgen05 tile: A (128,K) fp16, W (N,K) fp16 -> (128,N) fp32."""
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.shape[0] == 128

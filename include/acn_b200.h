@@ -23,7 +23,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define ACN_VERSION 107 /* major*100 + minor */
+#define ACN_VERSION 108 /* major*100 + minor */
 
 typedef struct acn_ctx acn_ctx;
 typedef void* acn_stream; /* cudaStream_t */
@@ -273,6 +273,9 @@ int acn_dda_route_rays(acn_ctx*, const float* rays8, int64_t N, const float* aab
                        int32_t* cid_out, float* best_len_or_null, int32_t* counts_or_null, acn_stream);
 
 /* ---- diagnostics ---------------------------------------------------------------------------- */
+/* on != 0: acn_hashgrid_bwd uses the plain per-(point, level) scatter instead of the run-length one (a cross-check). */
+int acn_debug_generic_scatter(int on);
+
 /* One tcgen05 tile GEMM  D(128,N) = A(128,K) * W(N,K)^T  (fp16 in, fp32 out); validates the
  * shared-memory / instruction descriptors the fused MLP kernels are built on.  N in
  * {16,32,64}, K in {16,32,64}. */

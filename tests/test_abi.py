@@ -39,7 +39,7 @@ def test_ctypes_table_matches_header(built_lib):
     from adaptive_city_nerf_b200 import _lib
     assert sorted(_lib.SIGNATURES) == header_symbols()
     l = _lib.lib()
-    assert l.acn_version() == 107
+    assert l.acn_version() == 108
     for name in _lib.SIGNATURES:
         assert getattr(l, name).argtypes == _lib.SIGNATURES[name]
     assert len(_lib.SIGNATURES["acn_hashgrid_fwd"]) == 15 and len(_lib.SIGNATURES["acn_field_bwd"]) == 18

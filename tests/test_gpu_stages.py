@@ -456,10 +456,30 @@ def test_hashgrid_bwd_march_vs_generic(ops):
         dout[::7] = 0.0                                     # zero rows are skipped
         a = torch.zeros(16 << log2T, 2, device="cuda")
         b = torch.zeros_like(a)
-        ops.hashgrid_bwd_rays(rays, t, dout, spec, box6, a)                       # march kernel
-        ops.hashgrid_bwd(ops.points(rays, t), dout, spec, box6, b)                # generic kernel
+        ops.hashgrid_bwd_rays(rays, t, dout, spec, box6, a)                       # march kernel (rays)
+        ops.debug_generic_scatter(True)
+        try:
+            ops.hashgrid_bwd(ops.points(rays, t), dout, spec, box6, b)            # plain per-(point, level) kernel
+        finally:
+            ops.debug_generic_scatter(False)
         scale = float(b.abs().max())
         assert float((a - b).abs().max()) <= 2e-5 * scale + 1e-6, (S, log2T, mode)
+        # march kernel over a point list (the routed path): in order, shuffled (every row its own cell), fp16, short tail
+        pts = ops.points(rays, t)
+        for order in (None, torch.randperm(N * S, device="cuda", generator=gen)):
+            pp, dd = (pts, dout) if order is None else (pts[order].contiguous(), dout[order].contiguous())
+            c = torch.zeros_like(a)
+            ops.hashgrid_bwd(pp, dd, spec, box6, c)
+            assert float((c - b).abs().max()) <= 2e-5 * scale + 1e-6, (S, log2T, mode, order is None)
+        c16 = torch.zeros_like(a)
+        ops.hashgrid_bwd(pts[:-37], dout[:-37].half(), spec, box6, c16)
+        d_ref = torch.zeros_like(a)
+        ops.debug_generic_scatter(True)
+        try:
+            ops.hashgrid_bwd(pts[:-37], dout[:-37], spec, box6, d_ref)
+        finally:
+            ops.debug_generic_scatter(False)
+        assert float((c16 - d_ref).abs().max()) <= 2e-3 * scale
         # fp16 dL/denc input
         a16 = torch.zeros_like(a)
         ops.hashgrid_bwd_rays(rays, t, dout.half(), spec, box6, a16)
