@@ -85,13 +85,33 @@ __global__ void __launch_bounds__(256) k_hashgrid_fwd(
         } else {
             GridCell g = grid_cell(px, py, pz, resf, interp);
             float f[8][F];
-            // (Pairing the x-neighbours of even x0 into one 16-byte load -- rows r and r^1, as the scatter kernels do
-            // below -- was measured neutral here: 3.96 vs 4.01 ms; the gather is bound inside L1TEX, not by requests.)
+            // x-neighbours of an even x0 are rows r and r^1 (the hash is x ^ ...): one aligned 16-byte load fetches both.
+            // Taken only when the whole warp agrees (no divergence): that is the frame case, where a warp holds one sample
+            // of 32 adjacent pixels and shares x0 up to the mid levels.  For unrelated points it was measured neutral
+            // (3.96 vs 4.01 ms) and the vote almost never passes.
+            bool paired = false;
+            if constexpr (F == 2) paired = !idx_out && __all_sync(__activemask(), !(g.x0 & 1u));
+            if (paired) {
+                if constexpr (F == 2) {
+                    const uint32_t yp0 = g.y0 * 2654435761u, yp1 = yp0 + 2654435761u;
+                    const uint32_t zp0 = g.z0 * 805459861u, zp1 = zp0 + 805459861u;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint32_t row = grid_corner_row(g, c, mask);
-                if (idx_out) idx_out[((size_t)p * L + l) * 8 + c] = (int32_t)(row + ((uint32_t)l << log2T));
-                load_feat<F>(lt, row, f[c]);
+                    for (int yz = 0; yz < 4; ++yz) {
+                        const uint32_t h = ((yz & 2) ? yp1 : yp0) ^ ((yz & 1) ? zp1 : zp0);
+                        const uint32_t r0 = (g.x0 ^ h) & mask;
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(lt) + (r0 >> 1));
+                        const bool odd = r0 & 1u;
+                        f[yz][0] = odd ? v.z : v.x; f[yz][1] = odd ? v.w : v.y;
+                        f[4 + yz][0] = odd ? v.x : v.z; f[4 + yz][1] = odd ? v.y : v.w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint32_t row = grid_corner_row(g, c, mask);
+                    if (idx_out) idx_out[((size_t)p * L + l) * 8 + c] = (int32_t)(row + ((uint32_t)l << log2T));
+                    load_feat<F>(lt, row, f[c]);
+                }
             }
             if constexpr (sizeof(OutT) == 2) {
                 // fp16 output: fused lerps a + w (b - a); the ~1e-7 difference to the reference's un-fused form
