@@ -250,22 +250,62 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_dispatch_points(
 // contiguous range per expert per block and writes sel / w / [xyz, dir] rows.  Same arithmetic as k_points +
 // k_route_points (terms outside the set contribute an exact +0 to the normaliser), so rows and weights are
 // bit-identical to the unfused path.
+// cdist_mm without the final square root (the value torch's cdist clamps at 0 and roots)
+template <int DIMS>
+__device__ __forceinline__ float cdist_mm_sq(const float* x, const float* __restrict__ c) {
+    float xn = __fmul_rn(x[0], x[0]), cn = __fmul_rn(__ldg(c), __ldg(c));
+#pragma unroll
+    for (int k = 1; k < DIMS; ++k) {
+        xn = __fadd_rn(xn, __fmul_rn(x[k], x[k]));
+        cn = __fadd_rn(cn, __fmul_rn(__ldg(c + k), __ldg(c + k)));
+    }
+    float acc = __fmul_rn(__fmul_rn(-2.0f, x[0]), __ldg(c));
+#pragma unroll
+    for (int k = 1; k < DIMS; ++k) acc = __fmaf_rn(__fmul_rn(-2.0f, x[k]), __ldg(c + k), acc);
+    acc = __fadd_rn(xn, acc);
+    acc = __fadd_rn(acc, cn);
+    return fmaxf(acc, 0.0f);
+}
+
+// Support set of one sample (meta_container.py:97-134): bit k set <=> d_k <= margin * min_j d_j, d = max(cdist, 1e-6)
+// (margin > 1), or the argmin (margin == 1).  The IEEE square roots are only taken where they can matter: with
+// a = d^2 before rounding, a_k > a_min * margin^2 * (1 + 2e-5) implies d_k > fl(margin * d_min) by a margin three orders
+// above the rounding of sqrt / the product, so such experts are out without a root; a lone survivor is the minimum
+// itself, which is always in the set (margin >= 1).  Everything else -- ties, boundary samples, tiny or non-finite
+// distances -- takes the exact path, so the result is bit-identical to evaluating every distance.
 template <int DIMS, int MAXK>
 __device__ __forceinline__ unsigned support_bits(const float* pos, const float* __restrict__ cen, int K, float margin) {
     constexpr int OFF = DIMS == 2 ? 1 : 0;
     unsigned bits = 0;
     if (margin > 1.0f) {
-        float d[MAXK];
-        float mind = __int_as_float(0x7f800000);
+        float a[MAXK];
+        float amin = __int_as_float(0x7f800000);
 #pragma unroll
         for (int k = 0; k < MAXK; ++k) {
-            d[k] = 0.0f;
-            if (k < K) { d[k] = fmaxf(cdist_mm<DIMS>(pos + OFF, cen + 3 * k + OFF), 1e-6f); mind = fminf(mind, d[k]); }
+            a[k] = 0.0f;
+            if (k < K) { a[k] = cdist_mm_sq<DIMS>(pos + OFF, cen + 3 * k + OFF); amin = fminf(amin, a[k]); }
+        }
+        const float cut = amin * (margin * margin * 1.00002f);
+        unsigned cand = 0;
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+            if (k < K && !(a[k] > cut)) cand |= 1u << k;          // NaN stays a candidate and fails the exact test below
+        if (__popc(cand) == 1 && amin >= 1e-11f && amin < 1e30f) return cand;
+        float mind = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+            if ((cand >> k) & 1u) { a[k] = fmaxf(__fsqrt_rn(a[k]), 1e-6f); mind = fminf(mind, a[k]); }
+        // the minimum over all experts is attained among the candidates (amin itself is one)
+        if (!(amin >= 1e-11f && amin < 1e30f)) {                 // 1e-6 floor in play, or overflow: every distance, exactly
+            cand = 0; mind = __int_as_float(0x7f800000);
+#pragma unroll
+            for (int k = 0; k < MAXK; ++k)
+                if (k < K) { a[k] = fmaxf(cdist_mm<DIMS>(pos + OFF, cen + 3 * k + OFF), 1e-6f); mind = fminf(mind, a[k]); cand |= 1u << k; }
         }
         const float thr = __fmul_rn(margin, mind);
 #pragma unroll
         for (int k = 0; k < MAXK; ++k)
-            if (k < K && d[k] <= thr) bits |= 1u << k;
+            if (((cand >> k) & 1u) && a[k] <= thr) bits |= 1u << k;
     } else {                                                // hard: first minimum wins, like argmin
         int best = 0;
         float bd = cdist_mm<DIMS>(pos + OFF, cen + OFF);
@@ -296,34 +336,59 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route_samples(
     // per gather instruction on a 1080p view.
     int64_t p;
     bool on;
-    if (ray_major_dev ? (__ldg(ray_major_dev) != 0) : (ray_major != 0)) {
+    const bool rm = ray_major_dev ? (__ldg(ray_major_dev) != 0) : (ray_major != 0);
+    // ray-major: the block owns a 32-ray x 16-sample tile.  t_vals and the support sets are (ray, sample) row-major, so a
+    // warp (= one sample of 32 rays) would touch 32 different lines per access; the tile goes through shared memory
+    // instead, moved by threads laid out (ray = tid / 16, sample = tid % 16): 64 contiguous bytes per ray.
+    __shared__ float s_t[32][ROUTE_WARPS + 1];
+    __shared__ uint16_t s_sup[32][ROUTE_WARPS + 2];
+    int64_t p_tile = 0;                                     // the element this thread moves for the tile
+    bool on_tile = false;
+    const int tr = threadIdx.x / ROUTE_WARPS, ts = threadIdx.x % ROUTE_WARPS;
+    if (rm) {
         const int sgroups = (S + ROUTE_WARPS - 1) / ROUTE_WARPS;
-        const int64_t r = (int64_t)(blockIdx.x / sgroups) * 32 + lane;
-        const int si = (blockIdx.x % sgroups) * ROUTE_WARPS + warp;
+        const int64_t r0 = (int64_t)(blockIdx.x / sgroups) * 32;
+        const int s0 = (blockIdx.x % sgroups) * ROUTE_WARPS;
+        const int64_t r = r0 + lane;
+        const int si = s0 + warp;
         on = si < S && r * S < P;
         p = r * S + si;
+        on_tile = (s0 + ts) < S && (r0 + tr) * S < P;
+        p_tile = (r0 + tr) * S + s0 + ts;
+        if (on_tile) {
+            s_t[tr][ts] = t_vals[p_tile];
+            if (BUCKET && support) s_sup[tr][ts] = support[p_tile];
+        }
     } else {
         p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         on = p < P;
     }
     if (!BUCKET) {
         for (int k = threadIdx.x; k < K; k += blockDim.x) s_k[k] = 0;
-        __syncthreads();
     }
+    if (rm || !BUCKET) __syncthreads();
     float pos[3] = { 0.f, 0.f, 0.f }, dir[3] = { 0.f, 0.f, 0.f };
     if (on) {
         const int64_t r = p / S;
         const float4 a = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * r));
         const float4 b = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * r) + 1);
-        const float t = t_vals[p];
+        const float t = rm ? s_t[lane][warp] : t_vals[p];
         dir[0] = a.w; dir[1] = b.x; dir[2] = b.y;
         pos[0] = __fadd_rn(a.x, __fmul_rn(dir[0], t));      // k_points
         pos[1] = __fadd_rn(a.y, __fmul_rn(dir[1], t));
         pos[2] = __fadd_rn(a.z, __fmul_rn(dir[2], t));
     }
     unsigned bits = 0;
-    if (on) bits = (BUCKET && support) ? (unsigned)support[p] : support_bits<DIMS, MAXK>(pos, cen, K, margin);
-    if (!BUCKET && support && on) support[p] = (uint16_t)bits;
+    if (on) bits = (BUCKET && support) ? (unsigned)(rm ? s_sup[lane][warp] : support[p]) : support_bits<DIMS, MAXK>(pos, cen, K, margin);
+    if (!BUCKET && support) {
+        if (rm) {
+            s_sup[lane][warp] = (uint16_t)bits;
+            __syncthreads();
+            if (on_tile) support[p_tile] = s_sup[tr][ts];
+        } else if (on) {
+            support[p] = (uint16_t)bits;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < MAXK; ++k) {
         if (k < K) {

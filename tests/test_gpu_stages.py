@@ -407,6 +407,41 @@ def test_route_and_bucket_straight_from_rays(ops, orc, golden, K, margin, dims):
     assert int(empty.sum()) == 0
 
 
+def test_route_from_rays_on_the_margin_boundary(ops, orc):
+    """Samples placed ON the surfaces d_k = margin * d_min (Apollonius circles of centroid pairs, rounded to fp32 so they
+    fall on either side by an ulp): the support sets from the fused kernels (which skip the square roots of clearly distant
+    experts) must equal the oracle's evaluation of every distance, bit for bit."""
+    rng = np.random.default_rng(12)
+    cen = synth.CENTROIDS_G22.astype(np.float64)
+    for margin in (1.05, 1.1, 1.5):
+        pts = []
+        for i in range(4):
+            for j in range(4):
+                if i == j:
+                    continue
+                c0, c1 = cen[i, 1:], cen[j, 1:]
+                m2 = np.float64(np.float32(margin)) ** 2
+                ctr, rad = (m2 * c0 - c1) / (m2 - 1.0), np.sqrt(m2) * np.linalg.norm(c0 - c1) / (m2 - 1.0)
+                th = rng.uniform(0, 2 * np.pi, 60000)
+                q = ctr + rad * np.stack([np.cos(th), np.sin(th)], 1)
+                q = q[(np.abs(q) < 1.2).all(1)]
+                pts.append(q)
+        yz = np.concatenate(pts)
+        yz = np.concatenate([yz, yz * (1 + rng.normal(0, 3e-7, yz.shape))])      # and a few ulps around them
+        N = yz.shape[0]
+        o = np.concatenate([rng.uniform(0, 0.4, (N, 1)), yz], 1).astype(F32)
+        rays_np = np.concatenate([o, np.zeros((N, 3), F32), np.zeros((N, 1), F32), np.ones((N, 1), F32)], 1).astype(F32)
+        rays = cu(rays_np)
+        t = torch.full((N, 1), 0.5, device="cuda")
+        counts, support = ops.route_count_rays(rays, t, cu(synth.CENTROIDS_G22), 2, margin, want_support=True)
+        ow, _ = orc.route_points(o, synth.CENTROIDS_G22, margin)
+        want = ((ow > 0) * (1 << np.arange(4))).sum(1)
+        got = support.cpu().numpy().astype(np.int64)
+        assert (got == want).all(), (margin, int((got != want).sum()))
+        assert ((ow > 0).sum(1) >= 2).mean() > 0.2            # the boundary really is exercised
+        assert (npy(counts) == (ow > 0).sum(0)).all()
+
+
 def _compare_buckets(K, off, cnt, a, b):
     (sel_a, xd_a, w_a), (sel_b, xd_b, w_b) = a, b
     for k in range(K):
