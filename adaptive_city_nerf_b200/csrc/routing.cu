@@ -7,7 +7,7 @@
 #include "acn_common.cuh"
 
 #define FULL 0xffffffffu
-static constexpr int ROUTE_THREADS = 512;    // points per block of the routing / bucketing kernels
+static constexpr int ROUTE_THREADS = 256;    // points per block of the routing / bucketing kernels
 static constexpr int ROUTE_WARPS = ROUTE_THREADS / 32;
 
 template <int DIMS>
