@@ -198,3 +198,17 @@ def test_train_step_host_logic_without_gpu(built_lib):
         opt.step()
     opt2 = FusedAdam([torch.nn.Parameter(torch.zeros(1))])
     opt2.step()                                                             # nothing has a gradient: a no-op, as in torch
+
+
+def test_task_grid_host_tensors_match_reference(golden):
+    """data/task_binning.TaskGrid builds the region box, cell bounds and tolerances with torch ops (no kernel): they must
+    equal what the reference's TaskDataset built (tests/golden/taskgrid.npz), bit for bit, on CPU tensors too."""
+    from adaptive_city_nerf_b200.data import TaskGrid
+    g = golden("taskgrid")
+    rays = torch.from_numpy(synth.task_rays())
+    for tag, cells, region in (("auto", (1, 6, 6), None), ("box", (2, 3, 4), tuple(map(tuple, synth.EXPERT_BOXES_G22[0].tolist())))):
+        grid = TaskGrid(rays, cells, region)
+        assert grid.num_cells == int(np.prod(cells))
+        assert (grid.aabb.numpy().view(np.uint32) == g[f"{tag}_aabb"].view(np.uint32)).all()
+        assert (grid.cell_bounds.numpy().view(np.uint32) == g[f"{tag}_cell_bounds"].view(np.uint32)).all()
+        assert grid.cell3.shape == (3,) and grid.tol.shape == (grid.num_cells,) and bool((grid.tol >= 1e-9).all())
