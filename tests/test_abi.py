@@ -212,3 +212,14 @@ def test_task_grid_host_tensors_match_reference(golden):
         assert (grid.aabb.numpy().view(np.uint32) == g[f"{tag}_aabb"].view(np.uint32)).all()
         assert (grid.cell_bounds.numpy().view(np.uint32) == g[f"{tag}_cell_bounds"].view(np.uint32)).all()
         assert grid.cell3.shape == (3,) and grid.tol.shape == (grid.num_cells,) and bool((grid.tol >= 1e-9).all())
+
+
+def test_integration_md_ctypes_example_matches_the_header():
+    """The argument counts of the calls shown in INTEGRATION.md section 2 are the header's."""
+    from adaptive_city_nerf_b200 import _lib
+    text = (ROOT / "INTEGRATION.md").read_text()
+    for name in ("acn_hashgrid_fwd_rays", "acn_field_fwd", "acn_composite_fwd"):
+        m = re.search(r"lib\." + name + r"\((.*?)\)\s*(?:#|\n[a-z#`])", text, flags=re.S)
+        assert m, name
+        args = re.sub(r"\([^()]*\)", "", m.group(1))              # drop nested calls such as C.c_int64(N)
+        assert len([a for a in args.split(",") if a.strip()]) == len(_lib.SIGNATURES[name]), name
