@@ -14,6 +14,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libacn_b200.so"
+DEBUG_LIB_PATH = _PKG / "libacn_b200_debug.so"
 
 F32, F16 = 0, 1
 INTERP = {"Nearest": 0, "Linear": 1, "Smoothstep": 2}
@@ -21,6 +22,8 @@ INTERP = {"Nearest": 0, "Linear": 1, "Smoothstep": 2}
 _lock = threading.Lock()
 _lib = None
 _ctx = {}
+_dlib = None
+_dctx = {}
 
 c_i64, c_int, c_f, c_p = C.c_int64, C.c_int, C.c_float, C.c_void_p
 
@@ -41,6 +44,7 @@ COLOR_SPACE = {"linear": 0, "srgb": 1, "identity": 2}
 
 
 HEADER = _PKG.parent / "include" / "acn_b200.h"
+DEBUG_HEADER = _PKG.parent / "include" / "acn_b200_debug.h"
 
 
 def _parse_header(path: Path):
@@ -94,7 +98,7 @@ class _Profile:
         return {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in cls.events.items()}
 
 
-_NOT_KERNELS = {"acn_version", "acn_last_error", "acn_create", "acn_destroy", "acn_device_info", "acn_debug_generic_scatter"}
+_NOT_KERNELS = {"acn_version", "acn_last_error", "acn_create", "acn_destroy", "acn_device_info", "acn_debug_field_trace"}
 
 
 class _Bound:
@@ -139,6 +143,45 @@ def lib():
                     setattr(ns, name, _wrap(name, fn))
                 _lib = ns
     return _lib
+
+
+def debug_lib():
+    """libacn_b200_debug.so: the probes and timelines of include/acn_b200_debug.h (plus a private copy of the product
+    entry points, so a traced kernel can be driven through the normal ABI).  tools/ and descriptor self-tests only."""
+    global _dlib
+    if _dlib is None:
+        with _lock:
+            if _dlib is None:
+                if not DEBUG_LIB_PATH.exists():
+                    raise RuntimeError(f"{DEBUG_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+                l = C.CDLL(str(DEBUG_LIB_PATH))
+                ns = _Bound()
+                sigs = dict(SIGNATURES)
+                sigs.update(_parse_header(DEBUG_HEADER))
+                for name, argtypes in sigs.items():
+                    fn = getattr(l, name)
+                    fn.argtypes = argtypes
+                    fn.restype = C.c_char_p if name == "acn_last_error" else c_int
+                    setattr(ns, name, fn)
+                _dlib = ns
+    return _dlib
+
+
+def debug_ctx(device: torch.device) -> c_p:
+    """Per-device context of the debug library (its own: the two libraries share no state)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    h = _dctx.get(idx)
+    if h is None:
+        out = c_p()
+        debug_check(debug_lib().acn_create(idx, C.byref(out)))
+        _dctx[idx] = h = out
+    return h
+
+
+def debug_check(rc: int) -> None:
+    if rc != 0:
+        msg = debug_lib().acn_last_error()
+        raise RuntimeError(f"libacn_b200_debug error {rc}: {msg.decode() if msg else '?'}")
 
 
 def check(rc: int) -> None:

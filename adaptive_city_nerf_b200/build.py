@@ -1,4 +1,8 @@
-"""In-tree nvcc build of libacn_b200.so (sm_100a only).  Used by __graft_entry__.build()."""
+"""In-tree nvcc build (sm_100a only) of
+    libacn_b200.so        the product: every kernel on the hot path + the C ABI of include/acn_b200.h
+    libacn_b200_debug.so  a superset build (-DACN_DEBUG_BUILD) + csrc/debug/: tcgen05 probes, kernel timelines, the L2
+                          gather / atomic peak micro-benchmarks (include/acn_b200_debug.h); tools/ and self-tests only
+Used by __graft_entry__.build()."""
 from __future__ import annotations
 
 import os
@@ -9,11 +13,12 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libacn_b200.so"
+LIB_DEBUG = PKG / "libacn_b200_debug.so"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-    "-Xptxas", "-v",
+    "-Xptxas", "-v", "-I", str(CSRC),
 ]
 
 
@@ -21,11 +26,15 @@ def sources():
     return sorted(CSRC.glob("*.cu"))
 
 
+def debug_sources():
+    return sorted((CSRC / "debug").glob("*.cu"))
+
+
 def needs_build() -> bool:
-    if not LIB.exists():
+    if not LIB.exists() or not LIB_DEBUG.exists():
         return True
-    t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "acn_b200.h"]
+    t = min(LIB.stat().st_mtime, LIB_DEBUG.stat().st_mtime)
+    deps = list(CSRC.rglob("*.cu")) + list(CSRC.rglob("*.cuh")) + list((PKG.parent / "include").glob("*.h"))
     return any(d.stat().st_mtime > t for d in deps)
 
 
@@ -34,28 +43,33 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = PKG / "build"
-    objdir.mkdir(exist_ok=True)
-    objs = []
-    procs = []
+    (objdir / "debug").mkdir(parents=True, exist_ok=True)
+    jobs = []       # (tag, source, object, extra flags)
     for src in sources():
-        obj = objdir / (src.stem + ".o")
-        objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    log = []
+        jobs.append(("product", src, objdir / (src.stem + ".o"), []))
+        jobs.append(("debug", src, objdir / "debug" / (src.stem + ".o"), ["-DACN_DEBUG_BUILD"]))
+    for src in debug_sources():
+        jobs.append(("debug", src, objdir / "debug" / (src.stem + ".o"), ["-DACN_DEBUG_BUILD"]))
+    procs = []
+    for tag, src, obj, extra in jobs:
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
+        procs.append((tag, src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = {"product": [], "debug": []}
     failed = False
-    for src, p in procs:
+    for tag, src, p in procs:
         out, _ = p.communicate()
-        log.append(f"== {src.name}\n{out}")
+        log[tag].append(f"== {src.name}\n{out}")
         failed |= p.returncode != 0
-    (objdir / "nvcc.log").write_text("\n".join(log))
+    (objdir / "nvcc.log").write_text("\n".join(log["product"]))
+    (objdir / "nvcc_debug.log").write_text("\n".join(log["debug"]))
     if failed or verbose:
-        print("\n".join(log), file=sys.stderr if failed else sys.stdout)
+        print("\n".join(log["product"] + log["debug"]), file=sys.stderr if failed else sys.stdout)
     if failed:
         raise RuntimeError("nvcc failed; see adaptive_city_nerf_b200/build/nvcc.log")
-    link = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
-            "-Xcompiler", "-fPIC"]
-    subprocess.run(link, check=True)
+    for lib, tag in ((LIB, "product"), (LIB_DEBUG, "debug")):
+        objs = [str(o) for t, _, o, _ in jobs if t == tag]
+        subprocess.run([nvcc, "-shared", "-o", str(lib), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-Xcompiler", "-fPIC"], check=True)
     return LIB
 
 

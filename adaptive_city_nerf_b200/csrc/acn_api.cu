@@ -58,14 +58,14 @@ extern "C" int acn_create(int device, acn_ctx** out) {
 }
 
 extern "C" int acn_destroy(acn_ctx* ctx) {
-    ACN_CHECK_CTX(ctx);
+    ACN_REQUIRE(ctx != nullptr, ACN_EINVAL, "acn_destroy: null context");
     if (ctx->scratch) cudaFree(ctx->scratch);
     delete ctx;
     return ACN_OK;
 }
 
 extern "C" int acn_device_info(acn_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes) {
-    ACN_CHECK_CTX(ctx);
+    ACN_REQUIRE(ctx != nullptr, ACN_EINVAL, "acn_device_info: null context");
     if (sm_count) *sm_count = ctx->sm_count;
     if (cc_major) *cc_major = ctx->cc_major;
     if (cc_minor) *cc_minor = ctx->cc_minor;

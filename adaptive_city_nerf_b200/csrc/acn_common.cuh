@@ -32,7 +32,15 @@ void acn_set_error(const char* fmt, ...);
         }                                            \
     } while (0)
 
-#define ACN_CHECK_CTX(ctx) ACN_REQUIRE((ctx) != nullptr, ACN_EINVAL, "%s: null context", __func__)
+// A context belongs to one device; a call made while another device is current would launch on a stream of that other
+// device.  Refuse it instead (the Python shim switches devices before it calls).
+#define ACN_CHECK_CTX(ctx)                                                                                              \
+    do {                                                                                                                \
+        ACN_REQUIRE((ctx) != nullptr, ACN_EINVAL, "%s: null context", __func__);                                        \
+        int cur__ = -1;                                                                                                 \
+        ACN_REQUIRE(cudaGetDevice(&cur__) == cudaSuccess && cur__ == (ctx)->device, ACN_EINVAL,                         \
+                    "%s: the context belongs to device %d but device %d is current", __func__, (ctx)->device, cur__);   \
+    } while (0)
 
 // Launch-error check without a device sync (SURVEY 8b "Error convention").
 #define ACN_CHECK_LAUNCH()                                                         \

@@ -4,6 +4,7 @@
 #include "field_common.cuh"
 #include "field_internal.cuh"
 #include "umma.cuh"
+#include "../../../include/acn_b200_debug.h"
 
 namespace {
 

@@ -3,6 +3,7 @@
 // mixed fp16/bf16 operands and the M = 64 accumulator layout.  Not on any product path.
 #include "acn_common.cuh"
 #include "umma.cuh"
+#include "../../../include/acn_b200_debug.h"
 
 namespace {
 

@@ -37,7 +37,11 @@
 // (m >> 4) * 32 + (m & 15); a TMEM A operand holds row r in lane r, two consecutive K elements per 32-bit column.
 #include "field_common.cuh"
 #include "field_internal.cuh"
+#include "hashgrid.cuh"
 #include "umma.cuh"
+#ifdef ACN_DEBUG_BUILD
+#include "../../include/acn_b200_debug.h"
+#endif
 
 namespace {
 
@@ -485,7 +489,20 @@ template <int E> struct BwdMap {
     static constexpr uint32_t w = BNS * SlotMap<E>::bytes;
     static constexpr uint32_t bars = (w + wmap(E).end + 127u) & ~127u;     // per slot: done_d, done_w
     static constexpr uint32_t tmem_ptr = bars + BNS * 2 * 8u;
-    static constexpr uint32_t bytes = tmem_ptr + 16u;
+    static constexpr uint32_t res = tmem_ptr + 16u;                         // fused scatter: float resolution per level (16)
+    static constexpr uint32_t bytes = res + 64u;
+};
+
+// Fused table scatter (acn_render_expert_bwd): instead of storing d_enc, the thread that holds 16 columns (8 levels) of
+// a point's encoding gradient forms the point's cell at each of those levels and adds w_corner * g to the 8 corner rows
+// of the table gradient -- models/encodings.py:331-381 differentiated w.r.t. the table, the same arithmetic as
+// k_hashgrid_bwd.  The 2 GiB (P,E) fp32 d_enc round trip through HBM disappears and the REDs (bound by the per-SM
+// atomic issue rate, not by anything the MMAs use) overlap the tensor-core work of the tiles in flight.
+struct ScatterArgs {
+    const float* x; int xs;                           // explicit positions (P,>=3), or
+    const float* rays; const float* t; int S;         // rays (N,8) + t (N,S): p = o + d*t (nerfs/ray_rendering.py:317)
+    const float* box6;                                // [min, extent] (world -> unit) or null
+    float* dtable; int L; int log2T; const int32_t* res; int interp;
 };
 
 // power-of-two loss scale from max |dL/dy|: max * scale in [2^9, 2^10)
@@ -531,11 +548,11 @@ __device__ __forceinline__ void epi_mask32_store(const Tile& act, int row, int c
     for (int q = 0; q < 4; ++q) sts128(chunk_addr(act, row, col0 / 8 + q), o[q]);
 }
 
-template <int E, bool TRACE>
+template <int E, bool TRACE, bool SCAT>
 __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     const __half* __restrict__ enc, const float* __restrict__ dirs, int dstride, int dgroup, int64_t P, int G,
     acn_field_weights w, const float4* __restrict__ d_rgb_sigma, const unsigned int* __restrict__ absmax_bits,
-    acn_field_grads g, float* __restrict__ d_enc, long long* __restrict__ trace)
+    acn_field_grads g, float* __restrict__ d_enc, long long* __restrict__ trace, ScatterArgs sc)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     using M = BwdMap<E>;
@@ -556,6 +573,7 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
         for (int i = 0; i < BNS * 2; ++i) umma::mbar_init_a(sb + M::bars + 8 * i, 1);
         umma::fence_mbar_init();
     }
+    if constexpr (SCAT) { if (tid < 16) umma::sts_f32(sb + M::res + 4u * tid, tid < sc.L ? (float)__ldg(sc.res + tid) : 1.0f); }
     if (warp == 0) umma::tmem_alloc(reinterpret_cast<uint32_t*>(smem_raw + M::tmem_ptr), BWD_TMEM_COLS);
     umma::fence_async_smem();
     umma::fence_before_sync();
@@ -593,7 +611,7 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     const int64_t tile_stride = (int64_t)gridDim.x * BNS;
     const float scale = grad_scale_from_max(__uint_as_float(__ldg(absmax_bits)));
     const float inv_scale = 1.0f / scale;
-    const bool want_denc = d_enc != nullptr;
+    const bool want_denc = SCAT || d_enc != nullptr;
 
     // Two warps of the slot issue: the chain issuer launches the MMAs the next epilogue waits for (forward layers, dgrad)
     // and commits them to done_d; a second warp, on another SM sub-partition, launches the weight-gradient MMAs of the
@@ -724,10 +742,57 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
         group_sync(bar_id, 256); issue(9);
         wait_done(done_d, ph_d); epi_mask32_load(tmem_d, col0, Th2, row, o); wait_done(done_w, ph_w); epi_mask32_store(Th2, row, col0, o);
         group_sync(bar_id, 256); issue(10);
+        float upos[3] = { 0.f, 0.f, 0.f };
+        if constexpr (SCAT) {   // the point's unit-cube position for the table scatter: in flight while the last two layers run
+            if (on) {
+                if (sc.rays) {
+                    const int64_t ray = p / sc.S;
+                    const float* ry = sc.rays + 8 * ray;
+                    const float tv = __ldg(sc.t + p);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) upos[c] = __fadd_rn(__ldg(ry + c), __fmul_rn(__ldg(ry + 3 + c), tv));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) upos[c] = __ldg(sc.x + p * sc.xs + c);
+                }
+                if (sc.box6) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) upos[c] = world_to_unit1(upos[c], __ldg(sc.box6 + c), __ldg(sc.box6 + 3 + c));
+                }
+            }
+        }
         wait_done(done_d, ph_d); epi_mask32_load(tmem_d, col0, Th1, row, o); wait_done(done_w, ph_w); epi_mask32_store(Th1, row, col0, o);
         group_sync(bar_id, 256); issue(11);
         wait_done(done_d, ph_d);
-        if (want_denc) {   // 16-column groups of d_enc alternate between the row's two threads
+        if constexpr (SCAT) {   // d_enc never leaves the SM: 8 levels of this point per thread, straight into the table gradient
+            const uint32_t hmask = (1u << sc.log2T) - 1u;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c0 = 16 * (2 * j + hcol);
+                if (c0 < E) {
+                    float v[16];
+                    umma::ld16(tmem_d + c0, v);
+                    umma::wait_ld();
+                    if (on) {
+#pragma unroll
+                        for (int lv = 0; lv < 8; ++lv) {
+                            const float gx = v[2 * lv] * inv_scale, gy = v[2 * lv + 1] * inv_scale;
+                            if (gx == 0.0f && gy == 0.0f) continue;      // fully occluded samples scatter nothing
+                            const int l = c0 / 2 + lv;
+                            const GridCell c = grid_cell(upos[0], upos[1], upos[2], umma::lds_f32(sb + M::res + 4u * l), sc.interp);
+                            const float wx[2] = { 1.0f - c.wx, c.wx }, wy[2] = { 1.0f - c.wy, c.wy }, wz[2] = { 1.0f - c.wz, c.wz };
+                            float2 acc[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const float wk = wz[k & 1] * wy[(k >> 1) & 1] * wx[(k >> 2) & 1];
+                                acc[k] = make_float2(gx * wk, gy * wk);
+                            }
+                            scatter_cell_f2(reinterpret_cast<float2*>(sc.dtable) + ((size_t)l << sc.log2T), c.x0, c.y0, c.z0, hmask, acc);
+                        }
+                    }
+                }
+            }
+        } else if (want_denc) {   // 16-column groups of d_enc alternate between the row's two threads
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int c0 = 16 * (2 * j + hcol);
@@ -825,7 +890,13 @@ int check_dims(const char* fn, int enc_dtype, int E, int H, int G, int C, const 
     return ACN_OK;
 }
 
-long long* g_field_trace = nullptr;   // set by acn_debug_field_trace for the following forward launches
+#ifdef ACN_DEBUG_BUILD
+long long* g_field_trace = nullptr;   // libacn_b200_debug.so only: set by acn_debug_field_trace for the following launches
+constexpr bool kTraceBuild = true;
+#else
+constexpr long long* g_field_trace = nullptr;   // the product library has no timeline build of the kernels
+constexpr bool kTraceBuild = false;
+#endif
 
 template <int E>
 int launch_fwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride, int dirs_group, int64_t P, int G,
@@ -835,9 +906,9 @@ int launch_fwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride
     const int64_t ntiles = (P + TM - 1) / TM;
     int64_t grid = (ntiles + FWG - 1) / FWG;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
-    if (g_field_trace && E == 32) {          // the timeline build of the kernel (tools/field_trace.py)
-        ACN_CUDA(cudaFuncSetAttribute(k_field_fwd_mma<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_field_fwd_mma<32, true><<<(int)grid, FWG * 128, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
+    if (kTraceBuild && g_field_trace && E == 32) {          // the timeline build of the kernel (tools/field_trace.py)
+        ACN_CUDA(cudaFuncSetAttribute(k_field_fwd_mma<32, kTraceBuild>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_field_fwd_mma<32, kTraceBuild><<<(int)grid, FWG * 128, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
                                                                        (float4*)rgb_sigma, g_field_trace);
     } else {
         ACN_CUDA(cudaFuncSetAttribute(k_field_fwd_mma<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -851,32 +922,55 @@ int launch_fwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride
 template <int E>
 int launch_bwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride, int dirs_group, int64_t P, int G,
                const acn_field_weights* w, const float* d_rgb_sigma, const unsigned int* absmax, const acn_field_grads* g,
-               float* d_enc, cudaStream_t st) {
+               float* d_enc, const ScatterArgs* sc, cudaStream_t st) {
     constexpr uint32_t smem = BwdMap<E>::bytes;
     ACN_REQUIRE((int)smem <= ctx->max_smem_optin, ACN_EUNSUPPORTED, "acn_field_bwd(f16): needs %u B shared memory", smem);
     const int64_t ntiles = (P + TM - 1) / TM;
     int64_t grid = (ntiles + BNS - 1) / BNS;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
-    if (g_field_trace && E == 32) {          // the timeline build of the kernel (tools/field_trace.py --bwd)
-        ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_field_bwd_mma<32, true><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
-                                                                       (const float4*)d_rgb_sigma, absmax, *g, d_enc, g_field_trace);
+    const ScatterArgs none{};
+    if (sc) {
+        if constexpr (E <= 32) {             // the fused table scatter: E = 2 L, L <= 16
+            ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<E, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_field_bwd_mma<E, false, true><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
+                                                                                 (const float4*)d_rgb_sigma, absmax, *g, nullptr, nullptr, *sc);
+        } else {
+            ACN_REQUIRE(false, ACN_EUNSUPPORTED, "acn_render_expert_bwd: encoding width %d > 32", E);
+        }
+    } else if (kTraceBuild && g_field_trace && E == 32) {          // the timeline build of the kernel (tools/field_trace.py --bwd)
+        ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<32, kTraceBuild, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_field_bwd_mma<32, kTraceBuild, false><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
+                                                                              (const float4*)d_rgb_sigma, absmax, *g, d_enc, g_field_trace, none);
     } else {
-        ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_field_bwd_mma<E, false><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
-                                                                       (const float4*)d_rgb_sigma, absmax, *g, d_enc, nullptr);
+        ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<E, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_field_bwd_mma<E, false, false><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
+                                                                              (const float4*)d_rgb_sigma, absmax, *g, d_enc, nullptr, none);
     }
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }
 
+// loss scale: max |dL/dy| over the batch -> one word of context scratch (a ring, so calls in flight on different
+// streams do not share a word)
+int absmax_word(acn_ctx* ctx, const char* fn, const float* d_rgb_sigma, int64_t P, cudaStream_t st, unsigned int** out) {
+    unsigned int* slot = acn_scratch_word(ctx);
+    ACN_REQUIRE(slot != nullptr, ACN_ECUDA, "%s(f16): no context scratch", fn);
+    ACN_CUDA(cudaMemsetAsync(slot, 0, sizeof(unsigned int), st));
+    k_absmax<<<acn_grid_1d(P, 256 * 8, (int64_t)ctx->sm_count * 8), 256, 0, st>>>((const float4*)d_rgb_sigma, P, slot);
+    ACN_CHECK_LAUNCH();
+    *out = slot;
+    return ACN_OK;
+}
+
 }  // namespace
 
+#ifdef ACN_DEBUG_BUILD
 extern "C" int acn_debug_field_trace(acn_ctx* ctx, long long* trace_or_null) {
     ACN_CHECK_CTX(ctx);
     g_field_trace = trace_or_null;
     return ACN_OK;
 }
+#endif
 
 int acn_field_fwd_tc(acn_ctx* ctx, const void* enc, int enc_dtype, const float* dirs, int dirs_stride, int dirs_group,
                      int64_t P, int E, int H, int G, int C, const acn_field_weights* w, float* rgb_sigma, cudaStream_t st) {
@@ -896,17 +990,47 @@ int acn_field_bwd_tc(acn_ctx* ctx, const void* enc, int enc_dtype, const float* 
     int rc = check_dims("acn_field_bwd", enc_dtype, E, H, G, C, enc);
     if (rc) return rc;
     ACN_REQUIRE(((uintptr_t)d_enc & 15) == 0, ACN_EINVAL, "acn_field_bwd(f16): d_enc must be 16-byte aligned");
-    // loss scale: max |dL/dy| over the batch -> one word of context scratch (a ring, so calls in flight on
-    // different streams do not share a word)
-    unsigned int* slot = acn_scratch_word(ctx);
-    ACN_REQUIRE(slot != nullptr, ACN_ECUDA, "acn_field_bwd(f16): no context scratch");
-    ACN_CUDA(cudaMemsetAsync(slot, 0, sizeof(unsigned int), st));
-    k_absmax<<<acn_grid_1d(P, 256 * 8, (int64_t)ctx->sm_count * 8), 256, 0, st>>>((const float4*)d_rgb_sigma, P, slot);
-    ACN_CHECK_LAUNCH();
+    unsigned int* slot = nullptr;
+    rc = absmax_word(ctx, "acn_field_bwd", d_rgb_sigma, P, st, &slot);
+    if (rc) return rc;
     switch (E) {
-        case 16: return launch_bwd<16>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, st);
-        case 32: return launch_bwd<32>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, st);
-        case 48: return launch_bwd<48>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, st);
-        default: return launch_bwd<64>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, st);
+        case 16: return launch_bwd<16>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, nullptr, st);
+        case 32: return launch_bwd<32>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, nullptr, st);
+        case 48: return launch_bwd<48>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, nullptr, st);
+        default: return launch_bwd<64>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, nullptr, st);
     }
+}
+
+// Fully fused backward of one expert on a batch of points (SURVEY 8b acn_render_expert_bwd): fused MLP backward +
+// hash-table gradient scatter in ONE kernel; d_enc never exists in HBM.
+extern "C" int acn_render_expert_bwd(acn_ctx* ctx, const float* x_or_null, int x_stride, const float* rays8_or_null,
+                                     const float* t_vals_or_null, int64_t P, int S, const float* box6_or_null, int L, int F,
+                                     int log2T, const int32_t* res, int interp, const void* enc_f16, const float* dirs,
+                                     int dirs_stride, int dirs_group, int H, int G, int C, const acn_field_weights* w,
+                                     const float* d_rgb_sigma, const acn_field_grads* g, float* dtable, acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    const char* fn = "acn_render_expert_bwd";
+    ACN_REQUIRE(P >= 0, ACN_EINVAL, "%s: negative P", fn);
+    ACN_REQUIRE(F == 2 && (L == 8 || L == 16), ACN_EUNSUPPORTED, "%s: built for F = 2 and 8 or 16 levels (got L=%d, F=%d)", fn, L, F);
+    ACN_REQUIRE(log2T >= 1 && log2T <= 24 && res, ACN_EINVAL, "%s: bad table size / res table", fn);
+    ACN_REQUIRE(interp == ACN_INTERP_LINEAR || interp == ACN_INTERP_SMOOTHSTEP, ACN_EUNSUPPORTED, "%s: interpolation must be Linear or Smoothstep", fn);
+    ACN_REQUIRE(w && g, ACN_EINVAL, "%s: null weights / grads", fn);
+    for (int i = 0; i < 14; ++i) ACN_REQUIRE(w->p[i] != nullptr, ACN_EINVAL, "%s: weight pointer %d is null", fn, i);
+    ACN_REQUIRE(dirs_stride >= 3 && dirs_group >= 1, ACN_EINVAL, "%s: bad dirs stride/group", fn);
+    if (P == 0) return ACN_OK;
+    const bool from_rays = rays8_or_null != nullptr;
+    ACN_REQUIRE(from_rays ? (t_vals_or_null && S >= 1 && P % S == 0) : (x_or_null && x_stride >= 3), ACN_EINVAL,
+                "%s: give either x (P,>=3) or rays8 + t_vals with P = N*S", fn);
+    ACN_REQUIRE(enc_f16 && dirs && d_rgb_sigma && dtable, ACN_EINVAL, "%s: null buffer", fn);
+    ACN_REQUIRE((((uintptr_t)d_rgb_sigma | (uintptr_t)dtable) & 15) == 0, ACN_EINVAL, "%s: d_rgb_sigma / dtable misaligned", fn);
+    const int E = L * F;
+    int rc = check_dims(fn, ACN_F16, E, H, G, C, enc_f16);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int* slot = nullptr;
+    rc = absmax_word(ctx, fn, d_rgb_sigma, P, st, &slot);
+    if (rc) return rc;
+    const ScatterArgs sc{ from_rays ? nullptr : x_or_null, x_stride, rays8_or_null, t_vals_or_null, S, box6_or_null, dtable, L, log2T, res, interp };
+    if (E == 16) return launch_bwd<16>(ctx, enc_f16, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, nullptr, &sc, st);
+    return launch_bwd<32>(ctx, enc_f16, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, nullptr, &sc, st);
 }

@@ -157,33 +157,6 @@ __device__ __forceinline__ void scatter_add(float* __restrict__ t, uint32_t row,
     }
 }
 
-// The 8 corner updates of one cell for F = 2, x-neighbours paired into one 16-byte RED when x0 is even
-// (the hash is x ^ (y*p1) ^ (z*p2), so for even x0 the x-neighbours are rows r and r^1: one aligned pair).  The
-// scatter is bound by scattered-RED issue per SM (~1.3 cycles per lane); this took it from 11.5 to 8.7 ms.
-// acc is indexed c = (x<<2)|(y<<1)|z.
-__device__ __forceinline__ void scatter_cell_f2(float2* __restrict__ lt, uint32_t x0, uint32_t y0, uint32_t z0, uint32_t mask,
-                                                const float2* acc) {
-    const uint32_t yp0 = y0 * 2654435761u, yp1 = yp0 + 2654435761u;
-    const uint32_t zp0 = z0 * 805459861u, zp1 = zp0 + 805459861u;
-    const bool xeven = !(x0 & 1u);
-#pragma unroll
-    for (int yz = 0; yz < 4; ++yz) {
-        const uint32_t h = ((yz & 2) ? yp1 : yp0) ^ ((yz & 1) ? zp1 : zp0);
-        const uint32_t r0 = (x0 ^ h) & mask;
-        const float2 a = acc[yz], b = acc[4 + yz];
-        const bool za = a.x == 0.0f && a.y == 0.0f, zb = b.x == 0.0f && b.y == 0.0f;
-        if (xeven) {
-            if (!(za && zb)) {
-                const float4 v = (r0 & 1u) ? make_float4(b.x, b.y, a.x, a.y) : make_float4(a.x, a.y, b.x, b.y);
-                atomicAdd(reinterpret_cast<float4*>(lt) + (r0 >> 1), v);
-            }
-        } else {
-            if (!za) atomicAdd(lt + r0, a);
-            if (!zb) atomicAdd(lt + (((x0 + 1u) ^ h) & mask), b);
-        }
-    }
-}
-
 template <typename T> __device__ __forceinline__ float from_in(T v);
 template <> __device__ __forceinline__ float from_in<float>(float v) { return v; }
 template <> __device__ __forceinline__ float from_in<__half>(__half v) { return __half2float(v); }
@@ -384,8 +357,6 @@ __global__ void __launch_bounds__(256) k_hashgrid_bwd_march_pts(
     if (have) scatter_cell_f2(lt, cx, cy, cz, mask, acc);
 }
 
-static int g_force_generic_scatter = 0;   // acn_debug_generic_scatter: tests cross-check the march kernels against the plain one
-
 // ------------------------------------------------------------------------------------------ C ABI
 static int check_grid_args(const char* fn, int64_t P, int xs, int L, int F, int log2T, const void* res, int interp) {
     ACN_REQUIRE(P >= 0 && xs >= 3, ACN_EINVAL, "%s: bad P / x_stride", fn);
@@ -432,7 +403,7 @@ static int hashgrid_fwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P
 
 static int hashgrid_bwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P, const float* box6_or_null, int L,
                              int F, int log2T, const int32_t* res, int interp, const void* dout, int dout_dtype,
-                             float* dtable, acn_stream stream) {
+                             float* dtable, acn_stream stream, bool plain = false) {
     ACN_CHECK_CTX(ctx);
     int rc = check_grid_args(fn, P, pos.rays ? 3 : pos.xs, L, F, log2T, res, interp);
     if (rc) return rc;
@@ -441,7 +412,7 @@ static int hashgrid_bwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P
     ACN_REQUIRE((pos.x || (pos.rays && pos.t && pos.S >= 1)) && dout && dtable, ACN_EINVAL, "%s: null buffer", fn);
     ACN_REQUIRE(((uintptr_t)dtable & 15) == 0, ACN_EINVAL, "%s: misaligned dtable", fn);
     cudaStream_t st = (cudaStream_t)stream;
-    if (pos.x && F == 2 && L <= 16 && interp != ACN_INTERP_NEAREST && !g_force_generic_scatter) {
+    if (pos.x && F == 2 && L <= 16 && interp != ACN_INTERP_NEAREST && !plain) {
         ACN_REQUIRE(((uintptr_t)dout & 7) == 0, ACN_EINVAL, "%s: misaligned dout", fn);
         const int seg = 64;
         const int grid_m = acn_grid_1d(((P + seg - 1) / seg) * 16, 256);
@@ -520,7 +491,10 @@ extern "C" int acn_hashgrid_bwd_rays(acn_ctx* ctx, const float* rays8, const flo
                              dtable, stream);
 }
 
-extern "C" int acn_debug_generic_scatter(int on) {
-    g_force_generic_scatter = on ? 1 : 0;
-    return ACN_OK;
+extern "C" int acn_hashgrid_bwd_plain(acn_ctx* ctx, const float* x, int64_t P, int x_stride, const float* box6_or_null, int L,
+                                      int F, int log2T, const int32_t* res, int interp, const void* dout, int dout_dtype,
+                                      float* dtable, acn_stream stream) {
+    PosSrc pos{ x, x_stride, nullptr, nullptr, 0, 0, nullptr };
+    return hashgrid_bwd_impl(ctx, "acn_hashgrid_bwd_plain", pos, P, box6_or_null, L, F, log2T, res, interp, dout, dout_dtype, dtable,
+                             stream, true);
 }

@@ -270,6 +270,34 @@ def field_bwd(enc: Tensor, dirs: Tensor, dirs_stride: int, dirs_group: int, ws: 
     return grads, d_enc
 
 
+def render_expert_bwd(enc: Tensor, pos: Sequence[Tensor], dirs: Tensor, dirs_stride: int, dirs_group: int, ws: Sequence[Tensor],
+                      d_rgb_sigma: Tensor, need: Sequence[bool], spec: "GridSpec", box6: Optional[Tensor], dtable: Tensor):
+    """Fused MLP backward + table scatter (acn_render_expert_bwd): -> the 14 weight gradients; dtable is accumulated into."""
+    P = enc.shape[0]
+    E, H, G, C = _field_dims(ws)
+    dev = enc.device
+    flat = torch.zeros(sum(w.numel() for w, n in zip(ws, need) if n), dtype=torch.float32, device=dev)
+    grads: List[Optional[Tensor]] = []
+    off = 0
+    for w, n in zip(ws, need):
+        grads.append(flat[off:off + w.numel()].view(w.shape) if n else None)
+        off += w.numel() if n else 0
+    wst, gst = pack_weights(ws), pack_weights(grads)
+    if len(pos) == 2:
+        rays, t = pos
+        x, xs, S = None, 3, t.shape[1]
+    else:
+        x, xs, rays, t, S = pos[0], pos[0].stride(0), None, None, 1
+    check(lib().acn_render_expert_bwd(ctx(dev), ptr(x), xs, ptr(rays), ptr(t), P, S, ptr(box6), spec.L, spec.F, spec.log2T,
+                                      ptr(_grid_res(spec, dev)), spec.interp, ptr(enc), ptr(dirs), dirs_stride, dirs_group,
+                                      H, G, C, C_.byref(wst), ptr(d_rgb_sigma), C_.byref(gst), ptr(dtable), stream(dev)))
+    return grads
+
+
+#: set False to run the two-kernel backward (MLP backward -> d_enc in HBM -> scatter); tests cross-check the two
+FUSED_EXPERT_BWD = True
+
+
 class ExpertFieldFn(torch.autograd.Function):
     """One expert on a batch of points: world->unit, hash encode, density trunk + heads, SH,
     colour MLP, activations (models/inr/meta_ngp.py:226-241) -> (P,4) [rgb, sigma].
@@ -316,6 +344,11 @@ class ExpertFieldFn(torch.autograd.Function):
         need_w = ctx_.needs_input_grad[9:]
         dirs = pos[0][:, 3:]
         g = g.contiguous().float()
+        if (FUSED_EXPERT_BWD and need_table and half and spec.F == 2 and spec.L in (8, 16) and spec.interp != 0
+                and enc.dtype == torch.float16):
+            dtable = torch.zeros(tshape, dtype=torch.float32, device=g.device)
+            grads = render_expert_bwd(enc, pos, dirs, dstride, dgroup, ws, g, need_w, spec, box6, dtable)
+            return (None, None, None, dtable, None, None, None, None, None, *grads)
         grads, d_enc = field_bwd(enc, dirs, dstride, dgroup, ws, half, g, need_table, need_w)
         dtable = None
         if need_table:
@@ -552,41 +585,74 @@ class BlendFn(torch.autograd.Function):
         return g, d_y, None, None
 
 
-# ------------------------------------------------------------------------------------------ diagnostics
-def debug_generic_scatter(on: bool) -> None:
-    """Cross-check switch: acn_hashgrid_bwd falls back to the plain per-(point, level) scatter while on."""
-    check(lib().acn_debug_generic_scatter(int(bool(on))))
+# ------------------------------------------------------------------------------------------ cross-checks and probes
+def hashgrid_bwd_plain(x: Tensor, dout: Tensor, spec: GridSpec, box6: Optional[Tensor], dtable: Tensor) -> None:
+    """acn_hashgrid_bwd_plain: the per-(point, level) scatter, whatever the configuration (the run-length kernels'
+    cross-check)."""
+    if x.dtype != torch.float32 or x.stride(1) != 1:
+        x = x.float().contiguous()
+    dout = dout.contiguous()
+    P, dev = x.shape[0], x.device
+    check(lib().acn_hashgrid_bwd_plain(ctx(dev), ptr(x), P, x.stride(0) if P else 3, ptr(box6), spec.L, spec.F, spec.log2T,
+                                       ptr(_grid_res(spec, dev)), spec.interp, ptr(dout), _dt(dout), ptr(dtable), stream(dev)))
+
+
+# The functions below drive libacn_b200_debug.so (include/acn_b200_debug.h), not the product library.
+def _dbg():
+    return _lib.debug_lib(), _lib.debug_check, _lib.debug_ctx
 
 
 def debug_umma_gemm(a: Tensor, w: Tensor) -> Tensor:
     """D = A @ W^T on one tcgen05 tile: A (128,K) fp16, W (N,K) fp16 -> (128,N) fp32."""
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.shape[0] == 128
+    l, chk, dctx = _dbg()
     a, w = a.contiguous(), w.contiguous()
     d = torch.empty(128, w.shape[0], dtype=torch.float32, device=a.device)
-    check(lib().acn_debug_umma_gemm(ctx(a.device), ptr(a), ptr(w), w.shape[0], a.shape[1], ptr(d), stream(a.device)))
+    chk(l.acn_debug_umma_gemm(dctx(a.device), ptr(a), ptr(w), w.shape[0], a.shape[1], ptr(d), stream(a.device)))
     return d
 
 
 def debug_umma_gemm_ts(a: Tensor, w: Tensor) -> Tensor:
     """D = A @ W^T with A staged in tensor memory (tcgen05.st) and read by the MMA from there."""
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.shape[0] == 128
+    l, chk, dctx = _dbg()
     a, w = a.contiguous(), w.contiguous()
     d = torch.empty(128, w.shape[0], dtype=torch.float32, device=a.device)
-    check(lib().acn_debug_umma_gemm_ts(ctx(a.device), ptr(a), ptr(w), w.shape[0], a.shape[1], ptr(d), stream(a.device)))
+    chk(l.acn_debug_umma_gemm_ts(dctx(a.device), ptr(a), ptr(w), w.shape[0], a.shape[1], ptr(d), stream(a.device)))
     return d
 
 
 def debug_umma_rate(mode: int, M: int, N: int, nmma: int, reps: int = 200, issuers: int = 1) -> List[int]:
     """Average SM cycles for `nmma` back-to-back tcgen05.mma + commit + wait, per issuing thread (acn_debug_umma_rate)."""
+    l, chk, dctx = _dbg()
     dev = torch.device("cuda", torch.cuda.current_device())
     out = torch.zeros(4, dtype=torch.int64, device=dev)
-    check(lib().acn_debug_umma_rate(ctx(dev), mode, M, N, nmma, reps, issuers, ptr(out), stream(dev)))
+    chk(l.acn_debug_umma_rate(dctx(dev), mode, M, N, nmma, reps, issuers, ptr(out), stream(dev)))
     return out.cpu().tolist()[:issuers]
 
 
+def debug_l2_probe(mode: int, bytes_per_access: int, buf: Tensor, iters: int, grid: int) -> int:
+    """One launch of the L2 gather (mode 0) / RED (mode 1) micro-benchmark -> accesses issued (acn_debug_l2_probe)."""
+    l, chk, dctx = _dbg()
+    dev = buf.device
+    sink = torch.zeros(4, dtype=torch.float32, device=dev)
+    chk(l.acn_debug_l2_probe(dctx(dev), mode, bytes_per_access, ptr(buf), buf.numel() * buf.element_size(), iters, grid,
+                             ptr(sink), stream(dev)))
+    return grid * 256 * iters * 8
+
+
 def debug_field_trace(buf: Optional[Tensor]) -> None:
-    """Arm (int64 CUDA tensor of 1024 words) or disarm (None) the forward-MLP timeline (acn_debug_field_trace)."""
+    """Arm (int64 CUDA tensor of 1024 words) or disarm (None) the MLP kernels' timeline in the DEBUG library; drive the
+    traced kernels with `use_debug_library()` active (tools/field_trace.py)."""
+    l, chk, dctx = _dbg()
     dev = buf.device if buf is not None else torch.device("cuda", torch.cuda.current_device())
     if buf is not None:
         assert buf.dtype == torch.int64 and buf.numel() >= 1024 and buf.is_contiguous()
-    check(lib().acn_debug_field_trace(ctx(dev), ptr(buf)))
+    chk(l.acn_debug_field_trace(dctx(dev), ptr(buf)))
+
+
+def use_debug_library() -> None:
+    """tools/ only: route every entry point of this module through libacn_b200_debug.so (same ABI, built with the kernel
+    timelines compiled in)."""
+    global lib, ctx, check
+    lib, ctx, check = _lib.debug_lib, _lib.debug_ctx, _lib.debug_check

@@ -23,7 +23,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define ACN_VERSION 108 /* major*100 + minor */
+#define ACN_VERSION 200 /* major*100 + minor */
 
 typedef struct acn_ctx acn_ctx;
 typedef void* acn_stream; /* cudaStream_t */
@@ -141,6 +141,19 @@ int acn_field_bwd(acn_ctx*, const void* enc, int enc_dtype, const float* dirs, i
                   int dirs_group, int64_t P, int E, int H, int G, int C,
                   const acn_field_weights* w, int precision, const float* d_rgb_sigma,
                   const acn_field_grads* g, void* d_enc_or_null, int d_enc_dtype, acn_stream);
+
+/* Fused per-expert backward for the `active_module` / routed-bucket render path (SURVEY 8b acn_render_expert_bwd;
+ * replaces autograd through nerfs/ray_rendering.py:317-325 -> models/inr/meta_ngp.py:226-241 ->
+ * models/encodings.py:331-381): the tcgen05 MLP backward of acn_field_bwd(ACN_F16) and the hash-table gradient scatter
+ * of acn_hashgrid_bwd in ONE kernel -- the (P, L*F) gradient of the encoding never exists in HBM.
+ * Positions: x_or_null (P,>=3) rows of stride x_stride, or rays8 (N,8) + t_vals (N,S) with P = N*S (p = o + d*t).
+ * enc_f16 (P, L*F): the fp16 encoding the forward saved.  F = 2, L in {8,16}, Linear / Smoothstep.  Weight gradients
+ * are accumulated into g, the table gradient into dtable (L*2^log2T, 2) fp32. */
+int acn_render_expert_bwd(acn_ctx*, const float* x_or_null, int x_stride, const float* rays8_or_null,
+                          const float* t_vals_or_null, int64_t P, int S, const float* box6_or_null, int L, int F,
+                          int log2T, const int32_t* res, int interp, const void* enc_f16, const float* dirs,
+                          int dirs_stride, int dirs_group, int H, int G, int C, const acn_field_weights* w,
+                          const float* d_rgb_sigma, const acn_field_grads* g, float* dtable, acn_stream);
 
 /* ---- stage 4: alpha compositing (nerfs/ray_rendering.py:114-165 volume_render) -------------- */
 int acn_composite_fwd(acn_ctx*, const float* rgb_sigma, const float* t_vals,
@@ -272,37 +285,11 @@ int acn_dda_route_rays(acn_ctx*, const float* rays8, int64_t N, const float* aab
                        const float* cell3, const float* cell_bounds, const float* tol, int max_steps,
                        int32_t* cid_out, float* best_len_or_null, int32_t* counts_or_null, acn_stream);
 
-/* ---- diagnostics ---------------------------------------------------------------------------- */
-/* on != 0: acn_hashgrid_bwd uses the plain per-(point, level) scatter instead of the run-length one (a cross-check). */
-int acn_debug_generic_scatter(int on);
-
-/* One tcgen05 tile GEMM  D(128,N) = A(128,K) * W(N,K)^T  (fp16 in, fp32 out); validates the
- * shared-memory / instruction descriptors the fused MLP kernels are built on.  N in
- * {16,32,64}, K in {16,32,64}. */
-int acn_debug_umma_gemm(acn_ctx*, const void* a_f16, const void* w_f16, int N, int K, float* d,
-                        acn_stream);
-
-/* Same product with A read from TENSOR MEMORY (written there by tcgen05.st): validates the TMEM operand layout of
- * the forward MLP kernel's activation chain. */
-int acn_debug_umma_gemm_ts(acn_ctx*, const void* a_f16, const void* w_f16, int N, int K, float* d, acn_stream);
-
-/* Dispatch-rate probe: `issuers` threads each issue `nmma` back-to-back M x N x 16 MMAs (mode 0: operands in shared
- * memory, 1: A in tensor memory), commit and wait, `reps` times, on every SM; out4[i] = average SM cycles per round of
- * issuer i on CTA 0 (tools/umma_rate.py). */
-int acn_debug_umma_rate(acn_ctx*, int mode, int M, int N, int nmma, int reps, int issuers, long long* out4, acn_stream);
-
-/* Raw harness: stages two 16-bit matrices as canonical tiles and issues `ksteps` MMAs with
- * host-supplied descriptors, then dumps TMEM lanes 0..127 x ncols.  Used by tools/umma_probe.py to
- * establish MN-major / mixed-dtype / M=64 layouts on hardware. */
-int acn_debug_umma_raw(acn_ctx*, const void* a16, int rows_a, int cols_a, const void* b16, int rows_b,
-                       int cols_b, uint32_t idesc, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step,
-                       uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, int ksteps, int ncols, float* out,
-                       acn_stream);
-
-/* Timeline of the fused forward MLP kernel: when `trace` (device, 1024 int64) is non-NULL, CTA 0 of the
- * following acn_field_fwd(ACN_F16) launches logs (SM clock << 8 | tag) pairs from row 0 of its first
- * warpgroup (tools/field_trace.py decodes them).  NULL switches it off. */
-int acn_debug_field_trace(acn_ctx*, long long* trace_or_null);
+/* Plain per-(point, level) table scatter (one thread per point and level, 8 corner REDs): what acn_hashgrid_bwd runs for
+ * F != 2 and "Nearest"; exported so tests can cross-check the run-length kernels against it on the same inputs. */
+int acn_hashgrid_bwd_plain(acn_ctx*, const float* x, int64_t P, int x_stride, const float* box6_or_null,
+                           int L, int F, int log2T, const int32_t* res, int interp, const void* dout,
+                           int dout_dtype, float* dtable, acn_stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

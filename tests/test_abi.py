@@ -35,11 +35,26 @@ def test_header_symbols_exported(built_lib):
     assert exported == header_symbols()
 
 
+def test_debug_library_is_separate_and_complete(built_lib):
+    """Probes and timelines live in libacn_b200_debug.so (include/acn_b200_debug.h): the product library exports no
+    acn_debug_* symbol, the debug library exports every prototype of both headers."""
+    from adaptive_city_nerf_b200 import _lib, build
+    nm = lambda lib: subprocess.run(["nm", "-D", "--defined-only", str(lib)], capture_output=True, text=True, check=True).stdout
+    prod = [l.split()[-1] for l in nm(built_lib).splitlines() if " T " in l]
+    assert not [s for s in prod if "debug" in s]
+    dbg = {l.split()[-1] for l in nm(build.LIB_DEBUG).splitlines() if " T " in l}
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "acn_b200_debug.h").read_text(), flags=re.S)
+    want = set(re.findall(r"\b(acn_debug_[a-z0-9_]+)\s*\(", text))
+    assert len(want) >= 6 and want <= dbg and set(header_symbols()) <= dbg
+    d = _lib.debug_lib()
+    assert d.acn_version() == 200
+
+
 def test_ctypes_table_matches_header(built_lib):
     from adaptive_city_nerf_b200 import _lib
     assert sorted(_lib.SIGNATURES) == header_symbols()
     l = _lib.lib()
-    assert l.acn_version() == 108
+    assert l.acn_version() == 200
     for name in _lib.SIGNATURES:
         assert getattr(l, name).argtypes == _lib.SIGNATURES[name]
     assert len(_lib.SIGNATURES["acn_hashgrid_fwd"]) == 15 and len(_lib.SIGNATURES["acn_field_bwd"]) == 18

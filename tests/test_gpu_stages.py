@@ -492,11 +492,7 @@ def test_hashgrid_bwd_march_vs_generic(ops):
         a = torch.zeros(16 << log2T, 2, device="cuda")
         b = torch.zeros_like(a)
         ops.hashgrid_bwd_rays(rays, t, dout, spec, box6, a)                       # march kernel (rays)
-        ops.debug_generic_scatter(True)
-        try:
-            ops.hashgrid_bwd(ops.points(rays, t), dout, spec, box6, b)            # plain per-(point, level) kernel
-        finally:
-            ops.debug_generic_scatter(False)
+        ops.hashgrid_bwd_plain(ops.points(rays, t), dout, spec, box6, b)          # plain per-(point, level) kernel
         scale = float(b.abs().max())
         assert float((a - b).abs().max()) <= 2e-5 * scale + 1e-6, (S, log2T, mode)
         # march kernel over a point list (the routed path): in order, shuffled (every row its own cell), fp16, short tail
@@ -509,11 +505,7 @@ def test_hashgrid_bwd_march_vs_generic(ops):
         c16 = torch.zeros_like(a)
         ops.hashgrid_bwd(pts[:-37], dout[:-37].half(), spec, box6, c16)
         d_ref = torch.zeros_like(a)
-        ops.debug_generic_scatter(True)
-        try:
-            ops.hashgrid_bwd(pts[:-37], dout[:-37], spec, box6, d_ref)
-        finally:
-            ops.debug_generic_scatter(False)
+        ops.hashgrid_bwd_plain(pts[:-37], dout[:-37], spec, box6, d_ref)
         assert float((c16 - d_ref).abs().max()) <= 2e-3 * scale
         # fp16 dL/denc input
         a16 = torch.zeros_like(a)

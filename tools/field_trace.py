@@ -7,6 +7,7 @@ sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests" / "golden")
 import synth
 from helpers import cu
 from adaptive_city_nerf_b200 import ops
+ops.use_debug_library()          # the timeline build of the kernels lives in libacn_b200_debug.so
 
 P, S = 1 << 21, 64
 sd = synth.make_expert_params(5, log2T=4)

@@ -29,8 +29,8 @@ def run(a, b, idsc, a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step, ksteps, ncols):
     at = torch.from_numpy(a.view(np.uint16)).to(dev) if a.dtype == np.float16 else a
     bt = torch.from_numpy(b.view(np.uint16)).to(dev) if b.dtype == np.float16 else b
     out = torch.full((128, ncols), float("nan"), device=dev)
-    l = _lib.lib()
-    _lib.check(l.acn_debug_umma_raw(_lib.ctx(dev), _lib.ptr(at), at.shape[0], at.shape[1], _lib.ptr(bt), bt.shape[0], bt.shape[1],
+    l = _lib.debug_lib()
+    _lib.debug_check(l.acn_debug_umma_raw(_lib.debug_ctx(dev), _lib.ptr(at), at.shape[0], at.shape[1], _lib.ptr(bt), bt.shape[0], bt.shape[1],
                                     idsc, a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step, ksteps, ncols, _lib.ptr(out), _lib.stream(dev)))
     torch.cuda.synchronize()
     return out.cpu().numpy()
