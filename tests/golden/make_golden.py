@@ -588,6 +588,301 @@ def gen_taskgrid():
     save("taskgrid.npz", **out)
 
 
+# --------------------------------------------------------------------------- round 2: the benchmarked arithmetic and configs 3-5
+def train_scene():
+    """The rays / targets / batches / jitter of gen_train (same seeds), regenerated instead of stored twice."""
+    steps, N, S = 150, 1024, 32
+    cams = synth.nadir_rays(92, 8, H=32, W=32, f=30.0)
+    box = SceneBox(aabb=T(synth.AABB_GLOBAL))
+    all_rays = []
+    for cam in cams:
+        dirs = get_ray_directions(cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], True, torch.device("cpu"))
+        r = get_rays(dirs, T(cam["c2w"]), scene_box=box).view(-1, 8)
+        r, valid = clamp_rays_near_far(r, (None, None))
+        all_rays.append(r[valid])
+    all_rays = torch.cat(all_rays)
+    tg = (0.45 - all_rays[:, 0]) / all_rays[:, 3]
+    hit = all_rays[:, :3] + all_rays[:, 3:6] * tg[:, None]
+    gt = torch.stack([0.5 + 0.5 * torch.sin(3 * hit[:, 1]), 0.5 + 0.5 * torch.cos(2 * hit[:, 2]),
+                      0.5 + 0.25 * torch.sin(2 * hit[:, 1] + hit[:, 2])], dim=1).clamp(0, 1)
+    batch_idx = np.random.default_rng(93).integers(0, all_rays.shape[0], (steps, N))
+    torch.manual_seed(1234)
+    jit = torch.rand(steps, N, S)
+    return steps, N, S, all_rays, gt, batch_idx, jit
+
+
+def with_jitter(j, fn):
+    orig = torch.rand_like
+    torch.rand_like = lambda x, _j=j: _j
+    try:
+        return fn()
+    finally:
+        torch.rand_like = orig
+
+
+def gen_train_amp():
+    """The reference's mixed-precision training step -- torch.autocast(float16) around the loss, GradScaler, global clip,
+    Adam: pipelines/offline_stage/meta_core.py:123-141 maml_meta_update (called unmodified) -- on the gen_train scene,
+    150 steps.  On a GPU the reference enters torch.cuda.amp.autocast; here the same autocast policy runs on the CPU
+    (matmul -> fp16 with fp32 accumulation, everything else as listed), which is the arithmetic the tcgen05 path must
+    track: PSNR trajectory + final eval PSNR."""
+    from pipelines.offline_stage.meta_core import maml_meta_update
+    import contextlib, io as _io
+    out = {}
+    steps, N, S, all_rays, gt, batch_idx, jit = train_scene()
+    conf = dict(HASH_CONF, log2_hashmap_size=14)
+    m = make_container(1, np.zeros((1, 3)), [synth.AABB_GLOBAL], 1.0, False, 91, hash_conf=conf)
+    with torch.no_grad():
+        m.submodules[0].xyz_encoder.hash_table.mul_(1e-3 / 0.5)
+    groups = m.get_param_groups()
+    opt = torch.optim.Adam([
+        {"params": groups["encoding"]["params"], "lr": 1e-2},
+        {"params": groups["sigma"]["params"], "lr": 2e-3},
+        {"params": groups["color"]["params"], "lr": 2e-3}], eps=1e-15)
+    scaler = torch.amp.GradScaler("cpu", init_scale=65536.0)
+    m.train()
+    psnr, scales = [], []
+    for it in range(steps):
+        idx = T(batch_idx[it])
+        rays, tgt = all_rays[idx], gt[idx]
+        scales.append(scaler.get_scale())
+        with torch.autocast("cpu", dtype=torch.float16):
+            rgb, *_ = with_jitter(jit[it], lambda: render_rays(m, rays, ray_samples=S, active_module=0))
+            loss = torch.nn.functional.mse_loss(rgb, tgt)
+        with contextlib.redirect_stdout(_io.StringIO()):
+            maml_meta_update(opt, loss, scaler, grad_clip=1.0)
+        psnr.append(-10.0 * np.log10(float(loss) + 1e-24))
+    out["psnr"] = np.array(psnr, np.float64)
+    out["scales"] = np.array(scales + [scaler.get_scale()], np.float64)
+    m.eval()
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.float16):
+        rgb, *_ = render_rays(m, all_rays[:2048], ray_samples=S, active_module=0)
+        out["final_eval_psnr"] = np.float64(-10.0 * np.log10(float(torch.nn.functional.mse_loss(rgb.float(), gt[:2048])) + 1e-24))
+    print("  train_amp psnr first/last:", psnr[0], psnr[-1], "eval:", out["final_eval_psnr"], "scale:", scales[0], "->", scales[-1])
+    save("train_amp.npz", **out)
+
+
+def rays_over_scene(seed, n_views, H, W, f, yaw_spread=True):
+    box = SceneBox(aabb=T(synth.AABB_GLOBAL))
+    all_rays = []
+    for cam in synth.nadir_rays(seed, n_views, H=H, W=W, f=f):
+        dirs = get_ray_directions(cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"], True, torch.device("cpu"))
+        r = get_rays(dirs, T(cam["c2w"]), scene_box=box).view(-1, 8)
+        r, valid = clamp_rays_near_far(r, (None, None))
+        all_rays.append(r[valid])
+    return torch.cat(all_rays)
+
+
+def gen_render8():
+    """BASELINE config 4 in small: the 2x4 grid (8 experts, margin 1.05, background head) rendered through
+    render_rays(..., active_module=None) -- models/inr/meta_container.py:275-343 -- in eval mode, with gradients of a
+    random functional for every expert and the background head."""
+    out = {}
+    cen = synth.CENTROIDS_G24
+    boxes = synth.expert_boxes_for_grid(cen)
+    S = 32
+    # three wide-angle views whose footprints cover all eight cells
+    rays = rays_over_scene(201, 3, 20, 20, 6.0)
+    out["rays"] = rays.numpy()
+    rng = np.random.default_rng(202)
+    G = rng.standard_normal((rays.shape[0], 3)).astype(F32)
+    Gd = rng.standard_normal((rays.shape[0],)).astype(F32)
+    out["G_rgb"], out["G_depth"] = G, Gd
+    mc = make_container(8, cen, boxes, 1.05, True, 203)
+    mc.eval()
+    o = render_rays(mc, rays, ray_samples=S, active_module=None, chunk=1 << 20)
+    g = grads_of(mc, (o[0] * T(G)).sum() + (o[1] * T(Gd)).sum())
+    for name, oi in zip(("rgb", "depth", "weights", "acc"), o):
+        out[name] = oi.detach().numpy()
+    for k in range(8):
+        for key in ("sigma_trunk.0.linear.weight", "sigma_trunk.1.linear.bias", "geo_head.weight", "color_mlp.0.linear.weight",
+                    "color_mlp.2.bias", "sigma_head.weight"):
+            out[f"grad.{k}.{key}"] = g[f"submodules.{k}.{key}"].numpy()
+        sub, dig = table_digest(g[f"submodules.{k}.xyz_encoder.hash_table"])
+        out[f"grad.{k}.table_sub"], out[f"grad.{k}.table_digest"] = sub, dig
+    for key in ("bg_mlp.0.weight", "bg_mlp.0.bias", "bg_mlp.2.weight", "bg_mlp.2.bias"):
+        out[f"grad.{key}"] = g[key].numpy()
+    with torch.no_grad():
+        pts = (rays[:, None, :3] + rays[:, None, 3:6] * stratified_t_vals(rays[:, 6], rays[:, 7], S, False)[..., None]).reshape(-1, 3)
+        w, _ = mc._routing(pts)
+        out["support"] = (w > 0).numpy()
+        print("  render8: rows per expert", (w > 0).sum(0).tolist(), "overlap rows", int(((w > 0).sum(1) > 1).sum()))
+    save("render8.npz", **out)
+
+
+def adapt_batches(steps, N):
+    """Support-ray batches for the adaptation fixture: views over the whole scene, except steps 3-5, whose rays all come
+    from ONE corner view (several experts then receive no ray: their parameters have grad None for those steps)."""
+    wide = rays_over_scene(301, 6, 24, 24, 9.0)
+    cam = dict(H=24, W=24, fx=40.0, fy=40.0, cx=12.0, cy=12.0, c2w=synth.camera_c2w(-0.7, -0.8, 0.2))
+    box = SceneBox(aabb=T(synth.AABB_GLOBAL))
+    dirs = get_ray_directions(24, 24, 40.0, 40.0, 12.0, 12.0, True, torch.device("cpu"))
+    corner = get_rays(dirs, T(cam["c2w"]), scene_box=box).view(-1, 8)
+    corner, valid = clamp_rays_near_far(corner, (None, None))
+    corner = corner[valid]
+    rng = np.random.default_rng(302)
+    batches = []
+    for it in range(steps):
+        src = corner if it in (3, 4, 5) else wide
+        batches.append(src[T(rng.integers(0, src.shape[0], N))])
+    rays = torch.stack(batches)
+    hit = rays[..., :3] + rays[..., 3:6] * ((0.45 - rays[..., 0]) / rays[..., 3])[..., None]
+    gt = torch.stack([0.5 + 0.5 * torch.sin(3 * hit[..., 1]), 0.5 + 0.5 * torch.cos(2 * hit[..., 2]),
+                      0.5 + 0.25 * torch.sin(2 * hit[..., 1] + hit[..., 2])], dim=-1).clamp(0, 1)
+    return rays, gt
+
+
+def gen_adapt():
+    """BASELINE config 5: online-stage adaptation of the WHOLE container (active_module=None, 8 experts, background head)
+    -- pipelines/online_stage/runtime_adapt.py:211-313 with common/utils.py get_optimizer (Adam; encoding 1e-2, sigma /
+    color 2e-3, background 1e-3: configs/eval.json), clip 1.0, 16 steps, 96 samples per ray.
+      fp32.*  runtime_adapt itself, called unmodified (on a CPU it switches AMP off: `enabled=... and cuda.is_available()`)
+      amp.*   the same loop body with the autocast / GradScaler it enters on a GPU, on the CPU autocast policy
+              (restated here line for line from :287-310, since the original hard-codes torch.cuda.amp)."""
+    for name in ("lpips", "pytorch_msssim", "imageio"):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            mod.ssim = mod.imwrite = mod.LPIPS = object
+            sys.modules[name] = mod
+    from common.utils import get_optimizer
+    from nerfs.losses import compute_mse_loss
+    from pipelines.online_stage.runtime_adapt import runtime_adapt
+    out = {}
+    steps, N, S = 16, 512, 96
+    rays, gt = adapt_batches(steps, N)
+    out["rays"], out["gt"] = rays.numpy(), gt.numpy()
+    torch.manual_seed(4321)
+    jit = torch.rand(steps, N, S)
+    out["jitter_seed"] = np.int64(4321)
+    cen = synth.CENTROIDS_G24
+    boxes = synth.expert_boxes_for_grid(cen)
+    conf = dict(HASH_CONF, log2_hashmap_size=12)
+    P = types.SimpleNamespace(lr=1e-3, encoding_lr=1e-2, sigma_lr=2e-3, color_lr=2e-3, bg_lr=1e-3, optimizer="adam",
+                              weight_decay=0.0, use_amp=True, ray_samples=S, chunk_points=1 << 22, color_space="linear")
+    keep = ("submodules.0.sigma_trunk.0.linear.weight", "submodules.3.color_mlp.2.weight", "submodules.7.geo_head.bias",
+            "bg_mlp.0.weight", "bg_mlp.2.bias")
+
+    def fresh():
+        m = make_container(8, cen, boxes, 1.05, True, 303, hash_conf=conf)
+        with torch.no_grad():
+            for sub in m.submodules:
+                sub.xyz_encoder.hash_table.mul_(1e-3 / 0.5)
+        m.train()
+        return m
+
+    class Loader:                      # yields (rays, rgbs) and arms the captured jitter for the step about to run
+        def __init__(self):
+            self.it = 0
+        def __iter__(self):
+            return self
+        def __next__(self):
+            if self.it >= steps:
+                raise StopIteration
+            torch.rand_like = lambda x, _j=jit[self.it]: _j
+            self.it += 1
+            return rays[self.it - 1], gt[self.it - 1]
+
+    # ---- fp32: the reference function itself ----
+    m = fresh()
+    opt = get_optimizer(P, m)
+    losses = []
+    orig_rand_like = torch.rand_like
+    import pipelines.online_stage.runtime_adapt as ra
+    orig_loss = ra.compute_mse_loss
+    def spy(*a, **k):
+        l = orig_loss(*a, **k)
+        losses.append(float(l.detach()))
+        return l
+    ra.compute_mse_loss = spy
+    try:
+        res = runtime_adapt(P=P, model=m, data_loader=Loader(), optimizer=opt, steps=steps, active_module=None, grad_clip=1.0)
+    finally:
+        torch.rand_like = orig_rand_like
+        ra.compute_mse_loss = orig_loss
+    assert res["steps"] == steps and len(losses) == steps
+    out["fp32.loss"] = np.array(losses, np.float64)
+    sd = dict(m.named_parameters())
+    for k in keep:
+        out[f"fp32.param.{k}"] = sd[k].detach().numpy().copy()
+    out["fp32.table_sub.0"] = sd["submodules.0.xyz_encoder.hash_table"].detach().numpy()[::97].copy()
+    out["fp32.adam_steps"] = np.array([float(opt.state[sd[f"submodules.{k}.sigma_head.weight"]]["step"]) if sd[f"submodules.{k}.sigma_head.weight"] in opt.state else 0.0
+                                       for k in range(8)])
+    print("  adapt fp32 loss first/last:", losses[0], losses[-1], "Adam steps per expert:", out["fp32.adam_steps"].tolist())
+
+    # ---- amp: same loop with autocast(float16) + GradScaler, as on a GPU ----
+    m = fresh()
+    opt = get_optimizer(P, m)
+    scaler = torch.amp.GradScaler("cpu")
+    losses, scales = [], []
+    for it in range(steps):
+        opt.zero_grad()
+        scales.append(scaler.get_scale())
+        with torch.autocast("cpu", dtype=torch.float16):
+            loss = with_jitter(jit[it], lambda: compute_mse_loss(P, model=m, data={"rays": rays[it], "rgbs": gt[it]}, params=None,
+                                                                  active_module=None, reduction="mean"))
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        scaler.step(opt)
+        scaler.update()
+        losses.append(float(loss.detach()))
+    out["amp.loss"] = np.array(losses, np.float64)
+    out["amp.scales"] = np.array(scales + [scaler.get_scale()], np.float64)
+    sd = dict(m.named_parameters())
+    for k in keep:
+        out[f"amp.param.{k}"] = sd[k].detach().numpy().copy()
+    print("  adapt amp  loss first/last:", losses[0], losses[-1], "scale:", scales[0], "->", scaler.get_scale())
+    save("adapt.npz", **out)
+
+
+def gen_hashgrid_t19():
+    """BASELINE-size table (T = 2^19, 16 levels, F = 2: 64 MiB): features of 2048 points and a digest of the table
+    gradient (models/encodings.py:331-381), Linear interpolation."""
+    out = {}
+    P, L, F, log2T = 2048, 16, 2, 19
+    x = hash_inputs(121, P)
+    table = np.random.default_rng(122).uniform(-0.5, 0.5, size=(L << log2T, F)).astype(F32)
+    dout = np.random.default_rng(123).standard_normal((P, L * F)).astype(F32)
+    enc = HashGridEncoder(levels=L, min_res=16, max_res=4096, log2_hashmap_size=log2T, features_per_level=F, interpolation="Linear")
+    with torch.no_grad():
+        enc.hash_table.copy_(T(table))
+    y = enc(T(x))
+    (y * T(dout)).sum().backward()
+    g = enc.hash_table.grad.numpy()
+    out["feat"] = y.detach().numpy()
+    nz = np.flatnonzero(np.abs(g).sum(1))
+    keep = nz[:: max(1, len(nz) // 4096)][:4096]
+    out["grad_rows"], out["grad_vals"] = keep.astype(np.int64), g[keep].copy()
+    out["grad_level_sums"] = g.reshape(L, 1 << log2T, F).sum(axis=1, dtype=np.float64)
+    out["grad_level_abs"] = np.abs(g).reshape(L, 1 << log2T, F).sum(axis=1, dtype=np.float64)
+    out["grad_nonzero_rows"] = np.int64(len(nz))
+    print("  hashgrid_t19: nonzero gradient rows", len(nz))
+    save("hashgrid_t19.npz", **out)
+
+
+def gen_field_half():
+    """The reference's fp16 arithmetic for one expert: MetaNGP.forward under torch.autocast(float16) (CPU policy = the
+    CUDA policy for these ops: matmul in fp16 with fp32 accumulation, bias add / ReLU / exp / sigmoid in fp32,
+    models/metamodule/metamodule.py:142-155) on the inputs of field.npz, and its autograd gradients under a
+    loss scale of 1024 (what GradScaler supplies), divided back out."""
+    out = {}
+    m = make_container(1, np.zeros((1, 3)), [synth.AABB_GLOBAL], 1.0, False, 31)
+    ex = m.submodules[0]
+    f = np.load(HERE / "field.npz")
+    x6 = T(np.concatenate([f["xyz"], f["dirs"]], axis=1))
+    G = T(f["G"])
+    scale = 1024.0
+    with torch.autocast("cpu", dtype=torch.float16):
+        y = ex(x6)
+    (y.float() * G * scale).sum().backward()
+    out["y"] = y.detach().float().numpy()
+    for key in synth.EXPERT_KEYS:
+        out["grad." + key] = (dict(ex.named_parameters())[key].grad / scale).numpy()
+    gt_ = ex.xyz_encoder.hash_table.grad / scale
+    out["grad.table_sub"], out["grad.table_digest"] = table_digest(gt_)
+    save("field_half.npz", **out)
+
+
 if __name__ == "__main__":
     which = set(sys.argv[1:])
     cc = None
@@ -606,3 +901,8 @@ if __name__ == "__main__":
     if want("loss"): gen_loss()
     if want("optim"): gen_optim()
     if want("taskgrid"): gen_taskgrid()
+    if want("train_amp"): gen_train_amp()
+    if want("render8"): gen_render8()
+    if want("adapt"): gen_adapt()
+    if want("hashgrid_t19"): gen_hashgrid_t19()
+    if want("field_half"): gen_field_half()

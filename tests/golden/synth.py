@@ -20,6 +20,31 @@ EXPERT_BOXES_G22 = np.array(
      [[-0.046124, -0.062537, -1.1], [0.497646, 1.1, 0.06695]],
      [[-0.046124, -0.062537, -0.06695], [0.497646, 1.1, 1.1]]], F32)
 
+def expert_boxes_for_grid(centroids, aabb=AABB_GLOBAL, overlap=1.10):
+    """Axis-aligned per-expert boxes for a regular (y,z) grid of centroids (cluster_2d): each cell reaches half a grid
+    spacing (x `overlap`) from its centroid, clipped to the global box; full x range.  Plays the role of the shipped
+    scene_boxes.pt for grids that ship none (the 2x4 grid of BASELINE configs 4/5)."""
+    c = np.asarray(centroids, np.float64)
+    out = []
+    ys, zs = np.unique(np.round(c[:, 1], 5)), np.unique(np.round(c[:, 2], 5))
+    hy = 0.5 * (ys[1] - ys[0]) if len(ys) > 1 else 10.0
+    hz = 0.5 * (zs[1] - zs[0]) if len(zs) > 1 else 10.0
+    for k in range(c.shape[0]):
+        lo = np.array([aabb[0, 0], max(aabb[0, 1], c[k, 1] - hy * overlap) if c[k, 1] - hy > aabb[0, 1] + 1e-6 and c[k, 1] > ys[0] + 1e-6 else aabb[0, 1],
+                       max(aabb[0, 2], c[k, 2] - hz * overlap) if c[k, 2] > zs[0] + 1e-6 else aabb[0, 2]])
+        hi = np.array([aabb[1, 0], min(aabb[1, 1], c[k, 1] + hy * overlap) if c[k, 1] < ys[-1] - 1e-6 else aabb[1, 1],
+                       min(aabb[1, 2], c[k, 2] + hz * overlap) if c[k, 2] < zs[-1] - 1e-6 else aabb[1, 2]])
+        out.append(np.stack([lo, hi]))
+    return np.asarray(out, F32)
+
+
+#: 2x4 grid of BASELINE configs 4/5: scripts/create_clusters.py:298-314 _grid_centroids(cams, 1, 2, 4, True) over the
+#: synthetic camera extent y,z in [-0.9, 0.9] (the values the reference returns; also stored in routing.npz `cen8`)
+CENTROIDS_G24 = np.array([[-0.04, -0.45, -0.67499995], [-0.04, -0.45, -0.22500002], [-0.04, -0.45, 0.22500002],
+                          [-0.04, -0.45, 0.67499995], [-0.04, 0.44999993, -0.67499995], [-0.04, 0.44999993, -0.22500002],
+                          [-0.04, 0.44999993, 0.22500002], [-0.04, 0.44999993, 0.67499995]], F32)
+
+
 EXPERT_KEYS = [
     "sigma_trunk.0.linear.weight", "sigma_trunk.0.linear.bias",
     "sigma_trunk.1.linear.weight", "sigma_trunk.1.linear.bias",
