@@ -35,10 +35,10 @@ class FieldWeights(C.Structure):
 class AdamTensor(C.Structure):
     """acn_adam_tensor (include/acn_b200.h)"""
     _fields_ = [("p", c_p), ("g", c_p), ("m", c_p), ("v", c_p), ("n", c_i64), ("lr", C.c_double),
-                ("weight_decay", C.c_double)]
+                ("weight_decay", C.c_double), ("step", c_p), ("bias", c_p)]
 
 
-ADAM_MAX_TENSORS = 48
+ADAM_MAX_TENSORS = 192
 LOSS_PARTIALS = 1024
 COLOR_SPACE = {"linear": 0, "srgb": 1, "identity": 2}
 

@@ -81,4 +81,5 @@ __device__ __forceinline__ void st_stream_f4(float4* p, float4 v) {
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+// torch.clamp semantics: NaN propagates (fminf / fmaxf alone would replace it by a bound)
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x != x ? x : fminf(fmaxf(x, lo), hi); }

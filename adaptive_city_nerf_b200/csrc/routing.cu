@@ -337,9 +337,10 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route_samples(
     int64_t p;
     bool on;
     const bool rm = ray_major_dev ? (__ldg(ray_major_dev) != 0) : (ray_major != 0);
-    // ray-major: the block owns a 32-ray x 16-sample tile.  t_vals and the support sets are (ray, sample) row-major, so a
-    // warp (= one sample of 32 rays) would touch 32 different lines per access; the tile goes through shared memory
-    // instead, moved by threads laid out (ray = tid / 16, sample = tid % 16): 64 contiguous bytes per ray.
+    // ray-major: the block owns a 32-ray x ROUTE_WARPS-sample tile (32 x 8).  t_vals and the support sets are (ray,
+    // sample) row-major, so a warp (= one sample of 32 rays) would touch 32 different lines per access; the tile goes
+    // through shared memory instead, moved by threads laid out (ray = tid / ROUTE_WARPS, sample = tid % ROUTE_WARPS):
+    // 32 contiguous bytes of t per ray.
     __shared__ float s_t[32][ROUTE_WARPS + 1];
     __shared__ uint16_t s_sup[32][ROUTE_WARPS + 2];
     int64_t p_tile = 0;                                     // the element this thread moves for the tile

@@ -187,11 +187,36 @@ __global__ void __launch_bounds__(256) k_grad_sqnorm(const __grid_constant__ Ada
 // Step decision (one thread): GradScaler.step's skip, clip_grad_norm_'s coefficient, Adam's bias corrections.
 // state (doubles) = [step, coef, skip, bias_correction1, sqrt(bias_correction2), total_norm, 0, 0]; found_inf_out
 // (float, optional) is what GradScaler.update() consumes.  acc is cleared for the next step.
-__global__ void k_adam_prepare(double* __restrict__ acc, const float* __restrict__ grad_scale,
-                               const float* __restrict__ found_inf_in, float max_norm, double beta1, double beta2,
-                               double* __restrict__ state, float* __restrict__ found_inf_out)
+// Per-tensor part of the decision: a tensor that takes part in a step that is not skipped advances ITS step count
+// (torch.optim.Adam keeps `step` per parameter and leaves it alone while the parameter's grad is None -- an expert that
+// saw no ray) and gets its bias corrections from it, in doubles like torch's host code.
+__device__ __forceinline__ void adam_advance_tensors(const AdamBatch& b, bool skip, double beta1, double beta2) {
+    for (int k = threadIdx.x; k < b.count; k += blockDim.x) {
+        const acn_adam_tensor& t = b.t[k];
+        if (!t.step || !t.bias) continue;
+        double step = (double)*t.step;
+        if (!skip) { step += 1.0; *t.step = (float)step; }
+        t.bias[0] = 1.0 - pow(beta1, step);
+        t.bias[1] = sqrt(1.0 - pow(beta2, step));
+    }
+}
+
+__global__ void __launch_bounds__(64) k_adam_advance(const __grid_constant__ AdamBatch b, const double* __restrict__ state,
+                                                     double beta1, double beta2)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    adam_advance_tensors(b, state[2] != 0.0, beta1, beta2);
+}
+
+__global__ void __launch_bounds__(64) k_adam_prepare(double* __restrict__ acc, const float* __restrict__ grad_scale,
+                               const float* __restrict__ found_inf_in, float max_norm, double beta1, double beta2,
+                               double* __restrict__ state, float* __restrict__ found_inf_out,
+                               const __grid_constant__ AdamBatch b)
+{
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = (acc[1] > 0.0 || !isfinite(acc[0]) || (found_inf_in && *found_inf_in > 0.0f)) ? 1 : 0;
+    __syncthreads();
+    adam_advance_tensors(b, s_bad != 0, beta1, beta2);
+    if (threadIdx.x != 0) return;
     const double sq = acc[0];
     const bool bad = acc[1] > 0.0 || !isfinite(sq) || (found_inf_in && *found_inf_in > 0.0f);
     acc[0] = 0.0;
@@ -235,11 +260,12 @@ __global__ void __launch_bounds__(256) k_adam_apply(const __grid_constant__ Adam
                                                     const double* __restrict__ state, double beta1, double beta2, double eps)
 {
     if (state[2] != 0.0) return;                      // non-finite gradient somewhere: the whole step is skipped
-    const AdamK K = {(float)state[1], (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)state[4]};
-    const double bc1 = state[3];
+    AdamK K = {(float)state[1], (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)state[4]};
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
     for (int k = 0; k < b.count; ++k) {
         const acn_adam_tensor& t = b.t[k];
+        const double bc1 = t.bias ? t.bias[0] : state[3];           // per-tensor step (torch.optim.Adam) or the global one
+        K.bc2_sqrt = (float)(t.bias ? t.bias[1] : state[4]);
         const float wd = (float)t.weight_decay, lr_wd = (float)(t.lr * t.weight_decay), step_size = (float)(t.lr / bc1);
         const int64_t n = t.n;
         const bool vec = (((uintptr_t)t.p | (uintptr_t)t.g | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0;
@@ -280,6 +306,8 @@ static int fill_batch(AdamBatch& b, const acn_adam_tensor* tensors, int count, b
     for (int k = 0; k < count; ++k) {
         b.t[k] = tensors[k];
         ACN_REQUIRE(b.t[k].n >= 0 && (b.t[k].n == 0 || b.t[k].g), ACN_EINVAL, "%s: tensor %d has no gradient", who, k);
+        ACN_REQUIRE((b.t[k].step == nullptr) == (b.t[k].bias == nullptr), ACN_EINVAL,
+                    "%s: tensor %d: step and bias must be given together", who, k);
         if (need_state)
             ACN_REQUIRE(b.t[k].n == 0 || (b.t[k].p && b.t[k].m && b.t[k].v), ACN_EINVAL,
                         "%s: tensor %d lacks p / exp_avg / exp_avg_sq", who, k);
@@ -309,14 +337,32 @@ extern "C" int acn_grad_sqnorm(acn_ctx* ctx, const acn_adam_tensor* tensors, int
 
 extern "C" int acn_adam_prepare(acn_ctx* ctx, double* acc2, const float* grad_scale_or_null,
                                 const float* found_inf_or_null, float max_norm, double beta1, double beta2,
-                                double* state8, float* found_inf_out_or_null, acn_stream stream)
+                                double* state8, float* found_inf_out_or_null, const acn_adam_tensor* tensors_or_null,
+                                int count, acn_stream stream)
 {
     ACN_CHECK_CTX(ctx);
     ACN_REQUIRE(acc2 && state8, ACN_EINVAL, "acn_adam_prepare: null accumulator / state");
     ACN_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0, ACN_EINVAL,
                 "acn_adam_prepare: betas (%g, %g) outside [0,1)", beta1, beta2);
-    k_adam_prepare<<<1, 32, 0, (cudaStream_t)stream>>>(acc2, grad_scale_or_null, found_inf_or_null, max_norm, beta1,
-                                                       beta2, state8, found_inf_out_or_null);
+    AdamBatch b;
+    int rc = fill_batch(b, tensors_or_null, tensors_or_null ? count : 0, false, "acn_adam_prepare");
+    if (rc) return rc;
+    k_adam_prepare<<<1, 64, 0, (cudaStream_t)stream>>>(acc2, grad_scale_or_null, found_inf_or_null, max_norm, beta1,
+                                                       beta2, state8, found_inf_out_or_null, b);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
+
+extern "C" int acn_adam_advance(acn_ctx* ctx, const acn_adam_tensor* tensors, int count, const double* state8,
+                                double beta1, double beta2, acn_stream stream)
+{
+    ACN_CHECK_CTX(ctx);
+    ACN_REQUIRE(state8 != nullptr, ACN_EINVAL, "acn_adam_advance: null state");
+    AdamBatch b;
+    int rc = fill_batch(b, tensors, count, false, "acn_adam_advance");
+    if (rc) return rc;
+    if (count == 0) return ACN_OK;
+    k_adam_advance<<<1, 64, 0, (cudaStream_t)stream>>>(b, state8, beta1, beta2);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }

@@ -287,7 +287,9 @@ class ExpertShardedContainer(torch.nn.Module):
         if use_peer:
             return self._forward_peer(dispatch, dev, all_counts, cnt, offsets, pos, fields, N)
         y = routed_exchange(xd, all_counts, fields, self.group)
-        out = torch.zeros(N, 4, dtype=torch.float32, device=dev) + 0.0 * y.sum()   # ties y in even if unused
+        # ties y into the graph even when this rank blends nothing (the exchange's backward is a collective) WITHOUT
+        # touching values: the sum over zero rows is an exact 0 whatever y holds (0 * inf = NaN would poison every ray)
+        out = torch.zeros(N, 4, dtype=torch.float32, device=dev) + y[:0].sum()
         off = offsets.tolist()
         for k in range(self.K):                               # blend in expert order, like the reference
             n = int(cnt[k])
@@ -354,8 +356,11 @@ def sharded_clip_grad_norm_(owned: Iterable[torch.nn.Parameter], shared: Iterabl
     `shared` ones (background head) are replicated and already all-reduced.  One scalar all-reduce."""
     owned = [p for p in owned if p.grad is not None]
     shared = [p for p in shared if p.grad is not None]
-    ref = (owned + shared)[0].grad if (owned or shared) else torch.zeros(())
-    sq = ref.new_zeros((), dtype=torch.float32)
+    if owned or shared:
+        dev = (owned + shared)[0].grad.device
+    else:   # a rank without gradients still takes part in the all-reduce: the scalar must live where the backend expects it
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    sq = torch.zeros((), dtype=torch.float32, device=dev)
     for p in owned:
         sq = sq + p.grad.float().pow(2).sum()
     dist.all_reduce(sq, group=group)

@@ -33,7 +33,14 @@ class FusedAdam(torch.optim.Optimizer):
       opt.step_scaled(scaler, max_norm=c)       everything in the three launches, including the inf check; also
                                                 performs `scaler.update()`
     `opt.last_norm` is the unscaled global gradient norm of the last step (a device scalar, what clip_grad_norm_
-    returns)."""
+    returns).
+
+    Step counts are per parameter, as in torch.optim.Adam: a parameter whose `.grad` is None on a step (an expert that
+    received no ray after `zero_grad(set_to_none=True)`) keeps its count, so its bias corrections pick up where they
+    left off; `state[p]["step"]` is that count (a device scalar) and round-trips through `state_dict()`.
+
+    CUDA graphs: lr, weight decay, betas, eps and max_norm are kernel ARGUMENTS -- a captured step replays the values
+    it was captured with (an lr scheduler has no effect on replays; re-capture after changing them)."""
 
     _step_supports_amp_scaling = True
 
@@ -45,6 +52,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.adamw, self.max_norm, self.write_grads = bool(adamw), max_norm, bool(write_grads)
         self._dev: Optional[torch.device] = None
         self._state8 = self._acc2 = self._found_inf = None
+        self._bias: Dict[torch.Tensor, torch.Tensor] = {}      # per parameter: [bias_correction1, sqrt(bias_correction2)] workspace
 
     # ---- device-side step state ---------------------------------------------------------------------------------
     def _device_state(self, dev: torch.device):
@@ -62,7 +70,7 @@ class FusedAdam(torch.optim.Optimizer):
 
     @property
     def steps_taken(self) -> torch.Tensor:
-        """Number of steps that were not skipped (device scalar)."""
+        """Number of optimizer steps that were not skipped (device scalar; per-parameter counts are in state[p]["step"])."""
         return self._state8[0]
 
     def _tensors(self):
@@ -84,11 +92,15 @@ class FusedAdam(torch.optim.Optimizer):
                 self._device_state(p.device)
                 st = self.state[p]
                 if "exp_avg" not in st:
-                    st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)   # filled in by state_dict()
+                    st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)   # advanced on the device, per parameter
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                bias = self._bias.get(p)
+                if bias is None:
+                    bias = self._bias[p] = torch.zeros(2, dtype=torch.float64, device=p.device)
                 t = AdamTensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
-                               p.numel(), float(group["lr"]), float(group["weight_decay"]))
+                               p.numel(), float(group["lr"]), float(group["weight_decay"]), st["step"].data_ptr(),
+                               bias.data_ptr())
                 out.append(t)
                 keep.append((p, g))
         return out, keep, betas, eps
@@ -110,7 +122,10 @@ class FusedAdam(torch.optim.Optimizer):
         for arr, n in chunks:
             check(L.acn_grad_sqnorm(c, C.cast(arr, C.c_void_p), n, ptr(gs), ptr(self._acc2), s))
         check(L.acn_adam_prepare(c, ptr(self._acc2), ptr(gs), ptr(fi), float(max_norm) if max_norm else 0.0,
-                                 float(betas[0]), float(betas[1]), ptr(self._state8), ptr(self._found_inf), s))
+                                 float(betas[0]), float(betas[1]), ptr(self._state8), ptr(self._found_inf),
+                                 C.cast(chunks[0][0], C.c_void_p), chunks[0][1], s))
+        for arr, n in chunks[1:]:
+            check(L.acn_adam_advance(c, C.cast(arr, C.c_void_p), n, ptr(self._state8), float(betas[0]), float(betas[1]), s))
         for arr, n in chunks:
             check(L.acn_adam_apply(c, C.cast(arr, C.c_void_p), n, ptr(self._state8), float(betas[0]), float(betas[1]),
                                    float(eps), int(self.adamw), int(self.write_grads), s))
@@ -139,23 +154,36 @@ class FusedAdam(torch.optim.Optimizer):
             return
         if scaler._scale is None:
             raise RuntimeError("step_scaled: call scaler.scale(loss).backward() first")
-        self._run(scaler._scale, None, max_norm)
+        from torch.amp.grad_scaler import OptState
+        st = scaler._per_optimizer_states[id(self)]
+        if st["stage"] is OptState.STEPPED:
+            raise RuntimeError("step_scaled: this optimizer has already stepped since the last scaler.update()")
+        if st["stage"] is OptState.UNSCALED:
+            # the caller already ran scaler.unscale_(opt) (maml_meta_update's order): the gradients are real, the
+            # scaler's own inf check stands -- do not divide by the scale a second time
+            found = [v.to(self._dev or v.device) for v in st["found_inf_per_device"].values()]
+            self._run(None, torch.stack(found).sum().reshape(1) if found else None, max_norm)
+        else:
+            self._run(scaler._scale, None, max_norm)
         if self._found_inf is not None:
             torch._amp_update_scale_(scaler._scale, scaler._growth_tracker, self._found_inf, scaler.get_growth_factor(),
                                      scaler.get_backoff_factor(), scaler.get_growth_interval())
+        scaler._per_optimizer_states.pop(id(self), None)       # what scaler.update() does: the next step starts READY
 
     # ---- checkpoints in torch.optim.Adam's layout (reference: utils.py save/load_checkpoint) ------------------------
     def state_dict(self) -> Dict[str, Any]:
-        if self._state8 is not None:
-            step = self._state8[0].float()
-            for st in self.state.values():
-                if "step" in st:
-                    st["step"] = step.clone()
-        return super().state_dict()
+        return super().state_dict()        # state[p]["step"] IS the per-parameter count: torch.optim.Adam's layout
 
     def load_state_dict(self, state_dict: Dict[str, Any]) -> None:
+        """Accepts torch.optim.Adam / AdamW checkpoints: per-parameter `step` (a CPU tensor there) moves to the
+        parameter's device and keeps its value."""
         super().load_state_dict(state_dict)
-        steps = [float(st["step"]) for st in self.state.values() if "step" in st]
+        steps = []
+        for p, st in self.state.items():
+            if "step" in st:
+                st["step"] = torch.as_tensor(st["step"], dtype=torch.float32).to(p.device).reshape(()).clone()
+                steps.append(float(st["step"]))
+        self._bias.clear()
         if steps:
             p0 = next(p for p in self.state if "step" in self.state[p])
             self._dev = None

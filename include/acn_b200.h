@@ -232,7 +232,7 @@ int acn_route_bucket_rays(acn_ctx*, const float* rays8, const float* t_vals, int
 /* ---- around the render: loss epilogue and optimizer tail --------------- */
 enum { ACN_COLOR_LINEAR = 0, ACN_COLOR_SRGB = 1, ACN_COLOR_IDENTITY = 2 };
 #define ACN_LOSS_PARTIALS 1024   /* doubles of workspace acn_color_mse may use */
-#define ACN_ADAM_MAX_TENSORS 48  /* tensors per acn_grad_sqnorm / acn_adam_apply call */
+#define ACN_ADAM_MAX_TENSORS 192 /* tensors per acn_grad_sqnorm / acn_adam_prepare / acn_adam_apply call */
 
 /* nerfs/color_space.py:22-66 color_space_transformer + nerfs/losses.py:32 F.mse_loss in one pass over n = 3N
  * elements: pred is the rendered LINEAR rgb, gt the sRGB ground truth.  loss_or_null (1): mean (mean != 0) or sum of
@@ -251,6 +251,10 @@ typedef struct {
     int64_t n;
     double lr;           /* the param group's lr */
     double weight_decay; /* the param group's weight decay */
+    float* step;         /* device, 1 float: THIS tensor's step count, as torch.optim.Adam keeps it per parameter (a tensor
+                          * that had no gradient on some steps lags behind the others); NULL = use the global count */
+    double* bias;        /* device, 2 doubles of workspace for this tensor: [bias_correction1, sqrt(bias_correction2)],
+                          * written by acn_adam_prepare / acn_adam_advance, read by acn_adam_apply; NULL with step == NULL */
 } acn_adam_tensor;
 
 /* Optimizer tail of pipelines/offline_stage/meta_core.py:123-141 maml_meta_update (scaler.unscale_ ->
@@ -262,6 +266,11 @@ typedef struct {
  *                     skip when any gradient (or *found_inf_or_null) is non-finite, as GradScaler.step does;
  *                     clip = min(1, max_norm / (total_norm + 1e-6)) when max_norm > 0 (torch clip_grad_norm_);
  *                     acc2 is cleared; found_inf_out_or_null (1 float) is for GradScaler.update().
+ *                     tensors_or_null / count: the tensors taking part in THIS step (those with a gradient): unless
+ *                     the step is skipped, each one's *step is incremented and its bias corrections are written to
+ *                     *bias from ITS step (torch.optim.Adam: a parameter whose grad is None keeps its step).
+ *   acn_adam_advance: the per-tensor part of acn_adam_prepare for a further batch of tensors (more than
+ *                     ACN_ADAM_MAX_TENSORS in one step); call after acn_adam_prepare.
  *   acn_adam_apply  : torch.optim.Adam (adamw = 0) / AdamW (adamw = 1) update of <= 48 tensors with the gradient
  *                     multiplied by coef on the fly; write_grads != 0 also stores the unscaled, clipped gradient
  *                     back (what the reference leaves in .grad). */
@@ -269,7 +278,9 @@ int acn_grad_sqnorm(acn_ctx*, const acn_adam_tensor* tensors, int count, const f
                     double* acc2, acn_stream);
 int acn_adam_prepare(acn_ctx*, double* acc2, const float* grad_scale_or_null, const float* found_inf_or_null,
                      float max_norm, double beta1, double beta2, double* state8, float* found_inf_out_or_null,
-                     acn_stream);
+                     const acn_adam_tensor* tensors_or_null, int count, acn_stream);
+int acn_adam_advance(acn_ctx*, const acn_adam_tensor* tensors, int count, const double* state8, double beta1,
+                     double beta2, acn_stream);
 int acn_adam_apply(acn_ctx*, const acn_adam_tensor* tensors, int count, const double* state8, double beta1,
                    double beta2, double eps, int adamw, int write_grads, acn_stream);
 

@@ -181,7 +181,7 @@ def test_train_step_host_logic_without_gpu(built_lib):
     import types
     from adaptive_city_nerf_b200 import _lib, ops
     from adaptive_city_nerf_b200.optim import FusedAdam, get_optimizer
-    assert C.sizeof(_lib.AdamTensor) == 56                                 # 4 pointers + int64 + 2 doubles
+    assert C.sizeof(_lib.AdamTensor) == 72                                 # 4 pointers + int64 + 2 doubles + step, bias pointers
     hdr = (ROOT / "include" / "acn_b200.h").read_text()
     assert f"#define ACN_ADAM_MAX_TENSORS {_lib.ADAM_MAX_TENSORS}" in hdr and f"#define ACN_LOSS_PARTIALS {_lib.LOSS_PARTIALS}" in hdr
     with pytest.raises(ValueError):
