@@ -122,24 +122,51 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route_points(
     }
 }
 
+// float atomic min / max on plain fp32 storage (mixed signs; the target starts at +inf / -inf)
+__device__ __forceinline__ void atomic_min_f32(float* addr, float v) {
+    if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
+    if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
 // scripts/create_clusters.py:592-632: per ray, S lerp'ed samples, min over samples of
 // D / (min_c D + 1e-8), compared with the margin.
-template <int DIMS, int MAXK>
+// AABB = true additionally streams the per-expert sample boxes of scripts/create_clusters.py:386-556 (update_aabbs:
+// mins_out / maxs_out / counts_out): every SAMPLE that passes the same test for expert c extends c's box with its 3-D
+// position o + d*t and counts once.  Non-finite samples (rays that miss the scene box carry near = far = inf) fail the
+// comparison and contribute nothing, as in the reference.  Thread-local boxes -> warp shuffles -> one atomic per warp.
+template <int DIMS, int MAXK, bool AABB>
 __global__ void __launch_bounds__(128) k_route_rays(
     const float* __restrict__ rays8, int64_t N, int S, const float* __restrict__ u_lin,
-    const float* __restrict__ cen, int K, float margin, uint8_t* __restrict__ mask)
+    const float* __restrict__ cen, int K, float margin, uint8_t* __restrict__ mask,
+    float* __restrict__ mins, float* __restrict__ maxs, unsigned long long* __restrict__ counts)
 {
     constexpr int OFF = DIMS == 2 ? 1 : 0;
+    constexpr int BK = AABB ? MAXK : 1;
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= N) return;
+    const bool ron = r < N;
+    if (!AABB && !ron) return;
+    if (!ron) r = N - 1;                                   // AABB: keep the lane alive for the shuffles
     const float4 a = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * r));
     const float4 b = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * r) + 1);
     const float o[3] = { a.x, a.y, a.z }, d[3] = { a.w, b.x, b.y };
     const float near = b.z, far = b.w;
     const float diff = __fsub_rn(far, near);
+    const float INF = __int_as_float(0x7f800000);
     float rmin[MAXK];
+    float bmin[BK][3], bmax[BK][3];
+    unsigned int bcnt[BK];
 #pragma unroll
-    for (int k = 0; k < MAXK; ++k) rmin[k] = __int_as_float(0x7f800000);
+    for (int k = 0; k < MAXK; ++k) rmin[k] = INF;
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+        bcnt[k] = 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { bmin[k][c] = INF; bmax[k][c] = -INF; }
+    }
     for (int s = 0; s < S; ++s) {
         float z = __ldg(u_lin + s);
         // torch.lerp on CPU is fused: w<0.5 ? a + w*(b-a) : b - (b-a)*(1-w)
@@ -148,20 +175,59 @@ __global__ void __launch_bounds__(128) k_route_rays(
 #pragma unroll
         for (int k = 0; k < DIMS; ++k) x[k] = __fadd_rn(o[OFF + k], __fmul_rn(d[OFF + k], t));
         float D[MAXK];
-        float m = __int_as_float(0x7f800000);
+        float m = INF;
 #pragma unroll
         for (int k = 0; k < MAXK; ++k) {
             if (k < K) { D[k] = cdist_mm<DIMS>(x, cen + 3 * k + OFF); m = fminf(m, D[k]); }
         }
         float den = __fadd_rn(m, 1e-8f);
+        float p3[3];
+        if constexpr (AABB) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) p3[c] = __fadd_rn(o[c], __fmul_rn(d[c], t));
+        }
 #pragma unroll
         for (int k = 0; k < MAXK; ++k) {
-            if (k < K) rmin[k] = fminf(rmin[k], __fdiv_rn(D[k], den));
+            if (k < K) {
+                const float q = __fdiv_rn(D[k], den);
+                rmin[k] = fminf(rmin[k], q);
+                if constexpr (AABB) {
+                    if (ron && q <= margin) {          // NaN fails
+                        ++bcnt[k];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { bmin[k][c] = fminf(bmin[k][c], p3[c]); bmax[k][c] = fmaxf(bmax[k][c], p3[c]); }
+                    }
+                }
+            }
         }
     }
+    if (ron) {
 #pragma unroll
-    for (int k = 0; k < MAXK; ++k) {
-        if (k < K) mask[r * K + k] = rmin[k] <= margin ? 1 : 0;
+        for (int k = 0; k < MAXK; ++k) {
+            if (k < K) mask[r * K + k] = rmin[k] <= margin ? 1 : 0;
+        }
+    }
+    if constexpr (AABB) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) {
+            if (k >= K) break;
+            unsigned int n = bcnt[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) n += __shfl_xor_sync(0xffffffffu, n, off);
+            if (n == 0) continue;                          // warp-uniform
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float lo = bmin[k][c], hi = bmax[k][c];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+                    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+                }
+                if (lane == 0) { atomic_min_f32(mins + 3 * k + c, lo); atomic_max_f32(maxs + 3 * k + c, hi); }
+            }
+            if (lane == 0 && counts) atomicAdd(counts + k, (unsigned long long)n);
+        }
     }
 }
 
@@ -502,19 +568,29 @@ extern "C" int acn_route_points(acn_ctx* ctx, const float* pts, int64_t P, int s
 
 extern "C" int acn_route_rays_voronoi(acn_ctx* ctx, const float* rays8, int64_t N, int S, const float* u_lin,
                                       const float* centroids, int K, int dims, float margin, uint8_t* mask,
-                                      acn_stream stream) {
+                                      float* mins_or_null, float* maxs_or_null, int64_t* counts_or_null, acn_stream stream) {
     ACN_CHECK_CTX(ctx);
     ACN_REQUIRE(N >= 0 && S >= 1 && u_lin && centroids, ACN_EINVAL, "acn_route_rays_voronoi: bad arguments");
     ACN_REQUIRE(K >= 1 && K <= 64, ACN_EUNSUPPORTED, "acn_route_rays_voronoi: K=%d outside [1,64]", K);
     ACN_REQUIRE(dims == 2 || dims == 3, ACN_EINVAL, "acn_route_rays_voronoi: dims must be 2 or 3");
+    const bool aabb = mins_or_null != nullptr;
+    ACN_REQUIRE((maxs_or_null != nullptr) == aabb && (aabb || !counts_or_null), ACN_EINVAL,
+                "acn_route_rays_voronoi: give mins and maxs together (counts only with them)");
+    ACN_REQUIRE(!aabb || K <= 16, ACN_EUNSUPPORTED, "acn_route_rays_voronoi: the per-expert boxes are built for K <= 16 (got %d)", K);
     if (N == 0) return ACN_OK;
     ACN_REQUIRE(rays8 && mask, ACN_EINVAL, "acn_route_rays_voronoi: null buffer");
     ACN_REQUIRE(((uintptr_t)rays8 & 15) == 0, ACN_EINVAL, "acn_route_rays_voronoi: rays8 must be 16-byte aligned");
     const int grid = acn_grid_1d(N, 128);
     cudaStream_t st = (cudaStream_t)stream;
-#define RR(D, MK) k_route_rays<D, MK><<<grid, 128, 0, st>>>(rays8, N, S, u_lin, centroids, K, margin, mask)
-    if (dims == 2) { if (K <= 4) RR(2, 4); else if (K <= 8) RR(2, 8); else if (K <= 16) RR(2, 16); else RR(2, 64); }
-    else           { if (K <= 4) RR(3, 4); else if (K <= 8) RR(3, 8); else if (K <= 16) RR(3, 16); else RR(3, 64); }
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(counts_or_null);
+#define RR(D, MK, AB) k_route_rays<D, MK, AB><<<grid, 128, 0, st>>>(rays8, N, S, u_lin, centroids, K, margin, mask, mins_or_null, maxs_or_null, cnt)
+    if (aabb) {
+        if (dims == 2) { if (K <= 4) RR(2, 4, true); else if (K <= 8) RR(2, 8, true); else RR(2, 16, true); }
+        else           { if (K <= 4) RR(3, 4, true); else if (K <= 8) RR(3, 8, true); else RR(3, 16, true); }
+    } else {
+        if (dims == 2) { if (K <= 4) RR(2, 4, false); else if (K <= 8) RR(2, 8, false); else if (K <= 16) RR(2, 16, false); else RR(2, 64, false); }
+        else           { if (K <= 4) RR(3, 4, false); else if (K <= 8) RR(3, 8, false); else if (K <= 16) RR(3, 16, false); else RR(3, 64, false); }
+    }
 #undef RR
     ACN_CHECK_LAUNCH();
     return ACN_OK;

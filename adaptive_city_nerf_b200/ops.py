@@ -481,13 +481,22 @@ def route_points(pts: Tensor, centroids: Tensor, dims: int, margin: float, want_
     return w, h, counts
 
 
-def route_rays_voronoi(rays: Tensor, S: int, centroids: Tensor, dims: int, margin: float) -> Tensor:
+def route_rays_voronoi(rays: Tensor, S: int, centroids: Tensor, dims: int, margin: float,
+                       aabb_out: Optional[Tuple[Tensor, Tensor, Optional[Tensor]]] = None) -> Tensor:
+    """Ray -> expert masks (N,K) bool.  aabb_out = (mins (K,3) fp32, maxs (K,3) fp32, counts (K,) int64 | None) on the device
+    are UPDATED with the samples assigned to each expert (scripts/create_clusters.py:386-556 update_aabbs)."""
     rays = dev_f32(rays, "rays")
     cen = dev_f32(centroids.to(rays.device), "centroids")
     N, K = rays.shape[0], cen.shape[0]
     mask = torch.empty(N, K, dtype=torch.uint8, device=rays.device)
+    mins = maxs = counts = None
+    if aabb_out is not None:
+        mins, maxs, counts = aabb_out
+        assert mins.dtype == torch.float32 and maxs.dtype == torch.float32 and mins.shape == (K, 3) == maxs.shape
+        assert mins.is_contiguous() and maxs.is_contiguous() and mins.device == rays.device == maxs.device
+        assert counts is None or (counts.dtype == torch.int64 and counts.shape == (K,) and counts.device == rays.device)
     check(lib().acn_route_rays_voronoi(ctx(rays.device), ptr(rays), N, S, ptr(u_lin(S, rays.device)), ptr(cen), K, dims,
-                                       float(margin), ptr(mask), stream(rays.device)))
+                                       float(margin), ptr(mask), ptr(mins), ptr(maxs), ptr(counts), stream(rays.device)))
     return mask.bool()
 
 

@@ -175,10 +175,14 @@ int acn_route_points(acn_ctx*, const float* pts, int64_t P, int stride, const fl
                      int K, int dims, float margin, float* weights_or_null,
                      int32_t* hard_or_null, int32_t* counts_or_null, acn_stream);
 
-/* scripts/create_clusters.py:559-634 compute_voronoi_orig: mask (N,K) uint8. */
+/* scripts/create_clusters.py:559-634 compute_voronoi_orig: mask (N,K) uint8.
+ * mins_or_null / maxs_or_null (K,3) fp32 and counts_or_null (K) int64: the per-expert sample boxes streamed by
+ * compute_voronoi_opt (:386-556 update_aabbs, mins_out / maxs_out / counts_out) -- UPDATED, not overwritten (start them
+ * at +inf / -inf / 0 and call once per image): every sample o + d*t with D_c / (min_c' D + 1e-8) <= margin extends
+ * expert c's box and counts once; non-finite samples contribute nothing.  K <= 16 with the boxes. */
 int acn_route_rays_voronoi(acn_ctx*, const float* rays8, int64_t N, int S, const float* u_lin,
                            const float* centroids, int K, int dims, float margin, uint8_t* mask,
-                           acn_stream);
+                           float* mins_or_null, float* maxs_or_null, int64_t* counts_or_null, acn_stream);
 
 /* Device-side dispatch for meta_container.py:306-337 (replaces nonzero/index_select and its
  * K host syncs).  For expert k, the points with weight > 0 (or hard == k) are written, in

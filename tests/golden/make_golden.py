@@ -883,6 +883,29 @@ def gen_field_half():
     save("field_half.npz", **out)
 
 
+def gen_scene_boxes():
+    """The reference's SHIPPED per-expert boxes (data/drz/out/example/masks/g22_grid_bm110_ss11/scene_boxes.pt: mins, maxs,
+    counts streamed over all 249 train + val images by scripts/create_clusters.py:792-973) together with what is needed to
+    redo the run: every image's pose and intrinsics (the metadata files, ~100 bytes each)."""
+    root = REF / "data/drz/out/example"
+    mdir = root / "masks/g22_grid_bm110_ss11"
+    sb = torch.load(mdir / "scene_boxes.pt")
+    out = {"mins": sb["mins"].numpy(), "maxs": sb["maxs"].numpy(), "counts": sb["counts"].numpy().astype(np.int64),
+           "centroids": sb["centroids"].numpy(), "aabb_global": sb["aabb_global"].numpy(),
+           "margin": np.float32(sb["boundary_margin"]), "ray_samples": np.int32(sb["ray_samples"])}
+    c2w, intr, hw, names = [], [], [], []
+    for split in ("train", "val"):
+        for mp in sorted((root / split / "metadata").glob("*.pt")):
+            md = torch.load(mp, map_location="cpu")
+            c2w.append(md["c2w"].numpy().astype(F32))
+            intr.append(np.array([float(a) for a in md["intrinsics"]], np.float64))
+            hw.append([int(md["H"]), int(md["W"])])
+            names.append(f"{split}/{mp.stem}")
+    out.update(c2w=np.stack(c2w), intrinsics=np.stack(intr), HW=np.array(hw, np.int32), names=np.array(names))
+    print(f"  scene_boxes: {len(names)} images, counts {out['counts'].tolist()}")
+    save("scene_boxes.npz", **out)
+
+
 if __name__ == "__main__":
     which = set(sys.argv[1:])
     cc = None
@@ -906,3 +929,4 @@ if __name__ == "__main__":
     if want("adapt"): gen_adapt()
     if want("hashgrid_t19"): gen_hashgrid_t19()
     if want("field_half"): gen_field_half()
+    if want("scene_boxes"): gen_scene_boxes()

@@ -78,7 +78,7 @@ def _rel_l2(a, b):
 
 def _emulate_fp16_field(enc16, dirs, ws, dy):
     """Torch restatement of csrc/field_mma.cu's arithmetic (the reference's autocast path, models/metamodule/
-    metamodule.py:150-155): fp16 operands (bias included), exact products with wide accumulation (fp64 here, fp32
+    metamodule.py:150-155): fp16 operands, fp32 bias (a hi + lo fp16 pair), exact products with wide accumulation (fp64 here, fp32
     in TMEM), ReLU and one rounding to fp16; gradient tiles are fp16 carrying a power-of-two scale;
     the ReLU masks are those of THIS forward.  Returns (rgb_sigma, 14 grads, d_enc)."""
     from adaptive_city_nerf_b200 import ops
@@ -88,7 +88,7 @@ def _emulate_fp16_field(enc16, dirs, ws, dy):
     wt0, bt0, wt1, bt1, wsg, bsg, wge, bge, wc0, bc0, wc1, bc1, wc2, bc2 = W
     G = wge.shape[0]
     x0 = enc16.to(D)
-    hid = lambda x, w, b: h(torch.relu(x @ h(w).t() + h(b)))      # bias rides in the accumulator: ONE rounding, with ReLU
+    hid = lambda x, w, b: h(torch.relu(x @ h(w).t() + b))         # fp32 bias (hi + lo fp16 pair) rides in the accumulator: ONE rounding, with ReLU
     h1 = hid(x0, wt0, bt0)
     h2 = hid(h1, wt1, bt1)
     sig_raw = (h2 @ h(wsg).t()).float().to(D) + bsg               # head accumulators stay fp32

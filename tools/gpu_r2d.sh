@@ -1,0 +1,9 @@
+#!/bin/bash
+# Round-2 visit D: dedicated scatter warps -- parity, timing, training diagnostics.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+echo "== tc"; timeout 600 python -m pytest tests/test_gpu_tc.py -q -m gpu --maxfail=30 -rf > gpurun_out/pytest_tc.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/pytest_tc.log
+echo "== fused bwd timing"; timeout 300 python tools/prof_fused_bwd.py > gpurun_out/fused_bwd.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/fused_bwd.log
+echo "== round2 tests"; timeout 900 python -m pytest tests/test_gpu_round2.py -q -m gpu --maxfail=30 -rf > gpurun_out/pytest_r2.log 2>&1; echo "rc=$?"; tail -12 gpurun_out/pytest_r2.log
+echo "== diag"; timeout 600 python tools/train_amp_diag.py > gpurun_out/train_amp_diag.log 2>&1; tail -5 gpurun_out/train_amp_diag.log
+echo "== bench";   timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "rc=$?"; tail -c 600 gpurun_out/bench.log
