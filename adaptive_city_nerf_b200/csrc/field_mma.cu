@@ -514,46 +514,6 @@ struct ScatterArgs {
     float* dtable; int L; int log2T; const int32_t* res; int interp;
 };
 
-// One (point, level) of the fused scatter: the point's cell at level l, the 8 corner contributions w_corner * g, REDs.
-// `dedup` (warp-uniform; coarse levels, where a ray stays in one cell for several samples and the lanes of a warp are 32
-// consecutive points): the lanes of a run of equal cells add their contributions with a segmented warp scan and only
-// the run's last lane issues the REDs -- fewer atomics, and no same-address collisions inside one RED instruction (which
-// the L2 atomic unit serialises).  The sum is over contiguous runs only, so it is exact whatever the point order.
-// Not inlined: it is called from every mbarrier wait of the layer chain.
-__device__ __noinline__ void scatter_unit(float2* __restrict__ lt, uint32_t hmask, int interp, float resf, float gx, float gy,
-                                          bool act, float px, float py, float pz, bool dedup, int lane) {
-    if (!dedup && !act) return;
-    const GridCell c = grid_cell(px, py, pz, resf, interp);
-    const float wx[2] = { 1.0f - c.wx, c.wx }, wy[2] = { 1.0f - c.wy, c.wy }, wz[2] = { 1.0f - c.wz, c.wz };
-    float2 acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float wk = act ? wz[k & 1] * wy[(k >> 1) & 1] * wx[(k >> 2) & 1] : 0.0f;
-        acc[k] = make_float2(gx * wk, gy * wk);
-    }
-    if (dedup) {
-        // cells of the coarse levels have < 2^10 cells per axis; an idle lane is a run of its own
-        const uint32_t key = act ? ((c.x0 & 1023u) | ((c.y0 & 1023u) << 10) | ((c.z0 & 1023u) << 20)) : (0x80000000u | (uint32_t)lane);
-        const uint32_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
-        const bool head = lane == 0 || kprev != key;
-        bool closed = head;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const bool cu = __shfl_up_sync(0xffffffffu, (int)closed, d) != 0;
-            const bool take = lane >= d && !closed;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float tx = __shfl_up_sync(0xffffffffu, acc[k].x, d), ty = __shfl_up_sync(0xffffffffu, acc[k].y, d);
-                if (take) { acc[k].x += tx; acc[k].y += ty; }
-            }
-            if (lane >= d) closed = closed || cu;
-        }
-        const bool hnext = __shfl_down_sync(0xffffffffu, (int)head, 1) != 0;
-        if (!(act && (lane == 31 || hnext))) return;
-    }
-    scatter_cell_f2(lt, c.x0, c.y0, c.z0, hmask, acc);
-}
-
 // power-of-two loss scale from max |dL/dy|: max * scale in [2^9, 2^10)
 __device__ __forceinline__ float grad_scale_from_max(float mx) {
     if (!(mx > 0.0f) || !(mx < 3.0e38f)) return 1.0f;
@@ -733,51 +693,75 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     load_inputs(tile, encq, dir, dy);
     Tracer<TRACE> tr{ (trace && blockIdx.x == 0 && tid == 0) ? trace : nullptr, 0, TRACE_CAP };
 
-    // Fused scatter, opportunistic: the 16 encoding-gradient columns (8 levels) this thread holds at the end of a tile are
-    // kept in registers and go out one (point, level) unit at a time WHILE THE THREAD WOULD OTHERWISE WAIT on an mbarrier
-    // of the next tile: every wait of the layer chain polls the barrier and runs one scatter unit per miss.  The address
-    // arithmetic and the REDs then fill the issue slots the chain leaves idle (22 % busy on its own) and never sit on its
-    // critical path for longer than one unit.  Measured on 2^24 samples: MLP backward + scatter as two kernels 4.5 + 8.9
-    // ms; all REDs at the end of the tile 11.2 ms; one level before each of the first eight waits 10.8 ms; + dedup of the
-    // coarse levels 10.0 ms; four dedicated scatter warps reading d_enc from TMEM 21 ms (a warp per sub-partition is
-    // instruction-latency bound on ~5000 instructions per tile pair: profiles/notes/).
+    // Fused scatter, software-pipelined: the 16 encoding-gradient columns (8 levels) this thread holds at the end of a
+    // tile are kept in registers and go out as REDs one level at a time in the first eight mbarrier waits of the NEXT tile
+    // -- the atomics then drain through the LSU while the tensor core runs that tile's MMAs, instead of as one burst of
+    // ~48 REDs per thread that stalls both slots' epilogues.  Measured on 2^24 samples: MLP backward + scatter as two
+    // kernels 4.5 + 8.9 ms; burst at the end of the tile 11.2 ms; this 10.8 ms; + dedup of the coarse levels 10.0 ms.
+    // Two ways to decouple the REDs from the chain further were tried and are SLOWER (patches under profiles/notes/):
+    // four dedicated scatter warps reading d_enc from a TMEM window (21 ms: one warp per sub-partition is bound by the
+    // latency of its ~5000 instructions per tile pair) and polling the chain's mbarriers with one scatter unit per
+    // miss (11.9 ms: the out-of-line unit and 128 registers cost more than the idle slots give).  ncu of this version:
+    // 1.08 G REDs, LSU wavefronts 51 %, L2 tags 46 %, tensor pipe 10 %, issue slots 33 % -- the kernel is bound by the
+    // issue of the ~33 k warp instructions per tile pair with 16 resident warps, not by a memory unit.
     float pv[16];
     float ppos[3] = { 0.f, 0.f, 0.f };
     bool pon = false;
     const int lv0 = (16 * hcol) / 2;                      // first level of this thread's column group
     const bool has_cols = 16 * hcol < E;
     const uint32_t hmask = SCAT ? ((1u << sc.log2T) - 1u) : 0u;
+    // Coarse levels (cells larger than the sample spacing: a ray stays in one cell for several samples, and the lanes of
+    // a warp are 32 consecutive samples): the lanes of a run of equal cells add their 8 corner contributions with a
+    // segmented warp scan and only the run's last lane issues the REDs -- fewer atomics, and no same-address collisions
+    // inside one RED instruction (which the L2 atomic unit serialises).  The sum is over contiguous runs only, so it is
+    // exact whatever the point order; at finer levels every lane scatters its own cell.
     constexpr int DEDUP_LEVELS = 4;
-    int next_lv = 8;                                      // warp-uniform: next pending level of the stash (8 = none)
-    auto scatter_next = [&]() {
+    auto drain = [&](int lv) {
         if constexpr (SCAT) {
-            float gx, gy;
-            switch (next_lv) {
-                case 0: gx = pv[0]; gy = pv[1]; break;
-                case 1: gx = pv[2]; gy = pv[3]; break;
-                case 2: gx = pv[4]; gy = pv[5]; break;
-                case 3: gx = pv[6]; gy = pv[7]; break;
-                case 4: gx = pv[8]; gy = pv[9]; break;
-                case 5: gx = pv[10]; gy = pv[11]; break;
-                case 6: gx = pv[12]; gy = pv[13]; break;
-                default: gx = pv[14]; gy = pv[15]; break;
+            const int l = lv0 + lv;
+            const float gx = pv[2 * lv], gy = pv[2 * lv + 1];
+            const bool act = pon && !(gx == 0.0f && gy == 0.0f);      // fully occluded samples scatter nothing
+            if (l < DEDUP_LEVELS) {                                    // warp-uniform (hcol is per warp)
+                const GridCell c = grid_cell(ppos[0], ppos[1], ppos[2], umma::lds_f32(sb + M::res + 4u * l), sc.interp);
+                const float wx[2] = { 1.0f - c.wx, c.wx }, wy[2] = { 1.0f - c.wy, c.wy }, wz[2] = { 1.0f - c.wz, c.wz };
+                float2 acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float wk = act ? wz[k & 1] * wy[(k >> 1) & 1] * wx[(k >> 2) & 1] : 0.0f;
+                    acc[k] = make_float2(gx * wk, gy * wk);
+                }
+                // cells of the coarse levels have < 2^10 cells per axis; an idle lane is a run of its own
+                const uint32_t key = act ? ((c.x0 & 1023u) | ((c.y0 & 1023u) << 10) | ((c.z0 & 1023u) << 20)) : (0x80000000u | (uint32_t)lane);
+                const uint32_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
+                const bool head = lane == 0 || kprev != key;
+                bool closed = head;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const bool cu = __shfl_up_sync(0xffffffffu, (int)closed, d) != 0;
+                    const bool take = lane >= d && !closed;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float tx = __shfl_up_sync(0xffffffffu, acc[k].x, d), ty = __shfl_up_sync(0xffffffffu, acc[k].y, d);
+                        if (take) { acc[k].x += tx; acc[k].y += ty; }
+                    }
+                    if (lane >= d) closed = closed || cu;
+                }
+                const bool hnext = __shfl_down_sync(0xffffffffu, (int)head, 1) != 0;
+                if (act && (lane == 31 || hnext))
+                    scatter_cell_f2(reinterpret_cast<float2*>(sc.dtable) + ((size_t)l << sc.log2T), c.x0, c.y0, c.z0, hmask, acc);
+                return;
             }
-            const int l = lv0 + next_lv;
-            scatter_unit(reinterpret_cast<float2*>(sc.dtable) + ((size_t)l << sc.log2T), hmask, sc.interp,
-                         umma::lds_f32(sb + M::res + 4u * l), gx, gy, pon && !(gx == 0.0f && gy == 0.0f), ppos[0], ppos[1], ppos[2],
-                         l < DEDUP_LEVELS, lane);
-            ++next_lv;
-        }
-    };
-    // wait on an mbarrier of the chain, doing pending scatter units while it is not ready
-    auto wait_work = [&](uint32_t bar, uint32_t& phase) {
-        if constexpr (SCAT) {
-            while (next_lv < 8) {
-                if (umma::mbar_test_a(bar, phase)) break;
-                scatter_next();
+            if (!act) return;
+            const GridCell c = grid_cell(ppos[0], ppos[1], ppos[2], umma::lds_f32(sb + M::res + 4u * l), sc.interp);
+            const float wx[2] = { 1.0f - c.wx, c.wx }, wy[2] = { 1.0f - c.wy, c.wy }, wz[2] = { 1.0f - c.wz, c.wz };
+            float2 acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float wk = wz[k & 1] * wy[(k >> 1) & 1] * wx[(k >> 2) & 1];
+                acc[k] = make_float2(gx * wk, gy * wk);
             }
+            scatter_cell_f2(reinterpret_cast<float2*>(sc.dtable) + ((size_t)l << sc.log2T), c.x0, c.y0, c.z0, hmask, acc);
         }
-        wait_done(bar, phase);
     };
 
     for (; tile < ntiles; tile += tile_stride) {
@@ -791,16 +775,22 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
         const float cdir[3] = { dir[0], dir[1], dir[2] };
         const float4 cdy = dy;
         load_inputs(tile + tile_stride, encq, dir, dy);        // prefetch: lands while this tile runs
-        wait_work(done_d, ph_d); tr(4); epi_hidden32(tmem_d, col0, Th1, row); tr(5); group_sync(bar_id, 256); tr(6); issue(1); tr(7);
-        wait_work(done_d, ph_d); epi_hidden32(tmem_d, col0, Th2, row); group_sync(bar_id, 256); issue(2);
-        wait_work(done_d, ph_d);
+        drain(0);
+        wait_done(done_d, ph_d); tr(4); epi_hidden32(tmem_d, col0, Th1, row); tr(5); group_sync(bar_id, 256); tr(6); issue(1); tr(7);
+        drain(1);
+        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, Th2, row); group_sync(bar_id, 256); issue(2);
+        drain(2);
+        wait_done(done_d, ph_d);
         float sig_raw = 0.0f;
         if (hcol) epi_heads_sh(cdir, Tcin, row);
         else sig_raw = epi_heads_geo(tmem_d, wb + wm.b_hd, G, Tcin, row, 1.0f);
         group_sync(bar_id, 256); issue(3);
-        wait_work(done_d, ph_d); epi_hidden32(tmem_d, col0, Tc1, row); group_sync(bar_id, 256); issue(4);
-        wait_work(done_d, ph_d); epi_hidden32(tmem_d, col0, Tc2, row); group_sync(bar_id, 256); issue(5);
-        wait_work(done_d, ph_d);
+        drain(3);
+        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, Tc1, row); group_sync(bar_id, 256); issue(4);
+        drain(4);
+        wait_done(done_d, ph_d); epi_hidden32(tmem_d, col0, Tc2, row); group_sync(bar_id, 256); issue(5);
+        drain(5);
+        wait_done(done_d, ph_d);
         float d_sig = 0.0f;
         if (!hcol) {   // output gradients (scaled): d rgb_raw = dy * y (1 - y); d sigma_raw = dy * exp(clamp(sigma_raw))
             float v[16], drr[16], bc2[3];
@@ -817,13 +807,15 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
         }
         tr(8);
         group_sync(bar_id, 256); tr(9); issue(6); tr(10);
+        drain(6);
         // ---------------- backward ----------------
         uint4 o[4];
-        wait_work(done_d, ph_d); tr(11); epi_mask32_load(tmem_d, col0, Tc2, row, o); tr(12); wait_work(done_w, ph_w); tr(13); epi_mask32_store(Tc2, row, col0, o);
+        wait_done(done_d, ph_d); tr(11); epi_mask32_load(tmem_d, col0, Tc2, row, o); tr(12); wait_done(done_w, ph_w); tr(13); epi_mask32_store(Tc2, row, col0, o);
         tr(14); group_sync(bar_id, 256); tr(15); issue(7); tr(16);
-        wait_work(done_d, ph_d); epi_mask32_load(tmem_d, col0, Tc1, row, o); wait_work(done_w, ph_w); epi_mask32_store(Tc1, row, col0, o);
+        drain(7);
+        wait_done(done_d, ph_d); epi_mask32_load(tmem_d, col0, Tc1, row, o); wait_done(done_w, ph_w); epi_mask32_store(Tc1, row, col0, o);
         group_sync(bar_id, 256); issue(8);
-        wait_work(done_d, ph_d);
+        wait_done(done_d, ph_d);
         if (!hcol) {   // d cin = [d sh | d geo | 0] -> heads gradient row [d geo | 0 | d sigma_raw @15]
             float v[16];
             umma::ld16(tmem_d + 16, v);
@@ -834,9 +826,9 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
             sts128(chunk_addr(Tghd, row, 0), pack8(v));
             sts128(chunk_addr(Tghd, row, 1), pack8(v + 8));
         }
-        wait_work(done_w, ph_w);
+        wait_done(done_w, ph_w);
         group_sync(bar_id, 256); issue(9);
-        wait_work(done_d, ph_d); epi_mask32_load(tmem_d, col0, Th2, row, o); wait_work(done_w, ph_w); epi_mask32_store(Th2, row, col0, o);
+        wait_done(done_d, ph_d); epi_mask32_load(tmem_d, col0, Th2, row, o); wait_done(done_w, ph_w); epi_mask32_store(Th2, row, col0, o);
         group_sync(bar_id, 256); issue(10);
         float upos[3] = { 0.f, 0.f, 0.f };
         if constexpr (SCAT) {   // the point's unit-cube position for the table scatter: in flight while the last two layers run
@@ -857,11 +849,10 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
                 }
             }
         }
-        wait_work(done_d, ph_d); epi_mask32_load(tmem_d, col0, Th1, row, o); wait_work(done_w, ph_w); epi_mask32_store(Th1, row, col0, o);
+        wait_done(done_d, ph_d); epi_mask32_load(tmem_d, col0, Th1, row, o); wait_done(done_w, ph_w); epi_mask32_store(Th1, row, col0, o);
         group_sync(bar_id, 256); issue(11);
-        wait_work(done_d, ph_d);
+        wait_done(done_d, ph_d);
         if constexpr (SCAT) {   // d_enc never leaves the SM: this thread's 8 levels are stashed for drain() during the next tile
-            while (next_lv < 8) scatter_next();          // whatever of the previous tile the waits did not absorb
             if (has_cols) {
                 float v[16];
                 umma::ld16(tmem_d + 16 * hcol, v);
@@ -870,7 +861,6 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
                 for (int j = 0; j < 16; ++j) pv[j] = v[j] * inv_scale;
                 ppos[0] = upos[0]; ppos[1] = upos[1]; ppos[2] = upos[2];
                 pon = on;
-                next_lv = 0;
             }
         } else if (want_denc) {   // 16-column groups of d_enc alternate between the row's two threads
 #pragma unroll
@@ -889,12 +879,13 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
                 }
             }
         }
-        wait_work(done_w, ph_w);     // the xe / h1 tiles are free again only now
+        wait_done(done_w, ph_w);     // the xe / h1 tiles are free again only now
         tr(17);
     }
 
     if constexpr (SCAT) {
-        while (next_lv < 8) scatter_next();
+#pragma unroll
+        for (int lv = 0; lv < 8; ++lv) drain(lv);
     }
     // ---------------- add the TMEM-resident weight gradients to global memory ----------------
     umma::fence_before_sync();

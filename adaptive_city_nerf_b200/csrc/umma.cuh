@@ -129,17 +129,6 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
     }
     __trap();
 }
-// non-blocking probe of an mbarrier phase (mbar_wait_a suspends the thread for a while inside try_wait; a thread that has
-// other work to do polls with this instead)
-__device__ __forceinline__ bool mbar_test_a(uint32_t addr, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    return ok != 0;
-}
 // true in exactly one lane of a converged warp; the form ptxas recognises as "single thread" for tcgen05 issue
 __device__ __forceinline__ bool elect_one() {
     uint32_t p;

@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+echo "== tc"; timeout 600 python -m pytest tests/test_gpu_tc.py -q -m gpu --maxfail=30 -rf > gpurun_out/pytest_tc.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/pytest_tc.log
+echo "== fused bwd timing"; timeout 300 python tools/prof_fused_bwd.py > gpurun_out/fused_bwd.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/fused_bwd.log
+echo "== round2 tests"; timeout 900 python -m pytest tests/test_gpu_round2.py -q -m gpu --maxfail=30 -rf --durations=5 > gpurun_out/pytest_r2.log 2>&1; echo "rc=$?"; tail -25 gpurun_out/pytest_r2.log
+echo "== bench";   timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "rc=$?"; tail -c 600 gpurun_out/bench.log
