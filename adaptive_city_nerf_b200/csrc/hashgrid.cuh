@@ -69,29 +69,29 @@ __device__ __forceinline__ float2 grid_level_f2(const float2* __restrict__ level
     return o;
 }
 
-// The 8 corner updates of one cell for F = 2, x-neighbours paired into one 16-byte RED when x0 is even
-// (the hash is x ^ (y*p1) ^ (z*p2), so for even x0 the x-neighbours are rows r and r^1: one aligned pair).  The
-// scatter is bound by scattered-RED issue per SM (~1.3 cycles per lane); this took it from 11.5 to 8.7 ms.
-// acc is indexed c = (x<<2)|(y<<1)|z.
+// The 8 corner updates of one cell for F = 2 as 16-byte REDs on row PAIRS (the hash is x ^ (y*p1) ^ (z*p2), so the
+// x-neighbours of an even x0 are rows r and r^1: one aligned pair, one RED carries both; for an odd x0 they sit in two
+// pairs and each RED adds zeros to the other row of its pair -- an 8-byte and a 16-byte RED cost the L2 the same
+// request).  Straight-line code: the second RED of a (y,z) corner is predicated on the parity of x0, nothing else
+// branches; the earlier version (8-byte REDs for odd x0, zero tests per corner) spent ~150 instructions per cell, and
+// the scatter kernels are bound by instruction issue, not by the atomic units (profiles/r02_v3_fused_bwd_ncu_*).
+// acc is indexed c = (x<<2)|(y<<1)|z.  lt must be 16-byte aligned.
 __device__ __forceinline__ void scatter_cell_f2(float2* __restrict__ lt, uint32_t x0, uint32_t y0, uint32_t z0, uint32_t mask,
                                                 const float2* acc) {
     const uint32_t yp0 = y0 * 2654435761u, yp1 = yp0 + 2654435761u;
     const uint32_t zp0 = z0 * 805459861u, zp1 = zp0 + 805459861u;
-    const bool xeven = !(x0 & 1u);
+    const bool odd = (x0 & 1u) != 0u;
+    float4* lt4 = reinterpret_cast<float4*>(lt);
 #pragma unroll
     for (int yz = 0; yz < 4; ++yz) {
         const uint32_t h = ((yz & 2) ? yp1 : yp0) ^ ((yz & 1) ? zp1 : zp0);
-        const uint32_t r0 = (x0 ^ h) & mask;
+        const uint32_t ra = (x0 ^ h) & mask;
         const float2 a = acc[yz], b = acc[4 + yz];
-        const bool za = a.x == 0.0f && a.y == 0.0f, zb = b.x == 0.0f && b.y == 0.0f;
-        if (xeven) {
-            if (!(za && zb)) {
-                const float4 v = (r0 & 1u) ? make_float4(b.x, b.y, a.x, a.y) : make_float4(a.x, a.y, b.x, b.y);
-                atomicAdd(reinterpret_cast<float4*>(lt) + (r0 >> 1), v);
-            }
-        } else {
-            if (!za) atomicAdd(lt + r0, a);
-            if (!zb) atomicAdd(lt + (((x0 + 1u) ^ h) & mask), b);
+        const float bx = odd ? 0.0f : b.x, by = odd ? 0.0f : b.y;            // even x0: b rides along in a's pair
+        atomicAdd(lt4 + (ra >> 1), (ra & 1u) ? make_float4(bx, by, a.x, a.y) : make_float4(a.x, a.y, bx, by));
+        if (odd) {
+            const uint32_t rb = ((x0 + 1u) ^ h) & mask;
+            atomicAdd(lt4 + (rb >> 1), (rb & 1u) ? make_float4(0.0f, 0.0f, b.x, b.y) : make_float4(b.x, b.y, 0.0f, 0.0f));
         }
     }
 }
