@@ -35,21 +35,22 @@ static int check_field(const char* fn, const void* enc, int enc_dtype, const flo
 }
 
 extern "C" int acn_field_fwd(acn_ctx* ctx, const void* enc, int enc_dtype, const float* dirs, int dirs_stride, int dirs_group,
-                             int64_t P, int E, int H, int G, int C, const acn_field_weights* w, int precision,
-                             float* rgb_sigma, acn_stream stream) {
+                             int64_t P, const int32_t* range_or_null, int E, int H, int G, int C, const acn_field_weights* w,
+                             int precision, float* rgb_sigma, acn_stream stream) {
     ACN_CHECK_CTX(ctx);
     int rc = check_field("acn_field_fwd", enc, enc_dtype, dirs, dirs_stride, dirs_group, P, w, precision);
     if (rc) return rc;
     if (P == 0) return ACN_OK;
     ACN_REQUIRE(rgb_sigma && ((uintptr_t)rgb_sigma & 15) == 0, ACN_EINVAL, "acn_field_fwd: rgb_sigma null or misaligned");
+    ACN_REQUIRE(!range_or_null || dirs_group == 1, ACN_EINVAL, "acn_field_fwd: a row range needs per-point directions");
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == ACN_F16)
-        return acn_field_fwd_tc(ctx, enc, enc_dtype, dirs, dirs_stride, dirs_group, P, E, H, G, C, w, rgb_sigma, st);
-    return acn_field_fwd_fp32(ctx, enc, enc_dtype, dirs, dirs_stride, dirs_group, P, E, H, G, C, w, rgb_sigma, st);
+        return acn_field_fwd_tc(ctx, enc, enc_dtype, dirs, dirs_stride, dirs_group, P, E, H, G, C, w, rgb_sigma, range_or_null, st);
+    return acn_field_fwd_fp32(ctx, enc, enc_dtype, dirs, dirs_stride, dirs_group, P, E, H, G, C, w, rgb_sigma, range_or_null, st);
 }
 
 extern "C" int acn_field_bwd(acn_ctx* ctx, const void* enc, int enc_dtype, const float* dirs, int dirs_stride, int dirs_group,
-                             int64_t P, int E, int H, int G, int C, const acn_field_weights* w, int precision,
+                             int64_t P, const int32_t* range_or_null, int E, int H, int G, int C, const acn_field_weights* w, int precision,
                              const float* d_rgb_sigma, const acn_field_grads* g, void* d_enc_or_null, int d_enc_dtype,
                              acn_stream stream) {
     ACN_CHECK_CTX(ctx);
@@ -59,11 +60,12 @@ extern "C" int acn_field_bwd(acn_ctx* ctx, const void* enc, int enc_dtype, const
     ACN_REQUIRE(d_enc_dtype == ACN_F32 || d_enc_dtype == ACN_F16, ACN_EINVAL, "acn_field_bwd: bad d_enc dtype");
     if (P == 0) return ACN_OK;
     ACN_REQUIRE(d_rgb_sigma && ((uintptr_t)d_rgb_sigma & 15) == 0, ACN_EINVAL, "acn_field_bwd: d_rgb_sigma null or misaligned");
+    ACN_REQUIRE(!range_or_null || dirs_group == 1, ACN_EINVAL, "acn_field_bwd: a row range needs per-point directions");
     if (precision == ACN_F16) {
         ACN_REQUIRE(d_enc_dtype == ACN_F32, ACN_EUNSUPPORTED, "acn_field_bwd(f16): d_enc must be fp32");
         return acn_field_bwd_tc(ctx, enc, enc_dtype, dirs, dirs_stride, dirs_group, P, E, H, G, C, w, d_rgb_sigma, g,
-                                (float*)d_enc_or_null, (cudaStream_t)stream);
+                                (float*)d_enc_or_null, range_or_null, (cudaStream_t)stream);
     }
     return acn_field_bwd_fp32(ctx, enc, enc_dtype, dirs, dirs_stride, dirs_group, P, E, H, G, C, w, d_rgb_sigma, g,
-                              d_enc_or_null, d_enc_dtype, (cudaStream_t)stream);
+                              d_enc_or_null, d_enc_dtype, range_or_null, (cudaStream_t)stream);
 }

@@ -217,9 +217,14 @@ __device__ void tile_forward(const EncT* __restrict__ enc, const float* __restri
 template <typename EncT>
 __global__ void __launch_bounds__(NT, 1) k_field_fwd_fp32(
     const EncT* __restrict__ enc, const float* __restrict__ dirs, int dstride, int dgroup, int64_t P, FieldDims d,
-    acn_field_weights w, float4* __restrict__ rgb_sigma)
+    acn_field_weights w, float4* __restrict__ rgb_sigma, const int32_t* __restrict__ range)
 {
     extern __shared__ __align__(16) float smem[];
+    if (range) {            // rows [range[0], range[1]) only: P was just the launch's upper bound
+        const int64_t r0 = __ldg(range);
+        P = __ldg(range + 1) - r0;
+        enc += r0 * d.E; dirs += r0 * dstride; rgb_sigma += r0;
+    }
     Smem s;
     carve(d, false, smem, &s);
     load_weights(w, d, s);
@@ -248,9 +253,16 @@ __device__ __forceinline__ float row_sum(const float* D, int row) {
 template <typename EncT, typename DEncT>
 __global__ void __launch_bounds__(NT, 1) k_field_bwd_fp32(
     const EncT* __restrict__ enc, const float* __restrict__ dirs, int dstride, int dgroup, int64_t P, FieldDims d,
-    acn_field_weights w, const float4* __restrict__ d_rgb_sigma, acn_field_grads g, DEncT* __restrict__ d_enc)
+    acn_field_weights w, const float4* __restrict__ d_rgb_sigma, acn_field_grads g, DEncT* __restrict__ d_enc,
+    const int32_t* __restrict__ range)
 {
     extern __shared__ __align__(16) float smem[];
+    if (range) {            // rows [range[0], range[1]) only: P was just the launch's upper bound
+        const int64_t r0 = __ldg(range);
+        P = __ldg(range + 1) - r0;
+        enc += r0 * d.E; dirs += r0 * dstride; d_rgb_sigma += r0;
+        if (d_enc) d_enc += r0 * d.E;
+    }
     Smem s;
     carve(d, true, smem, &s);
     load_weights(w, d, s);
@@ -380,7 +392,8 @@ int field_grid(acn_ctx* ctx, int64_t P) {
 
 // ------------------------------------------------------------------------------- launchers
 int acn_field_fwd_fp32(acn_ctx* ctx, const void* enc, int enc_dtype, const float* dirs, int dirs_stride, int dirs_group,
-                       int64_t P, int E, int H, int G, int C, const acn_field_weights* w, float* rgb_sigma, cudaStream_t st) {
+                       int64_t P, int E, int H, int G, int C, const acn_field_weights* w, float* rgb_sigma, const int32_t* range,
+                       cudaStream_t st) {
     FieldDims d;
     int rc = make_dims("acn_field_fwd", E, H, G, C, &d);
     if (rc) return rc;
@@ -389,11 +402,11 @@ int acn_field_fwd_fp32(acn_ctx* ctx, const void* enc, int enc_dtype, const float
     if (enc_dtype == ACN_F32) {
         ACN_CUDA(cudaFuncSetAttribute(k_field_fwd_fp32<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_field_fwd_fp32<float><<<field_grid(ctx, P), NT, smem, st>>>((const float*)enc, dirs, dirs_stride, dirs_group, P, d, *w,
-                                                                     (float4*)rgb_sigma);
+                                                                     (float4*)rgb_sigma, range);
     } else {
         ACN_CUDA(cudaFuncSetAttribute(k_field_fwd_fp32<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_field_fwd_fp32<__half><<<field_grid(ctx, P), NT, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, d, *w,
-                                                                      (float4*)rgb_sigma);
+                                                                      (float4*)rgb_sigma, range);
     }
     ACN_CHECK_LAUNCH();
     return ACN_OK;
@@ -401,7 +414,7 @@ int acn_field_fwd_fp32(acn_ctx* ctx, const void* enc, int enc_dtype, const float
 
 int acn_field_bwd_fp32(acn_ctx* ctx, const void* enc, int enc_dtype, const float* dirs, int dirs_stride, int dirs_group,
                        int64_t P, int E, int H, int G, int C, const acn_field_weights* w, const float* d_rgb_sigma,
-                       const acn_field_grads* g, void* d_enc, int d_enc_dtype, cudaStream_t st) {
+                       const acn_field_grads* g, void* d_enc, int d_enc_dtype, const int32_t* range, cudaStream_t st) {
     FieldDims d;
     int rc = make_dims("acn_field_bwd", E, H, G, C, &d);
     if (rc) return rc;
@@ -412,7 +425,7 @@ int acn_field_bwd_fp32(acn_ctx* ctx, const void* enc, int enc_dtype, const float
     do {                                                                                                                 \
         ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_fp32<ET, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_field_bwd_fp32<ET, DT><<<grid, NT, smem, st>>>((const ET*)enc, dirs, dirs_stride, dirs_group, P, d, *w,         \
-                                                         (const float4*)d_rgb_sigma, *g, (DT*)d_enc);                    \
+                                                         (const float4*)d_rgb_sigma, *g, (DT*)d_enc, range);             \
     } while (0)
     if (enc_dtype == ACN_F32) { if (d_enc_dtype == ACN_F32) LAUNCH(float, float); else LAUNCH(float, __half); }
     else                      { if (d_enc_dtype == ACN_F32) LAUNCH(__half, float); else LAUNCH(__half, __half); }

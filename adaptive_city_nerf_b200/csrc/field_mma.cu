@@ -340,9 +340,14 @@ __device__ __forceinline__ void epi_hidden_tmem(uint32_t acc) {
 template <int E, bool TRACE>
 __global__ void __launch_bounds__(FWG * 128, 1) k_field_fwd_mma(
     const __half* __restrict__ enc, const float* __restrict__ dirs, int dstride, int dgroup, int64_t P, int G,
-    acn_field_weights w, float4* __restrict__ rgb_sigma, long long* __restrict__ trace)
+    acn_field_weights w, float4* __restrict__ rgb_sigma, long long* __restrict__ trace, const int32_t* __restrict__ range)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if (range) {            // rows [range[0], range[1]) only (an expert's bucket): P was just the launch's upper bound
+        const int64_t r0 = __ldg(range);
+        P = __ldg(range + 1) - r0;
+        enc += r0 * E; dirs += r0 * dstride; rgb_sigma += r0;
+    }
     using M = FwdMap<E>;
     constexpr WMap wm = wmap(E);
     constexpr int EC = E / 8;
@@ -524,7 +529,9 @@ __device__ __forceinline__ float grad_scale_from_max(float mx) {
     return ldexpf(1.0f, e);
 }
 
-__global__ void __launch_bounds__(256) k_absmax(const float4* __restrict__ x, int64_t n4, unsigned int* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_absmax(const float4* __restrict__ x, int64_t n4, unsigned int* __restrict__ out,
+                                                const int32_t* __restrict__ range) {
+    if (range) { const int64_t r0 = __ldg(range); x += r0; n4 = __ldg(range + 1) - r0; }
     float m = 0.0f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 v = ld_stream_f4(x + i);
@@ -561,9 +568,16 @@ template <int E, bool TRACE, bool SCAT>
 __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
     const __half* __restrict__ enc, const float* __restrict__ dirs, int dstride, int dgroup, int64_t P, int G,
     acn_field_weights w, const float4* __restrict__ d_rgb_sigma, const unsigned int* __restrict__ absmax_bits,
-    acn_field_grads g, float* __restrict__ d_enc, long long* __restrict__ trace, ScatterArgs sc)
+    acn_field_grads g, float* __restrict__ d_enc, long long* __restrict__ trace, ScatterArgs sc, const int32_t* __restrict__ range)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if (range) {            // rows [range[0], range[1]) only (an expert's bucket): P was just the launch's upper bound
+        const int64_t r0 = __ldg(range);
+        P = __ldg(range + 1) - r0;
+        enc += r0 * E; dirs += r0 * dstride; d_rgb_sigma += r0;
+        if (d_enc) d_enc += r0 * E;
+        if (sc.x) sc.x += r0 * sc.xs;
+    }
     using M = BwdMap<E>;
     using SM = SlotMap<E>;
     constexpr WMap wm = wmap(E);
@@ -974,7 +988,7 @@ constexpr bool kTraceBuild = false;
 
 template <int E>
 int launch_fwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride, int dirs_group, int64_t P, int G,
-               const acn_field_weights* w, float* rgb_sigma, cudaStream_t st) {
+               const acn_field_weights* w, float* rgb_sigma, const int32_t* range, cudaStream_t st) {
     constexpr uint32_t smem = FwdMap<E>::bytes;
     ACN_REQUIRE((int)smem <= ctx->max_smem_optin, ACN_EUNSUPPORTED, "acn_field_fwd(f16): needs %u B shared memory", smem);
     const int64_t ntiles = (P + TM - 1) / TM;
@@ -983,11 +997,11 @@ int launch_fwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride
     if (kTraceBuild && g_field_trace && E == 32) {          // the timeline build of the kernel (tools/field_trace.py)
         ACN_CUDA(cudaFuncSetAttribute(k_field_fwd_mma<32, kTraceBuild>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_field_fwd_mma<32, kTraceBuild><<<(int)grid, FWG * 128, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
-                                                                       (float4*)rgb_sigma, g_field_trace);
+                                                                       (float4*)rgb_sigma, g_field_trace, range);
     } else {
         ACN_CUDA(cudaFuncSetAttribute(k_field_fwd_mma<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_field_fwd_mma<E, false><<<(int)grid, FWG * 128, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
-                                                                       (float4*)rgb_sigma, nullptr);
+                                                                       (float4*)rgb_sigma, nullptr, range);
     }
     ACN_CHECK_LAUNCH();
     return ACN_OK;
@@ -996,7 +1010,7 @@ int launch_fwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride
 template <int E>
 int launch_bwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride, int dirs_group, int64_t P, int G,
                const acn_field_weights* w, const float* d_rgb_sigma, const unsigned int* absmax, const acn_field_grads* g,
-               float* d_enc, const ScatterArgs* sc, cudaStream_t st) {
+               float* d_enc, const ScatterArgs* sc, const int32_t* range, cudaStream_t st) {
     constexpr uint32_t smem = BwdMap<E>::bytes;
     ACN_REQUIRE((int)smem <= ctx->max_smem_optin, ACN_EUNSUPPORTED, "acn_field_bwd(f16): needs %u B shared memory", smem);
     const int64_t ntiles = (P + TM - 1) / TM;
@@ -1007,18 +1021,18 @@ int launch_bwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride
         if constexpr (E <= 32) {             // the fused table scatter: E = 2 L, L <= 16
             ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<E, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_field_bwd_mma<E, false, true><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
-                                                                                 (const float4*)d_rgb_sigma, absmax, *g, nullptr, nullptr, *sc);
+                                                                                 (const float4*)d_rgb_sigma, absmax, *g, nullptr, nullptr, *sc, range);
         } else {
             ACN_REQUIRE(false, ACN_EUNSUPPORTED, "acn_render_expert_bwd: encoding width %d > 32", E);
         }
     } else if (kTraceBuild && g_field_trace && E == 32) {          // the timeline build of the kernel (tools/field_trace.py --bwd)
         ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<32, kTraceBuild, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_field_bwd_mma<32, kTraceBuild, false><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
-                                                                              (const float4*)d_rgb_sigma, absmax, *g, d_enc, g_field_trace, none);
+                                                                              (const float4*)d_rgb_sigma, absmax, *g, d_enc, g_field_trace, none, range);
     } else {
         ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<E, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_field_bwd_mma<E, false, false><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
-                                                                              (const float4*)d_rgb_sigma, absmax, *g, d_enc, nullptr, none);
+                                                                              (const float4*)d_rgb_sigma, absmax, *g, d_enc, nullptr, none, range);
     }
     ACN_CHECK_LAUNCH();
     return ACN_OK;
@@ -1026,11 +1040,11 @@ int launch_bwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride
 
 // loss scale: max |dL/dy| over the batch -> one word of context scratch (a ring, so calls in flight on different
 // streams do not share a word)
-int absmax_word(acn_ctx* ctx, const char* fn, const float* d_rgb_sigma, int64_t P, cudaStream_t st, unsigned int** out) {
+int absmax_word(acn_ctx* ctx, const char* fn, const float* d_rgb_sigma, int64_t P, const int32_t* range, cudaStream_t st, unsigned int** out) {
     unsigned int* slot = acn_scratch_word(ctx);
     ACN_REQUIRE(slot != nullptr, ACN_ECUDA, "%s(f16): no context scratch", fn);
     ACN_CUDA(cudaMemsetAsync(slot, 0, sizeof(unsigned int), st));
-    k_absmax<<<acn_grid_1d(P, 256 * 8, (int64_t)ctx->sm_count * 8), 256, 0, st>>>((const float4*)d_rgb_sigma, P, slot);
+    k_absmax<<<acn_grid_1d(P, 256 * 8, (int64_t)ctx->sm_count * 8), 256, 0, st>>>((const float4*)d_rgb_sigma, P, slot, range);
     ACN_CHECK_LAUNCH();
     *out = slot;
     return ACN_OK;
@@ -1047,38 +1061,40 @@ extern "C" int acn_debug_field_trace(acn_ctx* ctx, long long* trace_or_null) {
 #endif
 
 int acn_field_fwd_tc(acn_ctx* ctx, const void* enc, int enc_dtype, const float* dirs, int dirs_stride, int dirs_group,
-                     int64_t P, int E, int H, int G, int C, const acn_field_weights* w, float* rgb_sigma, cudaStream_t st) {
+                     int64_t P, int E, int H, int G, int C, const acn_field_weights* w, float* rgb_sigma, const int32_t* range,
+                     cudaStream_t st) {
     int rc = check_dims("acn_field_fwd", enc_dtype, E, H, G, C, enc);
     if (rc) return rc;
     switch (E) {
-        case 16: return launch_fwd<16>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, rgb_sigma, st);
-        case 32: return launch_fwd<32>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, rgb_sigma, st);
-        case 48: return launch_fwd<48>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, rgb_sigma, st);
-        default: return launch_fwd<64>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, rgb_sigma, st);
+        case 16: return launch_fwd<16>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, rgb_sigma, range, st);
+        case 32: return launch_fwd<32>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, rgb_sigma, range, st);
+        case 48: return launch_fwd<48>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, rgb_sigma, range, st);
+        default: return launch_fwd<64>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, rgb_sigma, range, st);
     }
 }
 
 int acn_field_bwd_tc(acn_ctx* ctx, const void* enc, int enc_dtype, const float* dirs, int dirs_stride, int dirs_group,
                      int64_t P, int E, int H, int G, int C, const acn_field_weights* w, const float* d_rgb_sigma,
-                     const acn_field_grads* g, float* d_enc, cudaStream_t st) {
+                     const acn_field_grads* g, float* d_enc, const int32_t* range, cudaStream_t st) {
     int rc = check_dims("acn_field_bwd", enc_dtype, E, H, G, C, enc);
     if (rc) return rc;
     ACN_REQUIRE(((uintptr_t)d_enc & 15) == 0, ACN_EINVAL, "acn_field_bwd(f16): d_enc must be 16-byte aligned");
     unsigned int* slot = nullptr;
-    rc = absmax_word(ctx, "acn_field_bwd", d_rgb_sigma, P, st, &slot);
+    rc = absmax_word(ctx, "acn_field_bwd", d_rgb_sigma, P, range, st, &slot);
     if (rc) return rc;
     switch (E) {
-        case 16: return launch_bwd<16>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, nullptr, st);
-        case 32: return launch_bwd<32>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, nullptr, st);
-        case 48: return launch_bwd<48>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, nullptr, st);
-        default: return launch_bwd<64>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, nullptr, st);
+        case 16: return launch_bwd<16>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, nullptr, range, st);
+        case 32: return launch_bwd<32>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, nullptr, range, st);
+        case 48: return launch_bwd<48>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, nullptr, range, st);
+        default: return launch_bwd<64>(ctx, enc, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, d_enc, nullptr, range, st);
     }
 }
 
 // Fully fused backward of one expert on a batch of points (SURVEY 8b acn_render_expert_bwd): fused MLP backward +
 // hash-table gradient scatter in ONE kernel; d_enc never exists in HBM.
 extern "C" int acn_render_expert_bwd(acn_ctx* ctx, const float* x_or_null, int x_stride, const float* rays8_or_null,
-                                     const float* t_vals_or_null, int64_t P, int S, const float* box6_or_null, int L, int F,
+                                     const float* t_vals_or_null, int64_t P, int S, const int32_t* range_or_null,
+                                     const float* box6_or_null, int L, int F,
                                      int log2T, const int32_t* res, int interp, const void* enc_f16, const float* dirs,
                                      int dirs_stride, int dirs_group, int H, int G, int C, const acn_field_weights* w,
                                      const float* d_rgb_sigma, const acn_field_grads* g, float* dtable, acn_stream stream) {
@@ -1095,6 +1111,7 @@ extern "C" int acn_render_expert_bwd(acn_ctx* ctx, const float* x_or_null, int x
     const bool from_rays = rays8_or_null != nullptr;
     ACN_REQUIRE(from_rays ? (t_vals_or_null && S >= 1 && P % S == 0) : (x_or_null && x_stride >= 3), ACN_EINVAL,
                 "%s: give either x (P,>=3) or rays8 + t_vals with P = N*S", fn);
+    ACN_REQUIRE(!range_or_null || (!from_rays && dirs_group == 1), ACN_EINVAL, "%s: a row range needs explicit positions and per-point directions", fn);
     ACN_REQUIRE(enc_f16 && dirs && d_rgb_sigma && dtable, ACN_EINVAL, "%s: null buffer", fn);
     ACN_REQUIRE((((uintptr_t)d_rgb_sigma | (uintptr_t)dtable) & 15) == 0, ACN_EINVAL, "%s: d_rgb_sigma / dtable misaligned", fn);
     const int E = L * F;
@@ -1102,9 +1119,9 @@ extern "C" int acn_render_expert_bwd(acn_ctx* ctx, const float* x_or_null, int x
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned int* slot = nullptr;
-    rc = absmax_word(ctx, fn, d_rgb_sigma, P, st, &slot);
+    rc = absmax_word(ctx, fn, d_rgb_sigma, P, range_or_null, st, &slot);
     if (rc) return rc;
     const ScatterArgs sc{ from_rays ? nullptr : x_or_null, x_stride, rays8_or_null, t_vals_or_null, S, box6_or_null, dtable, L, log2T, res, interp };
-    if (E == 16) return launch_bwd<16>(ctx, enc_f16, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, nullptr, &sc, st);
-    return launch_bwd<32>(ctx, enc_f16, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, nullptr, &sc, st);
+    if (E == 16) return launch_bwd<16>(ctx, enc_f16, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, nullptr, &sc, range_or_null, st);
+    return launch_bwd<32>(ctx, enc_f16, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, nullptr, &sc, range_or_null, st);
 }

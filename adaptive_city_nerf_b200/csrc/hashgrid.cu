@@ -44,22 +44,11 @@ template <> __device__ __forceinline__ float to_out<float>(float v) { return v; 
 template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
 
 template <int F, typename OutT>
-__global__ void __launch_bounds__(256) k_hashgrid_fwd(
-    PosSrc pos, int64_t P, const float* __restrict__ box6,
+__device__ __forceinline__ void hashgrid_encode_point(
+    const PosSrc& pos, int64_t p, const float* __restrict__ box6,
     const float* __restrict__ table, int L, int log2T, const int32_t* __restrict__ res, int interp,
     OutT* __restrict__ out, int32_t* __restrict__ idx_out)
 {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos.ray_major_dev ? (__ldg(pos.ray_major_dev) != 0) : (pos.ray_major != 0)) {
-        // frames (consecutive rays = adjacent pixels): a warp takes ONE sample of 32 neighbouring rays, so its lanes
-        // sit in the same or neighbouring cells up to the levels whose cells are as small as a pixel footprint
-        const int sgroups = (pos.S + 7) / 8;
-        const int64_t r = (int64_t)(blockIdx.x / sgroups) * 32 + (threadIdx.x & 31);
-        const int si = (blockIdx.x % sgroups) * 8 + (threadIdx.x >> 5);
-        if (si >= pos.S) return;
-        p = r * pos.S + si;
-    }
-    if (p >= P) return;
     float px, py, pz;
     load_pos(pos, p, px, py, pz);
     if (box6) {
@@ -145,6 +134,35 @@ __global__ void __launch_bounds__(256) k_hashgrid_fwd(
     }
 }
 
+// Thread per point.  Rows: all of [0, P), or -- `range` (device, 2 int32) given -- rows [range[0], range[1]) with P only
+// an upper bound on their number (the routed path: an expert's bucket, whose size the host never reads); the grid is
+// then capped and strides.
+template <int F, typename OutT>
+__global__ void __launch_bounds__(256) k_hashgrid_fwd(
+    PosSrc pos, int64_t P, const int32_t* __restrict__ range, const float* __restrict__ box6,
+    const float* __restrict__ table, int L, int log2T, const int32_t* __restrict__ res, int interp,
+    OutT* __restrict__ out, int32_t* __restrict__ idx_out)
+{
+    if (range) {
+        const int64_t r0 = __ldg(range), r1 = __ldg(range + 1);
+        for (int64_t p = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < r1; p += (int64_t)gridDim.x * blockDim.x)
+            hashgrid_encode_point<F, OutT>(pos, p, box6, table, L, log2T, res, interp, out, idx_out);
+        return;
+    }
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos.ray_major_dev ? (__ldg(pos.ray_major_dev) != 0) : (pos.ray_major != 0)) {
+        // frames (consecutive rays = adjacent pixels): a warp takes ONE sample of 32 neighbouring rays, so its lanes
+        // sit in the same or neighbouring cells up to the levels whose cells are as small as a pixel footprint
+        const int sgroups = (pos.S + 7) / 8;
+        const int64_t r = (int64_t)(blockIdx.x / sgroups) * 32 + (threadIdx.x & 31);
+        const int si = (blockIdx.x % sgroups) * 8 + (threadIdx.x >> 5);
+        if (si >= pos.S) return;
+        p = r * pos.S + si;
+    }
+    if (p >= P) return;
+    hashgrid_encode_point<F, OutT>(pos, p, box6, table, L, log2T, res, interp, out, idx_out);
+}
+
 template <int F>
 __device__ __forceinline__ void scatter_add(float* __restrict__ t, uint32_t row, const float* g, float w) {
     if constexpr (F == 2) {
@@ -162,8 +180,13 @@ template <> __device__ __forceinline__ float from_in<float>(float v) { return v;
 template <> __device__ __forceinline__ float from_in<__half>(__half v) { return __half2float(v); }
 
 template <int F, typename InT>
+__device__ __forceinline__ void hashgrid_scatter_point_level(
+    const PosSrc& pos, int64_t p, int l, const float* __restrict__ box6, int L, int log2T,
+    const int32_t* __restrict__ res, int interp, const InT* __restrict__ dout, float* __restrict__ dtable);
+
+template <int F, typename InT>
 __global__ void __launch_bounds__(256) k_hashgrid_bwd(
-    PosSrc pos, int64_t P, const float* __restrict__ box6, int L, int log2T,
+    PosSrc pos, int64_t P, const int32_t* __restrict__ range, const float* __restrict__ box6, int L, int log2T,
     const int32_t* __restrict__ res, int interp, const InT* __restrict__ dout, float* __restrict__ dtable)
 {
     // Blocks are visited in a scrambled order (blockIdx * prime mod gridDim, a bijection because the prime exceeds
@@ -171,10 +194,18 @@ __global__ void __launch_bounds__(256) k_hashgrid_bwd(
     // the same few hundred rows of the coarse levels and serialise in the L2 atomic units (measured: 21.8 ms for a
     // routed batch in bucket order vs 8.6 ms for the same points shuffled).
     const int64_t blk = (int64_t)(((uint64_t)blockIdx.x * 2654435761ull) % (uint64_t)gridDim.x);
-    int64_t idx = blk * blockDim.x + threadIdx.x;
-    if (idx >= P * L) return;
-    int64_t p = idx / L;
-    int l = (int)(idx - p * L);
+    int64_t r0 = 0, Pn = P;
+    if (range) { r0 = __ldg(range); Pn = __ldg(range + 1) - r0; }      // rows [range[0], range[1]); P is then only a bound
+    for (int64_t idx = blk * blockDim.x + threadIdx.x; idx < Pn * L; idx += (int64_t)gridDim.x * blockDim.x)
+        hashgrid_scatter_point_level<F, InT>(pos, r0 + idx / L, (int)(idx % L), box6, L, log2T, res, interp, dout, dtable);
+}
+
+template <int F, typename InT>
+__device__ __forceinline__ void hashgrid_scatter_point_level(
+    const PosSrc& pos, int64_t p, int l, const float* __restrict__ box6, int L, int log2T,
+    const int32_t* __restrict__ res, int interp, const InT* __restrict__ dout, float* __restrict__ dtable)
+{
+    const int64_t idx = p * L + l;
     float g[F];
     bool any = false;
 #pragma unroll
@@ -296,13 +327,22 @@ __global__ void __launch_bounds__(256) k_hashgrid_bwd_march(
 // cross-check; measured on the 4-expert routed step: 11.6 ms -> see DESIGN.md.)
 template <typename InT>
 __global__ void __launch_bounds__(256) k_hashgrid_bwd_march_pts(
-    const float* __restrict__ x, int xs, int64_t P, int seg,
+    const float* __restrict__ x, int xs, int64_t P, const int32_t* __restrict__ range, int seg,
     const float* __restrict__ box6, int L, int log2T, const int32_t* __restrict__ res, int interp,
     const InT* __restrict__ dout, float* __restrict__ dtable)
 {
+    if (range) {            // rows [range[0], range[1]) of x / dout; P is then only an upper bound on their number
+        const int64_t r0 = __ldg(range);
+        P = __ldg(range + 1) - r0;
+        x += r0 * xs;
+        dout += r0 * L * 2;
+    }
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t grp = gid >> 4;
     const int l = (int)(gid & 15);
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nseg = (P + seg - 1) / seg;
+  for (int64_t wp = gid >> 5; 2 * wp < nseg; wp += nwarps) {      // a warp takes two segments per round (warp-uniform trip count)
+    const int64_t grp = 2 * wp + ((gid >> 4) & 1);
     const int64_t row0 = grp * seg;
     const int n = row0 < P ? (int)((P - row0) < seg ? (P - row0) : seg) : 0;   // uniform over the 16-lane group
     const bool on = l < L;
@@ -355,6 +395,7 @@ __global__ void __launch_bounds__(256) k_hashgrid_bwd_march_pts(
         }
     }
     if (have) scatter_cell_f2(lt, cx, cy, cz, mask, acc);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ C ABI
@@ -376,7 +417,13 @@ static int check_grid_args(const char* fn, int64_t P, int xs, int L, int F, int 
         default: { constexpr int FF = 8; CALL; } break; \
     }
 
-static int hashgrid_fwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P, const float* box6_or_null,
+// launches over a device-side row range stride a capped grid (the host does not know how many rows there are)
+static int range_grid(acn_ctx* ctx, int64_t blocks) {
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+static int hashgrid_fwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P, const int32_t* range, const float* box6_or_null,
                              const float* table, int L, int F, int log2T, const int32_t* res, int interp,
                              void* out, int out_dtype, int32_t* idx_out_or_null, acn_stream stream) {
     ACN_CHECK_CTX(ctx);
@@ -388,20 +435,22 @@ static int hashgrid_fwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P
     ACN_REQUIRE(((uintptr_t)table & 15) == 0 && ((uintptr_t)out & 7) == 0, ACN_EINVAL, "%s: misaligned table/out", fn);
     const int block = 256;
     // the ray-major grid covers the sample-major one too, so a launch whose mapping is decided on the device uses it
-    const int grid = (pos.ray_major || pos.ray_major_dev) ? (int)(((P / pos.S + 31) / 32) * ((pos.S + 7) / 8)) : acn_grid_1d(P, block);
+    ACN_REQUIRE(!range || pos.x, ACN_EINVAL, "%s: a row range needs explicit positions", fn);
+    const int grid = range ? range_grid(ctx, (P + block - 1) / block)
+                   : (pos.ray_major || pos.ray_major_dev) ? (int)(((P / pos.S + 31) / 32) * ((pos.S + 7) / 8)) : acn_grid_1d(P, block);
     cudaStream_t st = (cudaStream_t)stream;
     if (out_dtype == ACN_F32) {
-        DISPATCH_F(F, (k_hashgrid_fwd<FF, float><<<grid, block, 0, st>>>(pos, P, box6_or_null, table, L, log2T, res,
+        DISPATCH_F(F, (k_hashgrid_fwd<FF, float><<<grid, block, 0, st>>>(pos, P, range, box6_or_null, table, L, log2T, res,
                                                                         interp, (float*)out, idx_out_or_null)));
     } else {
-        DISPATCH_F(F, (k_hashgrid_fwd<FF, __half><<<grid, block, 0, st>>>(pos, P, box6_or_null, table, L, log2T, res,
+        DISPATCH_F(F, (k_hashgrid_fwd<FF, __half><<<grid, block, 0, st>>>(pos, P, range, box6_or_null, table, L, log2T, res,
                                                                          interp, (__half*)out, idx_out_or_null)));
     }
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }
 
-static int hashgrid_bwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P, const float* box6_or_null, int L,
+static int hashgrid_bwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P, const int32_t* range, const float* box6_or_null, int L,
                              int F, int log2T, const int32_t* res, int interp, const void* dout, int dout_dtype,
                              float* dtable, acn_stream stream, bool plain = false) {
     ACN_CHECK_CTX(ctx);
@@ -415,42 +464,45 @@ static int hashgrid_bwd_impl(acn_ctx* ctx, const char* fn, PosSrc pos, int64_t P
     if (pos.x && F == 2 && L <= 16 && interp != ACN_INTERP_NEAREST && !plain) {
         ACN_REQUIRE(((uintptr_t)dout & 7) == 0, ACN_EINVAL, "%s: misaligned dout", fn);
         const int seg = 64;
-        const int grid_m = acn_grid_1d(((P + seg - 1) / seg) * 16, 256);
+        const int64_t blocks_m = (((P + seg - 1) / seg) * 16 + 255) / 256;
+        const int grid_m = range ? range_grid(ctx, blocks_m) : acn_grid_1d(blocks_m * 256, 256);
         if (dout_dtype == ACN_F32)
-            k_hashgrid_bwd_march_pts<float><<<grid_m, 256, 0, st>>>(pos.x, pos.xs, P, seg, box6_or_null, L, log2T, res, interp,
+            k_hashgrid_bwd_march_pts<float><<<grid_m, 256, 0, st>>>(pos.x, pos.xs, P, range, seg, box6_or_null, L, log2T, res, interp,
                                                                    (const float*)dout, dtable);
         else
-            k_hashgrid_bwd_march_pts<__half><<<grid_m, 256, 0, st>>>(pos.x, pos.xs, P, seg, box6_or_null, L, log2T, res, interp,
+            k_hashgrid_bwd_march_pts<__half><<<grid_m, 256, 0, st>>>(pos.x, pos.xs, P, range, seg, box6_or_null, L, log2T, res, interp,
                                                                     (const __half*)dout, dtable);
         ACN_CHECK_LAUNCH();
         return ACN_OK;
     }
     const int block = 256;
-    const int grid = acn_grid_1d(P * L, block);
+    ACN_REQUIRE(!range || pos.x, ACN_EINVAL, "%s: a row range needs explicit positions", fn);
+    const int grid = range ? range_grid(ctx, (P * L + block - 1) / block) : acn_grid_1d(P * L, block);
     if (dout_dtype == ACN_F32) {
-        DISPATCH_F(F, (k_hashgrid_bwd<FF, float><<<grid, block, 0, st>>>(pos, P, box6_or_null, L, log2T, res, interp,
+        DISPATCH_F(F, (k_hashgrid_bwd<FF, float><<<grid, block, 0, st>>>(pos, P, range, box6_or_null, L, log2T, res, interp,
                                                                         (const float*)dout, dtable)));
     } else {
-        DISPATCH_F(F, (k_hashgrid_bwd<FF, __half><<<grid, block, 0, st>>>(pos, P, box6_or_null, L, log2T, res, interp,
+        DISPATCH_F(F, (k_hashgrid_bwd<FF, __half><<<grid, block, 0, st>>>(pos, P, range, box6_or_null, L, log2T, res, interp,
                                                                          (const __half*)dout, dtable)));
     }
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }
 
-extern "C" int acn_hashgrid_fwd(acn_ctx* ctx, const float* x, int64_t P, int x_stride, const float* box6_or_null,
-                                const float* table, int L, int F, int log2T, const int32_t* res, int interp,
-                                void* out, int out_dtype, int32_t* idx_out_or_null, acn_stream stream) {
+extern "C" int acn_hashgrid_fwd(acn_ctx* ctx, const float* x, int64_t P, int x_stride, const int32_t* range_or_null,
+                                const float* box6_or_null, const float* table, int L, int F, int log2T, const int32_t* res,
+                                int interp, void* out, int out_dtype, int32_t* idx_out_or_null, acn_stream stream) {
     PosSrc pos{ x, x_stride, nullptr, nullptr, 0, 0, nullptr };
-    return hashgrid_fwd_impl(ctx, "acn_hashgrid_fwd", pos, P, box6_or_null, table, L, F, log2T, res, interp, out, out_dtype,
-                             idx_out_or_null, stream);
+    return hashgrid_fwd_impl(ctx, "acn_hashgrid_fwd", pos, P, range_or_null, box6_or_null, table, L, F, log2T, res, interp, out,
+                             out_dtype, idx_out_or_null, stream);
 }
 
-extern "C" int acn_hashgrid_bwd(acn_ctx* ctx, const float* x, int64_t P, int x_stride, const float* box6_or_null, int L,
-                                int F, int log2T, const int32_t* res, int interp, const void* dout, int dout_dtype,
-                                float* dtable, acn_stream stream) {
+extern "C" int acn_hashgrid_bwd(acn_ctx* ctx, const float* x, int64_t P, int x_stride, const int32_t* range_or_null,
+                                const float* box6_or_null, int L, int F, int log2T, const int32_t* res, int interp,
+                                const void* dout, int dout_dtype, float* dtable, acn_stream stream) {
     PosSrc pos{ x, x_stride, nullptr, nullptr, 0, 0, nullptr };
-    return hashgrid_bwd_impl(ctx, "acn_hashgrid_bwd", pos, P, box6_or_null, L, F, log2T, res, interp, dout, dout_dtype, dtable, stream);
+    return hashgrid_bwd_impl(ctx, "acn_hashgrid_bwd", pos, P, range_or_null, box6_or_null, L, F, log2T, res, interp, dout, dout_dtype,
+                             dtable, stream);
 }
 
 extern "C" int acn_hashgrid_fwd_rays(acn_ctx* ctx, const float* rays8, const float* t_vals, int64_t N, int S,
@@ -459,7 +511,7 @@ extern "C" int acn_hashgrid_fwd_rays(acn_ctx* ctx, const float* rays8, const flo
                                      const int32_t* ray_major_dev_or_null, acn_stream stream) {
     ACN_REQUIRE(N >= 0 && S >= 1, ACN_EINVAL, "acn_hashgrid_fwd_rays: bad N / S");
     PosSrc pos{ nullptr, 0, rays8, t_vals, S, ray_major ? 1 : 0, ray_major_dev_or_null };
-    return hashgrid_fwd_impl(ctx, "acn_hashgrid_fwd_rays", pos, N * S, box6_or_null, table, L, F, log2T, res, interp, out,
+    return hashgrid_fwd_impl(ctx, "acn_hashgrid_fwd_rays", pos, N * S, nullptr, box6_or_null, table, L, F, log2T, res, interp, out,
                              out_dtype, nullptr, stream);
 }
 
@@ -487,7 +539,7 @@ extern "C" int acn_hashgrid_bwd_rays(acn_ctx* ctx, const float* rays8, const flo
         return ACN_OK;
     }
     PosSrc pos{ nullptr, 0, rays8, t_vals, S, 0, nullptr };
-    return hashgrid_bwd_impl(ctx, "acn_hashgrid_bwd_rays", pos, N * S, box6_or_null, L, F, log2T, res, interp, dout, dout_dtype,
+    return hashgrid_bwd_impl(ctx, "acn_hashgrid_bwd_rays", pos, N * S, nullptr, box6_or_null, L, F, log2T, res, interp, dout, dout_dtype,
                              dtable, stream);
 }
 
@@ -495,6 +547,6 @@ extern "C" int acn_hashgrid_bwd_plain(acn_ctx* ctx, const float* x, int64_t P, i
                                       int F, int log2T, const int32_t* res, int interp, const void* dout, int dout_dtype,
                                       float* dtable, acn_stream stream) {
     PosSrc pos{ x, x_stride, nullptr, nullptr, 0, 0, nullptr };
-    return hashgrid_bwd_impl(ctx, "acn_hashgrid_bwd_plain", pos, P, box6_or_null, L, F, log2T, res, interp, dout, dout_dtype, dtable,
+    return hashgrid_bwd_impl(ctx, "acn_hashgrid_bwd_plain", pos, P, nullptr, box6_or_null, L, F, log2T, res, interp, dout, dout_dtype, dtable,
                              stream, true);
 }

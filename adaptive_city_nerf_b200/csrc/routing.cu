@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route_samples(
     int K, float margin, int ray_major, const int32_t* __restrict__ ray_major_dev, uint16_t* __restrict__ support,
     int32_t* __restrict__ counts,
     const int32_t* __restrict__ offsets, int32_t* __restrict__ cursor, int32_t* __restrict__ sel, float* __restrict__ xd_out,
-    float* __restrict__ w_out, const unsigned long long* __restrict__ row_base, const int32_t* __restrict__ row_off)
+    float* __restrict__ w_out, const unsigned long long* __restrict__ row_base, const int32_t* __restrict__ row_off,
+    const int32_t* __restrict__ row_limit)
 {
     extern __shared__ int s_k[];      // COUNT: K ints; BUCKET: ROUTE_WARPS * K ints
     constexpr int OFF = DIMS == 2 ? 1 : 0;
@@ -501,7 +502,9 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route_samples(
         if (k < K) {
             const bool in = (bits >> k) & 1u;
             const unsigned m = __ballot_sync(FULL, in);
-            if (in) {
+            // row_limit (capacity-bounded buckets: the host never read the counts, acn_bucket_plan clamped them to what
+            // fits): rows beyond an expert's share are dropped; the plan has raised the overflow flag
+            if (in && (!row_limit || s_k[warp * K + k] + __popc(m & ((1u << lane) - 1u)) < __ldg(row_limit + k))) {
                 const int idx = s_k[warp * K + k] + __popc(m & ((1u << lane) - 1u));
                 const int slot = __ldg(offsets + k) + idx;
                 sel[slot] = (int32_t)p;
@@ -518,25 +521,34 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route_samples(
     }
 }
 
+// Rows [0, M) of (y, w, sel), or -- `range` (device, 2 int32) given -- rows [range[0], range[1]) with M an upper bound on
+// their number (grid-stride).  y_base_off: y is addressed from row (range[0] - y_row0) when y_row0 is given (an owner's
+// buffer whose rows start elsewhere than the local bucket's).
 __global__ void k_blend_add(const float4* __restrict__ y, const float* __restrict__ w, const int32_t* __restrict__ sel,
-                            int64_t M, float4* __restrict__ out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M) return;
-    float4 v = y[i];
-    float ww = w ? w[i] : 1.0f;
-    int32_t p = sel[i];
-    float4 o = out[p];
-    o.x += v.x * ww; o.y += v.y * ww; o.z += v.z * ww; o.w += v.w * ww;
-    out[p] = o;
+                            int64_t M, const int32_t* __restrict__ range, const int32_t* __restrict__ y_row0, float4* __restrict__ out) {
+    int64_t r0 = 0, r1 = M;
+    if (range) { r0 = __ldg(range); r1 = __ldg(range + 1); }
+    const int64_t yoff = y_row0 ? (int64_t)__ldg(y_row0) - r0 : 0;
+    for (int64_t i = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = y[i + yoff];
+        float ww = w ? w[i] : 1.0f;
+        int32_t p = sel[i];
+        float4 o = out[p];
+        o.x += v.x * ww; o.y += v.y * ww; o.z += v.z * ww; o.w += v.w * ww;
+        out[p] = o;
+    }
 }
 
 __global__ void k_blend_bwd(const float4* __restrict__ d_out, const float* __restrict__ w, const int32_t* __restrict__ sel,
-                            int64_t M, float4* __restrict__ d_y) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M) return;
-    float4 g = d_out[sel[i]];
-    float ww = w ? w[i] : 1.0f;
-    d_y[i] = make_float4(g.x * ww, g.y * ww, g.z * ww, g.w * ww);
+                            int64_t M, const int32_t* __restrict__ range, const int32_t* __restrict__ y_row0, float4* __restrict__ d_y) {
+    int64_t r0 = 0, r1 = M;
+    if (range) { r0 = __ldg(range); r1 = __ldg(range + 1); }
+    const int64_t yoff = y_row0 ? (int64_t)__ldg(y_row0) - r0 : 0;
+    for (int64_t i = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 g = d_out[sel[i]];
+        float ww = w ? w[i] : 1.0f;
+        d_y[i + yoff] = make_float4(g.x * ww, g.y * ww, g.z * ww, g.w * ww);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ C ABI
@@ -634,13 +646,13 @@ template <bool BUCKET>
 static int launch_route_samples(const float* rays8, const float* t_vals, int64_t N, int S, const float* cen, int K, int dims,
                                 float margin, int ray_major, const int32_t* ray_major_dev, uint16_t* support, int32_t* counts,
                                 const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out,
-                                const unsigned long long* row_base, const int32_t* row_off, cudaStream_t st) {
+                                const unsigned long long* row_base, const int32_t* row_off, const int32_t* row_limit, cudaStream_t st) {
     const int64_t P = N * S;
     const int grid = (ray_major || ray_major_dev) ? (int)(((N + 31) / 32) * ((S + ROUTE_WARPS - 1) / ROUTE_WARPS)) : acn_grid_1d(P, ROUTE_THREADS);
     const size_t smem = (size_t)(BUCKET ? ROUTE_WARPS : 1) * K * sizeof(int);
 #define RS(D, MK) k_route_samples<D, MK, BUCKET><<<grid, ROUTE_THREADS, smem, st>>>(rays8, t_vals, P, S, cen, K, margin, ray_major, ray_major_dev, \
                                                                                   support, \
-                                                                                  counts, offsets, cursor, sel, xd_out, w_out, row_base, row_off)
+                                                                                  counts, offsets, cursor, sel, xd_out, w_out, row_base, row_off, row_limit)
     if (dims == 2) { if (K <= 4) RS(2, 4); else if (K <= 8) RS(2, 8); else RS(2, 16); }
     else           { if (K <= 4) RS(3, 4); else if (K <= 8) RS(3, 8); else RS(3, 16); }
 #undef RS
@@ -668,7 +680,7 @@ extern "C" int acn_route_count_rays(acn_ctx* ctx, const float* rays8, const floa
     ACN_REQUIRE(counts, ACN_EINVAL, "acn_route_count_rays: null counts");
     if (N == 0) return ACN_OK;
     launch_route_samples<false>(rays8, t_vals, N, S, centroids, K, dims, margin, ray_major, ray_major_dev_or_null, support_or_null, counts, nullptr, nullptr, nullptr,
-                                nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+                                nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }
@@ -677,7 +689,8 @@ extern "C" int acn_route_bucket_rays(acn_ctx* ctx, const float* rays8, const flo
                                      const float* centroids, int K, int dims, float margin, int ray_major,
                                      const int32_t* ray_major_dev_or_null, const uint16_t* support_or_null,
                                      const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out,
-                                     const uint64_t* row_base_or_null, const int32_t* row_off_or_null, acn_stream stream) {
+                                     const uint64_t* row_base_or_null, const int32_t* row_off_or_null,
+                                     const int32_t* row_limit_or_null, acn_stream stream) {
     ACN_CHECK_CTX(ctx);
     int rc = check_route_samples("acn_route_bucket_rays", rays8, t_vals, N, S, centroids, K, dims, margin);
     if (rc) return rc;
@@ -690,29 +703,65 @@ extern "C" int acn_route_bucket_rays(acn_ctx* ctx, const float* rays8, const flo
     launch_route_samples<true>(rays8, t_vals, N, S, centroids, K, dims, margin, ray_major, ray_major_dev_or_null,
                                const_cast<uint16_t*>(support_or_null), nullptr,
                                offsets, cursor, sel, xd_out, w_out, (const unsigned long long*)row_base_or_null, row_off_or_null,
-                               (cudaStream_t)stream);
+                               row_limit_or_null, (cudaStream_t)stream);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }
 
-extern "C" int acn_blend_add(acn_ctx* ctx, const float* y, const float* w, const int32_t* sel, int64_t M, float* out,
-                             acn_stream stream) {
+// Turns the device-side per-expert row counts of a routed batch into the bucket layout WITHOUT the host reading them
+// ("dispatch counts stay on device"): seg (K+1) = exclusive scan of the counts clamped to `cap` rows in
+// total, limit (K) = rows of each expert that fit, cursor (K) = 0 for the bucket pass, *overflow |= 1 when rows were cut.
+__global__ void k_bucket_plan(const int32_t* __restrict__ counts, int K, int64_t cap, int32_t* __restrict__ seg,
+                              int32_t* __restrict__ limit, int32_t* __restrict__ cursor, int32_t* __restrict__ overflow) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int64_t run = 0;
+    bool cut = false;
+    seg[0] = 0;
+    for (int k = 0; k < K; ++k) {
+        int64_t c = counts[k];
+        if (run + c > cap) { c = cap - run; cut = true; }
+        limit[k] = (int32_t)c;
+        cursor[k] = 0;
+        run += c;
+        seg[k + 1] = (int32_t)run;
+    }
+    if (cut && overflow) *overflow = 1;
+}
+
+extern "C" int acn_bucket_plan(acn_ctx* ctx, const int32_t* counts, int K, int64_t cap, int32_t* seg, int32_t* limit,
+                               int32_t* cursor, int32_t* overflow_or_null, acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    ACN_REQUIRE(counts && seg && limit && cursor && K >= 1 && cap >= 0 && cap < ((int64_t)1 << 31), ACN_EINVAL, "acn_bucket_plan: bad arguments");
+    k_bucket_plan<<<1, 32, 0, (cudaStream_t)stream>>>(counts, K, cap, seg, limit, cursor, overflow_or_null);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
+
+static int blend_grid(acn_ctx* ctx, int64_t M, bool ranged) {
+    const int64_t blocks = (M + 255) / 256, cap = (int64_t)ctx->sm_count * 16;
+    return (int)(blocks < 1 ? 1 : (ranged && blocks > cap ? cap : blocks));
+}
+
+extern "C" int acn_blend_add(acn_ctx* ctx, const float* y, const float* w, const int32_t* sel, int64_t M,
+                             const int32_t* range_or_null, const int32_t* y_row0_or_null, float* out, acn_stream stream) {
     ACN_CHECK_CTX(ctx);
     ACN_REQUIRE(M >= 0, ACN_EINVAL, "acn_blend_add: negative M");
     if (M == 0) return ACN_OK;
     ACN_REQUIRE(y && sel && out, ACN_EINVAL, "acn_blend_add: null buffer");
-    k_blend_add<<<acn_grid_1d(M, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)y, w, sel, M, (float4*)out);
+    k_blend_add<<<blend_grid(ctx, M, range_or_null != nullptr), 256, 0, (cudaStream_t)stream>>>((const float4*)y, w, sel, M, range_or_null,
+                                                                                               y_row0_or_null, (float4*)out);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }
 
-extern "C" int acn_blend_bwd(acn_ctx* ctx, const float* d_out, const float* w, const int32_t* sel, int64_t M, float* d_y,
-                             acn_stream stream) {
+extern "C" int acn_blend_bwd(acn_ctx* ctx, const float* d_out, const float* w, const int32_t* sel, int64_t M,
+                             const int32_t* range_or_null, const int32_t* y_row0_or_null, float* d_y, acn_stream stream) {
     ACN_CHECK_CTX(ctx);
     ACN_REQUIRE(M >= 0, ACN_EINVAL, "acn_blend_bwd: negative M");
     if (M == 0) return ACN_OK;
     ACN_REQUIRE(d_out && sel && d_y, ACN_EINVAL, "acn_blend_bwd: null buffer");
-    k_blend_bwd<<<acn_grid_1d(M, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_out, w, sel, M, (float4*)d_y);
+    k_blend_bwd<<<blend_grid(ctx, M, range_or_null != nullptr), 256, 0, (cudaStream_t)stream>>>((const float4*)d_out, w, sel, M, range_or_null,
+                                                                                               y_row0_or_null, (float4*)d_y);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }

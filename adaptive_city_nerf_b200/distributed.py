@@ -162,7 +162,7 @@ class _PeerCombine(torch.autograd.Function):
             if n:
                 yk = px.peer_y(owner)[ro:ro + n]
                 ops.check(ops.lib().acn_blend_add(ops.ctx(out.device), ops.ptr(yk), ops.ptr(wsel[lo:lo + n]), ops.ptr(sel[lo:lo + n]), n,
-                                                  ops.ptr(out), ops.stream(out.device)))
+                                                  None, None, ops.ptr(out), ops.stream(out.device)))
         ctx.px, ctx.M, ctx.plan = px, M, plan
         ctx.save_for_backward(sel, wsel)
         return out
@@ -177,7 +177,7 @@ class _PeerCombine(torch.autograd.Function):
             if n:
                 dyk = px.peer_dy(owner)[ro:ro + n]
                 ops.check(ops.lib().acn_blend_bwd(ops.ctx(g.device), ops.ptr(g), ops.ptr(wsel[lo:lo + n]), ops.ptr(sel[lo:lo + n]), n,
-                                                  ops.ptr(dyk), ops.stream(g.device)))
+                                                  None, None, ops.ptr(dyk), ops.stream(g.device)))
         px.h_dy.barrier()                                    # every home rank's dL/dy has landed in my dy
         return px.dy[:M].clone(), None, None, None, None, None, None
 

@@ -4,9 +4,11 @@ models/inr/meta_container.py:21-503).
 Routing (`_routing`, stage 5) runs in csrc/routing.cu with torch.cdist's exact rounding order,
 so the hard assignment and the soft support set are bit-exact w.r.t. the reference CPU path.
 The reference dispatches with K rounds of nonzero()/index_select()/index_add_() (one host sync
-per expert); here one kernel buckets all points for all experts on the device (the K counts
-come back in a single 4K-byte copy used to size the buffers), each expert runs its fused field
-kernels on its bucket, and a blend kernel accumulates `w_k * y_k` in expert order."""
+per expert).  Here the render path (`forward_rays`) never reads anything back: a count pass leaves
+the per-expert row counts on the device, `acn_bucket_plan` turns them into the bucket layout there,
+the bucket pass writes capacity-bounded buckets, every expert's kernels take their row range as a
+device pointer, and a blend kernel accumulates `w_k * y_k` in expert order.  (`forward(x)` on an
+explicit point list still sizes its buckets with one 4K-byte host read.)"""
 from __future__ import annotations
 
 from typing import Dict, List, Literal, Optional, OrderedDict, Tuple
@@ -103,6 +105,25 @@ class MetaContainer(MetaModule):
 
     #: the fused route-from-rays kernels keep one weight per expert in registers
     FUSED_ROUTE_MAX_EXPERTS = 16
+    #: rows the routed buckets are allocated for, as a multiple of the number of samples, when boundary_margin > 1 (a
+    #: sample inside the overlap band of a 2-D grid goes to 2-4 experts; with margin 1 every sample has exactly one
+    #: expert and the buckets are exact).  Rows that do not fit are dropped and `check_route_overflow()` reports it.
+    route_capacity_factor = 2.0
+
+    def _overflow_flag(self, device) -> torch.Tensor:
+        f = getattr(self, "_route_overflow", None)
+        if f is None or f.device != device:
+            f = self._route_overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        return f
+
+    def check_route_overflow(self) -> None:
+        """Raises if a routed batch since the last check needed more bucket rows than `route_capacity_factor` provides
+        (its overflowing rows were dropped).  Reads one device word: call it outside the steps you are timing."""
+        f = getattr(self, "_route_overflow", None)
+        if f is not None and int(f.item()) != 0:
+            f.zero_()
+            raise RuntimeError("routed buckets overflowed: raise MetaContainer.route_capacity_factor "
+                               f"(now {self.route_capacity_factor}); the affected batches dropped samples")
 
     def forward_rays(self, rays: torch.Tensor, t: torch.Tensor, params: Optional[OrderedDict] = None,
                      ray_major=False) -> torch.Tensor:
@@ -117,16 +138,31 @@ class MetaContainer(MetaModule):
         # ray_major (frames: consecutive rays = adjacent pixels) orders the buckets so that a warp of the experts' gathers
         # sees one sample of 32 neighbouring pixels; otherwise a ray's samples stay together (shuffled training rays).
         # bool, or a device flag from ops.rays_coherent_flag.
+        P = N * S
+        cap = P if self.boundary_margin <= 1.0 else int(min(float(K), float(self.route_capacity_factor)) * P)
         with torch.no_grad():
             counts, support = ops.route_count_rays(rays, t, self.centroids, dims, self.boundary_margin, want_support=True,
                                                    ray_major=ray_major)
-            cnt = counts.cpu()                                                   # the one host read: K ints
-            offsets = torch.zeros(K, dtype=torch.int32)
-            offsets[1:] = torch.cumsum(cnt, 0)[:-1].to(torch.int32)
-            sel, xd, wsel = ops.route_bucket_rays(rays, t, self.centroids, dims, self.boundary_margin,
-                                                  offsets.to(rays.device), int(cnt.sum()), support=support,
-                                                  ray_major=ray_major)
-        return self._evaluate_buckets(N * S, cnt, offsets, sel, xd, wsel, self._sub_params(params), rays.device).view(N, S, -1)
+            seg, limit, cursor = ops.bucket_plan(counts, cap, self._overflow_flag(rays.device))     # stays on the device
+            sel, xd, wsel = ops.route_bucket_rays(rays, t, self.centroids, dims, self.boundary_margin, seg, cap, support=support,
+                                                  ray_major=ray_major, row_limit=limit, cursor=cursor)
+        y = self._evaluate_segments(xd, seg, list(range(K)), self._sub_params(params))
+        return ops.BlendRangesFn.apply(y, wsel, sel, seg, P).view(N, S, -1)
+
+    def _evaluate_segments(self, xd: torch.Tensor, seg: torch.Tensor, expert_ids: List[int], sub_params: List) -> torch.Tensor:
+        """Experts `expert_ids` on the row ranges [seg[i], seg[i+1]) of xd (device-side ranges) -> (cap,4)."""
+        from .meta_ngp import autocast_half
+        subs = [self.submodules[k] for k in expert_ids]
+        for sub in subs:
+            sub._check_fused()
+        half = subs[0]._use_half(xd.device)
+        experts = [(sub.xyz_encoder.grid_spec(), sub.box6()) for sub in subs]
+        nodes = [ops.grad_node_of(sub.xyz_encoder.hash_table) for sub in subs]
+        flat = []
+        for sub, k in zip(subs, expert_ids):
+            flat.append(sub.xyz_encoder.hash_table)
+            flat += sub.fused_weights(sub_params[k])
+        return ops.RoutedFieldFn.apply(xd, seg, half, experts, nodes, *flat)
 
     def _routed(self, x: torch.Tensor, sub_params: List) -> torch.Tensor:
         N, K = x.shape[0], len(self.submodules)

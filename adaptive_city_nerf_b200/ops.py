@@ -157,7 +157,7 @@ def hashgrid_fwd(x: Tensor, table: Tensor, spec: GridSpec, box6: Optional[Tensor
     table = dev_f32(table, "hash_table")
     out = torch.empty(P, spec.L * spec.F, dtype=out_dtype, device=dev)
     idx = torch.zeros(P, spec.L, 8, dtype=torch.int32, device=dev) if want_idx else None
-    check(lib().acn_hashgrid_fwd(ctx(dev), ptr(x), P, x.stride(0) if P else 3, ptr(box6), ptr(table), spec.L, spec.F,
+    check(lib().acn_hashgrid_fwd(ctx(dev), ptr(x), P, x.stride(0) if P else 3, None, ptr(box6), ptr(table), spec.L, spec.F,
                                  spec.log2T, ptr(_grid_res(spec, dev)), spec.interp, ptr(out), _dt(out), ptr(idx),
                                  stream(dev)))
     return (out, idx) if want_idx else out
@@ -169,7 +169,7 @@ def hashgrid_bwd(x: Tensor, dout: Tensor, spec: GridSpec, box6: Optional[Tensor]
     dout = dout.contiguous()
     P = x.shape[0]
     dev = x.device
-    check(lib().acn_hashgrid_bwd(ctx(dev), ptr(x), P, x.stride(0) if P else 3, ptr(box6), spec.L, spec.F, spec.log2T,
+    check(lib().acn_hashgrid_bwd(ctx(dev), ptr(x), P, x.stride(0) if P else 3, None, ptr(box6), spec.L, spec.F, spec.log2T,
                                  ptr(_grid_res(spec, dev)), spec.interp, ptr(dout), _dt(dout), ptr(dtable), stream(dev)))
 
 
@@ -240,7 +240,7 @@ def field_fwd(enc: Tensor, dirs: Tensor, dirs_stride: int, dirs_group: int, ws: 
     enc = enc.contiguous()
     out = torch.empty(P, 4, dtype=torch.float32, device=dev)
     st = pack_weights(ws)
-    check(lib().acn_field_fwd(ctx(dev), ptr(enc), _dt(enc), ptr(dirs), dirs_stride, dirs_group, P, E, H, G, C, C_.byref(st),
+    check(lib().acn_field_fwd(ctx(dev), ptr(enc), _dt(enc), ptr(dirs), dirs_stride, dirs_group, P, None, E, H, G, C, C_.byref(st),
                               F16 if half else F32, ptr(out), stream(dev)))
     return out
 
@@ -264,7 +264,7 @@ def field_bwd(enc: Tensor, dirs: Tensor, dirs_stride: int, dirs_group: int, ws: 
     # ~1e-9 and would flush to zero in fp16 (the reference needs GradScaler for the same reason)
     d_enc = torch.empty(P, E, dtype=torch.float32, device=dev) if want_enc_grad else None
     wst, gst = pack_weights(ws), pack_weights(grads)
-    check(lib().acn_field_bwd(ctx(dev), ptr(enc), _dt(enc), ptr(dirs), dirs_stride, dirs_group, P, E, H, G, C,
+    check(lib().acn_field_bwd(ctx(dev), ptr(enc), _dt(enc), ptr(dirs), dirs_stride, dirs_group, P, None, E, H, G, C,
                               C_.byref(wst), F16 if half else F32, ptr(d_rgb_sigma), C_.byref(gst),
                               ptr(d_enc), F32, stream(dev)))
     return grads, d_enc
@@ -288,7 +288,7 @@ def render_expert_bwd(enc: Tensor, pos: Sequence[Tensor], dirs: Tensor, dirs_str
         x, xs, S = None, 3, t.shape[1]
     else:
         x, xs, rays, t, S = pos[0], pos[0].stride(0), None, None, 1
-    check(lib().acn_render_expert_bwd(ctx(dev), ptr(x), xs, ptr(rays), ptr(t), P, S, ptr(box6), spec.L, spec.F, spec.log2T,
+    check(lib().acn_render_expert_bwd(ctx(dev), ptr(x), xs, ptr(rays), ptr(t), P, S, None, ptr(box6), spec.L, spec.F, spec.log2T,
                                       ptr(_grid_res(spec, dev)), spec.interp, ptr(enc), ptr(dirs), dirs_stride, dirs_group,
                                       H, G, C, C_.byref(wst), ptr(d_rgb_sigma), C_.byref(gst), ptr(dtable), stream(dev)))
     return grads
@@ -526,9 +526,20 @@ def route_count_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, marg
     return (counts, support) if want_support else counts
 
 
+def bucket_plan(counts: Tensor, cap: int, overflow: Optional[Tensor] = None):
+    """Device-side bucket layout from device-side counts (acn_bucket_plan): -> seg (K+1,) int32 exclusive offsets clamped
+    to `cap` rows, limit (K,) rows per expert that fit, cursor (K,) zeros.  `overflow` (1,) int32 is set when rows were cut."""
+    K, dev = counts.shape[0], counts.device
+    seg = torch.empty(K + 1, dtype=torch.int32, device=dev)
+    limit = torch.empty(K, dtype=torch.int32, device=dev)
+    cursor = torch.empty(K, dtype=torch.int32, device=dev)
+    check(lib().acn_bucket_plan(ctx(dev), ptr(counts), K, int(cap), ptr(seg), ptr(limit), ptr(cursor), ptr(overflow), stream(dev)))
+    return seg, limit, cursor
+
+
 def route_bucket_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, margin: float, offsets: Tensor, total: int,
                       support: Optional[Tensor] = None, ray_major=False, row_base: Optional[Tensor] = None,
-                      row_off: Optional[Tensor] = None):
+                      row_off: Optional[Tensor] = None, row_limit: Optional[Tensor] = None, cursor: Optional[Tensor] = None):
     """-> sel (total,) int32 sample index, xd (total,6) [xyz, dir] rows, w (total,) blend weights; expert k's rows lie in
     [offsets[k], offsets[k] + counts[k])."""
     rays, t = dev_f32(rays, "rays"), dev_f32(t, "t_vals")
@@ -538,11 +549,12 @@ def route_bucket_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, mar
     sel = torch.empty(total, dtype=torch.int32, device=dev)
     xd = torch.empty(total, 6, dtype=torch.float32, device=dev) if row_base is None else None   # else: rows go to row_base[k]
     w = torch.empty(total, dtype=torch.float32, device=dev)
-    cursor = torch.zeros(K, dtype=torch.int32, device=dev)
+    if cursor is None:
+        cursor = torch.zeros(K, dtype=torch.int32, device=dev)
     assert row_base is None or (row_base.dtype == torch.int64 and row_off.dtype == torch.int32 and row_base.numel() == K == row_off.numel())
     check(lib().acn_route_bucket_rays(ctx(dev), ptr(rays), ptr(t), N, S, ptr(cen), K, dims, float(margin), *_ray_major_args(ray_major),
                                       ptr(support), ptr(offsets), ptr(cursor), ptr(sel), ptr(xd), ptr(w), ptr(row_base), ptr(row_off),
-                                      stream(dev)))
+                                      ptr(row_limit), stream(dev)))
     return sel, xd, w
 
 
@@ -572,6 +584,112 @@ def dispatch_points(id6: Tensor, weights: Optional[Tensor], hard: Optional[Tenso
     return sel, w
 
 
+class RoutedFieldFn(torch.autograd.Function):
+    """Several experts on their buckets of ONE routed row list whose bucket sizes only the device knows
+    (models/inr/meta_container.py:306-337 without its K host syncs): xd (cap,>=6) [xyz, dir] rows, seg (n+1,) int32 device
+    offsets -- expert i of `experts` evaluates rows [seg[i], seg[i+1]) -- -> y (cap,4) [rgb, sigma] (rows outside the
+    ranges are never written nor read).  Every kernel takes the range as a device pointer; nothing is read back.
+    experts: list of (GridSpec, box6).  Flat tensor arguments: per expert its hash table, then its 14 MLP tensors."""
+
+    @staticmethod
+    def forward(ctx_, xd, seg, half, experts, table_nodes, *tensors):
+        n = len(experts)
+        assert len(tensors) == 15 * n and seg.dtype == torch.int32 and seg.numel() == n + 1
+        if xd.dtype != torch.float32 or not xd.is_contiguous():
+            xd = xd.float().contiguous()
+        cap, dev = xd.shape[0], xd.device
+        tables = [dev_f32(tensors[15 * i], "hash_table") for i in range(n)]
+        wss = [[dev_f32(w, "MLP weight") for w in tensors[15 * i + 1:15 * i + 15]] for i in range(n)]
+        E = experts[0][0].L * experts[0][0].F
+        enc = torch.empty(cap, E, dtype=torch.float16 if half else torch.float32, device=dev)
+        y = torch.empty(cap, 4, dtype=torch.float32, device=dev)
+        dirs = xd[:, 3:]
+        L_ = lib()
+        for i, (spec, box6) in enumerate(experts):
+            rng = seg[i:i + 2]
+            _, H, G, C = _field_dims(wss[i])
+            check(L_.acn_hashgrid_fwd(ctx(dev), ptr(xd), cap, xd.stride(0), ptr(rng), ptr(box6), ptr(tables[i]), spec.L, spec.F,
+                                      spec.log2T, ptr(_grid_res(spec, dev)), spec.interp, ptr(enc), _dt(enc), None, stream(dev)))
+            st = pack_weights(wss[i])
+            check(L_.acn_field_fwd(ctx(dev), ptr(enc), _dt(enc), ptr(dirs), xd.stride(0), 1, cap, ptr(rng), E, H, G, C, C_.byref(st),
+                                   F16 if half else F32, ptr(y), stream(dev)))
+        ctx_.save_for_backward(enc, xd, seg, *[b for _, b in experts if b is not None], *[w for ws in wss for w in ws])
+        ctx_.meta = ([s_ for s_, _ in experts], [b is not None for _, b in experts], half, [t.shape for t in tables])
+        ctx_.table_nodes = table_nodes
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx_, g):
+        specs, has_box, half, tshapes = ctx_.meta
+        n = len(specs)
+        saved = ctx_.saved_tensors
+        enc, xd, seg = saved[0], saved[1], saved[2]
+        nb = sum(has_box)
+        boxes_it = iter(saved[3:3 + nb])
+        boxes = [next(boxes_it) if hb else None for hb in has_box]
+        wflat = saved[3 + nb:]
+        g = g.contiguous().float()
+        cap, dev = xd.shape[0], xd.device
+        dirs = xd[:, 3:]
+        L_ = lib()
+        out = []
+        d_enc = None
+        for i in range(n):
+            spec, box6, ws = specs[i], boxes[i], wflat[14 * i:14 * i + 14]
+            E, H, G, C = _field_dims(ws)
+            rng = seg[i:i + 2]
+            need_table = ctx_.needs_input_grad[5 + 15 * i] and engine_wants(ctx_.table_nodes[i])
+            need_w = ctx_.needs_input_grad[6 + 15 * i:20 + 15 * i]
+            flat = torch.zeros(sum(w.numel() for w, nd in zip(ws, need_w) if nd), dtype=torch.float32, device=dev)
+            grads, off = [], 0
+            for w, nd in zip(ws, need_w):
+                grads.append(flat[off:off + w.numel()].view(w.shape) if nd else None)
+                off += w.numel() if nd else 0
+            wst, gst = pack_weights(ws), pack_weights(grads)
+            dtable = torch.zeros(tshapes[i], dtype=torch.float32, device=dev) if need_table else None
+            if (FUSED_EXPERT_BWD and need_table and half and spec.F == 2 and spec.L in (8, 16) and spec.interp != 0):
+                check(L_.acn_render_expert_bwd(ctx(dev), ptr(xd), xd.stride(0), None, None, cap, 1, ptr(rng), ptr(box6), spec.L, spec.F,
+                                               spec.log2T, ptr(_grid_res(spec, dev)), spec.interp, ptr(enc), ptr(dirs), xd.stride(0), 1,
+                                               H, G, C, C_.byref(wst), ptr(g), C_.byref(gst), ptr(dtable), stream(dev)))
+            else:
+                if need_table and d_enc is None:
+                    d_enc = torch.empty(cap, E, dtype=torch.float32, device=dev)
+                check(L_.acn_field_bwd(ctx(dev), ptr(enc), _dt(enc), ptr(dirs), xd.stride(0), 1, cap, ptr(rng), E, H, G, C, C_.byref(wst),
+                                       F16 if half else F32, ptr(g), C_.byref(gst), ptr(d_enc) if need_table else None, F32, stream(dev)))
+                if need_table:
+                    check(L_.acn_hashgrid_bwd(ctx(dev), ptr(xd), cap, xd.stride(0), ptr(rng), ptr(box6), spec.L, spec.F, spec.log2T,
+                                              ptr(_grid_res(spec, dev)), spec.interp, ptr(d_enc), F32, ptr(dtable), stream(dev)))
+            out += [dtable, *grads]
+        return (None, None, None, None, None, *out)
+
+
+class BlendRangesFn(torch.autograd.Function):
+    """out[sel[i]] += y[i] * w[i] for the rows of every expert's range, one launch per expert in expert order (the
+    reference's summation order, meta_container.py:321 / :336), ranges read on the device.  seg (n+1,) int32."""
+
+    @staticmethod
+    def forward(ctx_, y, w, sel, seg, N):
+        y = y.contiguous()
+        dev = y.device
+        out = torch.zeros(N, 4, dtype=torch.float32, device=dev)
+        for i in range(seg.numel() - 1):
+            check(lib().acn_blend_add(ctx(dev), ptr(y), ptr(w), ptr(sel), sel.shape[0], ptr(seg[i:i + 2]), None, ptr(out), stream(dev)))
+        ctx_.save_for_backward(w, sel, seg)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx_, g):
+        w, sel, seg = ctx_.saved_tensors
+        g = g.contiguous()
+        dev = g.device
+        d_y = torch.empty(sel.shape[0], 4, dtype=torch.float32, device=dev)
+        span = torch.stack([seg[0], seg[-1]])
+        check(lib().acn_blend_bwd(ctx(dev), ptr(g), ptr(w), ptr(sel), sel.shape[0], ptr(span), None, ptr(d_y), stream(dev)))
+        return d_y, None, None, None, None
+
+
 class BlendFn(torch.autograd.Function):
     """out[sel[i]] += y[i] * w[i] (models/inr/meta_container.py:321 index_add_ / :336 index_copy_)
     for one expert's routed rows; `out` is threaded through so experts accumulate in k order."""
@@ -579,7 +697,7 @@ class BlendFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx_, out, y, w, sel):
         y = y.contiguous()
-        check(lib().acn_blend_add(ctx(y.device), ptr(y), ptr(w), ptr(sel), y.shape[0], ptr(out), stream(y.device)))
+        check(lib().acn_blend_add(ctx(y.device), ptr(y), ptr(w), ptr(sel), y.shape[0], None, None, ptr(out), stream(y.device)))
         ctx_.save_for_backward(w, sel)
         ctx_.mark_dirty(out)
         return out
@@ -590,7 +708,7 @@ class BlendFn(torch.autograd.Function):
         w, sel = ctx_.saved_tensors
         g = g.contiguous()
         d_y = torch.empty(sel.shape[0], 4, dtype=torch.float32, device=g.device)
-        check(lib().acn_blend_bwd(ctx(g.device), ptr(g), ptr(w), ptr(sel), sel.shape[0], ptr(d_y), stream(g.device)))
+        check(lib().acn_blend_bwd(ctx(g.device), ptr(g), ptr(w), ptr(sel), sel.shape[0], None, None, ptr(d_y), stream(g.device)))
         return g, d_y, None, None
 
 

@@ -87,18 +87,24 @@ int acn_rays_coherent(acn_ctx*, const float* rays8, int64_t N, int S, float thre
 
 /* ---- stage 2: multiresolution hash grid (models/encodings.py:160-381, torch branch) --------- */
 
-/* x: (P,>=3) with row stride x_stride floats.  box6_or_null = [min xyz, extent xyz] (device):
+/* ROW RANGES (the routed container path: an expert's bucket, whose size only the device knows -- nothing is read back
+ * to the host, SURVEY 8b "dispatch counts stay on device").  Entry points that take `range_or_null` process, when it is
+ * given (device, 2 int32 [first, end)), only those rows of their row-indexed arrays -- all pointers stay the bases of
+ * the FULL arrays -- and P is then an UPPER BOUND on end - first, used to size the launch.  Per-point directions only
+ * (dirs_group == 1).
+ *
+ * x: (P,>=3) with row stride x_stride floats.  box6_or_null = [min xyz, extent xyz] (device):
  * when given, x is in world coordinates and models/inr/meta_ngp.py:155-158 _world_to_unit is
  * applied first.  table: (L*2^log2T, F) fp32.  res: (L) int32 on the device.
  * out: (P, L*F) fp32 or fp16.  idx_out_or_null: (P,L,8) int32 table rows (parity checks). */
-int acn_hashgrid_fwd(acn_ctx*, const float* x, int64_t P, int x_stride, const float* box6_or_null,
-                     const float* table, int L, int F, int log2T, const int32_t* res, int interp,
-                     void* out, int out_dtype, int32_t* idx_out_or_null, acn_stream);
+int acn_hashgrid_fwd(acn_ctx*, const float* x, int64_t P, int x_stride, const int32_t* range_or_null,
+                     const float* box6_or_null, const float* table, int L, int F, int log2T, const int32_t* res,
+                     int interp, void* out, int out_dtype, int32_t* idx_out_or_null, acn_stream);
 
 /* Autograd of the above w.r.t. the table: dtable (L*2^log2T, F) fp32 is ACCUMULATED into. */
-int acn_hashgrid_bwd(acn_ctx*, const float* x, int64_t P, int x_stride, const float* box6_or_null,
-                     int L, int F, int log2T, const int32_t* res, int interp, const void* dout,
-                     int dout_dtype, float* dtable, acn_stream);
+int acn_hashgrid_bwd(acn_ctx*, const float* x, int64_t P, int x_stride, const int32_t* range_or_null,
+                     const float* box6_or_null, int L, int F, int log2T, const int32_t* res, int interp,
+                     const void* dout, int dout_dtype, float* dtable, acn_stream);
 
 /* Same, with the points formed on the fly from rays (N,8) and t_vals (N,S): p = o + d*t
  * (nerfs/ray_rendering.py:317); the reference's (N*S,6) id6 tensor is never materialised.
@@ -133,12 +139,12 @@ int acn_sh16(acn_ctx*, const float* dirs, int64_t P, int stride, float* out, acn
  * group S.  precision ACN_F32: SIMT fp32 math.  ACN_F16: tcgen05 tensor cores, fp16
  * operands / fp32 accumulate (the reference's autocast path).  -> rgb_sigma (P,4) fp32. */
 int acn_field_fwd(acn_ctx*, const void* enc, int enc_dtype, const float* dirs, int dirs_stride,
-                  int dirs_group, int64_t P, int E, int H, int G, int C,
+                  int dirs_group, int64_t P, const int32_t* range_or_null, int E, int H, int G, int C,
                   const acn_field_weights* w, int precision, float* rgb_sigma, acn_stream);
 
 /* d_rgb_sigma (P,4) -> weight grads (accumulated) and d_enc (P,E) (NULL to skip). */
 int acn_field_bwd(acn_ctx*, const void* enc, int enc_dtype, const float* dirs, int dirs_stride,
-                  int dirs_group, int64_t P, int E, int H, int G, int C,
+                  int dirs_group, int64_t P, const int32_t* range_or_null, int E, int H, int G, int C,
                   const acn_field_weights* w, int precision, const float* d_rgb_sigma,
                   const acn_field_grads* g, void* d_enc_or_null, int d_enc_dtype, acn_stream);
 
@@ -150,7 +156,8 @@ int acn_field_bwd(acn_ctx*, const void* enc, int enc_dtype, const float* dirs, i
  * enc_f16 (P, L*F): the fp16 encoding the forward saved.  F = 2, L in {8,16}, Linear / Smoothstep.  Weight gradients
  * are accumulated into g, the table gradient into dtable (L*2^log2T, 2) fp32. */
 int acn_render_expert_bwd(acn_ctx*, const float* x_or_null, int x_stride, const float* rays8_or_null,
-                          const float* t_vals_or_null, int64_t P, int S, const float* box6_or_null, int L, int F,
+                          const float* t_vals_or_null, int64_t P, int S, const int32_t* range_or_null,
+                          const float* box6_or_null, int L, int F,
                           int log2T, const int32_t* res, int interp, const void* enc_f16, const float* dirs,
                           int dirs_stride, int dirs_group, int H, int G, int C, const acn_field_weights* w,
                           const float* d_rgb_sigma, const acn_field_grads* g, float* dtable, acn_stream);
@@ -203,12 +210,15 @@ int acn_dispatch_points(acn_ctx*, const float* id6, int64_t P, const float* weig
                         const int32_t* hard_or_null, int K, const int32_t* offsets, int32_t* cursor,
                         int32_t* sel, float* w_out, const uint64_t* row_base, const int32_t* row_off, acn_stream);
 
-/* out[sel[i]] += y[i] * w[i]  (index_add_, meta_container.py:321) over M routed rows of 4.  y may be peer memory. */
+/* out[sel[i]] += y[i] * w[i]  (index_add_, meta_container.py:321) over M routed rows of 4.  y may be peer memory.
+ * range_or_null: rows [range[0], range[1]) of (w, sel) only (see "ROW RANGES").  y_row0_or_null (device, 1 int32): y is
+ * then read at row *y_row0 + (i - range[0]) -- the rows an expert's OWNER holds for this rank start elsewhere in its
+ * buffer than in the local bucket. */
 int acn_blend_add(acn_ctx*, const float* y, const float* w, const int32_t* sel, int64_t M,
-                  float* out, acn_stream);
-/* d_y[i] = d_out[sel[i]] * w[i] */
+                  const int32_t* range_or_null, const int32_t* y_row0_or_null, float* out, acn_stream);
+/* d_y[i] = d_out[sel[i]] * w[i]  (same addressing of d_y as of y above) */
 int acn_blend_bwd(acn_ctx*, const float* d_out, const float* w, const int32_t* sel, int64_t M,
-                  float* d_y, acn_stream);
+                  const int32_t* range_or_null, const int32_t* y_row0_or_null, float* d_y, acn_stream);
 
 /* The container's render path without the point and weight matrices: routing (meta_container.py:97-134) of the samples
  * o + d*t of packed rays (nerfs/ray_rendering.py:317-319) and their bucketing (:306-337), straight from (rays8, t_vals).
@@ -222,7 +232,8 @@ int acn_blend_bwd(acn_ctx*, const float* d_out, const float* w, const int32_t* s
  * frames, where consecutive rays are adjacent pixels, a warp of the experts' gather kernels then works on neighbouring
  * cells.  The set of rows per expert does not depend on it.  ray_major_dev_or_null (device, 1 int32) overrides it.
  * row_base / row_off (K each, as in acn_dispatch_points): when given, expert k's [xyz, dir] rows are stored into that
- * buffer (peer memory of the GPU that owns k) instead of xd_out.
+ * buffer (peer memory of the GPU that owns k) instead of xd_out.  row_limit (K): at most that many rows per expert are
+ * written (see acn_bucket_plan).
  * Same arithmetic as acn_points + acn_route_points + acn_bucket_points (rows and weights are bit-identical); K <= 16. */
 int acn_route_count_rays(acn_ctx*, const float* rays8, const float* t_vals, int64_t N, int S,
                          const float* centroids, int K, int dims, float margin, int ray_major,
@@ -231,7 +242,16 @@ int acn_route_bucket_rays(acn_ctx*, const float* rays8, const float* t_vals, int
                           const float* centroids, int K, int dims, float margin, int ray_major,
                           const int32_t* ray_major_dev_or_null, const uint16_t* support_or_null,
                           const int32_t* offsets, int32_t* cursor, int32_t* sel, float* xd_out, float* w_out,
-                          const uint64_t* row_base_or_null, const int32_t* row_off_or_null, acn_stream);
+                          const uint64_t* row_base_or_null, const int32_t* row_off_or_null,
+                          const int32_t* row_limit_or_null, acn_stream);
+
+/* The bucket layout from DEVICE-side counts, nothing read back (SURVEY 8b "dispatch counts stay on device"; the reference
+ * syncs K times per container forward, meta_container.py:309-313): seg (K+1) int32 = exclusive scan of counts (K),
+ * clamped so that the total stays within cap rows (the size the caller allocated the bucket arrays with); limit (K) =
+ * rows of each expert that fit (hand it to acn_route_bucket_rays as row_limit: rows beyond are dropped); cursor (K) is
+ * zeroed for the bucket pass; *overflow_or_null is SET to 1 when rows were cut (never cleared: the caller polls it). */
+int acn_bucket_plan(acn_ctx*, const int32_t* counts, int K, int64_t cap, int32_t* seg, int32_t* limit,
+                    int32_t* cursor, int32_t* overflow_or_null, acn_stream);
 
 /* ---- around the render: loss epilogue and optimizer tail --------------- */
 enum { ACN_COLOR_LINEAR = 0, ACN_COLOR_SRGB = 1, ACN_COLOR_IDENTITY = 2 };

@@ -57,7 +57,7 @@ def test_ctypes_table_matches_header(built_lib):
     assert l.acn_version() == 200
     for name in _lib.SIGNATURES:
         assert getattr(l, name).argtypes == _lib.SIGNATURES[name]
-    assert len(_lib.SIGNATURES["acn_hashgrid_fwd"]) == 15 and len(_lib.SIGNATURES["acn_field_bwd"]) == 18
+    assert len(_lib.SIGNATURES["acn_hashgrid_fwd"]) == 16 and len(_lib.SIGNATURES["acn_field_bwd"]) == 19
 
 
 def test_error_convention_without_gpu(built_lib):
