@@ -154,27 +154,34 @@ __global__ void __launch_bounds__(256) k_grad_sqnorm(const __grid_constant__ Ada
     for (int k = 0; k < b.count; ++k) {
         const float* g = b.t[k].g;
         const int64_t n = b.t[k].n;
+        const float nz0 = s0 + s1 + s2 + s3;               // sums of squares only grow: a change = this tensor has a non-zero
+        bool nzt = false;                                  // (squares of tiny values underflow: test the values themselves)
         if (((uintptr_t)g & 15) == 0) {
             const float4* g4 = reinterpret_cast<const float4*>(g);
             const int64_t n4 = n >> 2;
             for (int64_t i = tid; i < n4; i += nth) {
                 float4 v = ld_stream_f4(g4 + i);
+                nzt |= (v.x != 0.0f) | (v.y != 0.0f) | (v.z != 0.0f) | (v.w != 0.0f);
                 v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
                 bad |= !isfinite(v.x) | !isfinite(v.y) | !isfinite(v.z) | !isfinite(v.w);
                 s0 = fmaf(v.x, v.x, s0); s1 = fmaf(v.y, v.y, s1); s2 = fmaf(v.z, v.z, s2); s3 = fmaf(v.w, v.w, s3);
             }
             for (int64_t i = (n4 << 2) + tid; i < n; i += nth) {
+                nzt |= g[i] != 0.0f;
                 float v = g[i] * inv;
                 bad |= !isfinite(v);
                 s0 = fmaf(v, v, s0);
             }
         } else {
             for (int64_t i = tid; i < n; i += nth) {
+                nzt |= g[i] != 0.0f;
                 float v = g[i] * inv;
                 bad |= !isfinite(v);
                 s0 = fmaf(v, v, s0);
             }
         }
+        (void)nz0;
+        if (b.t[k].bias && __syncthreads_or(nzt) && threadIdx.x == 0) b.t[k].bias[2] = 1.0;   // benign race: every writer stores 1
     }
     double s = block_sum_d((double)s0 + (double)s1 + (double)s2 + (double)s3, sh);
     const int any_bad = __syncthreads_or(bad);
@@ -190,32 +197,38 @@ __global__ void __launch_bounds__(256) k_grad_sqnorm(const __grid_constant__ Ada
 // Per-tensor part of the decision: a tensor that takes part in a step that is not skipped advances ITS step count
 // (torch.optim.Adam keeps `step` per parameter and leaves it alone while the parameter's grad is None -- an expert that
 // saw no ray) and gets its bias corrections from it, in doubles like torch's host code.
-__device__ __forceinline__ void adam_advance_tensors(const AdamBatch& b, bool skip, double beta1, double beta2) {
+// skip_zero: a tensor whose gradient is identically zero this step is treated like torch treats `grad is None` -- left
+// alone, step count included.  That is how the sync-free routed path says "this expert received no row": its autograd
+// node cannot return None without reading the row count back to the host, it returns zeros.
+__device__ __forceinline__ void adam_advance_tensors(const AdamBatch& b, bool skip, double beta1, double beta2, bool skip_zero) {
     for (int k = threadIdx.x; k < b.count; k += blockDim.x) {
         const acn_adam_tensor& t = b.t[k];
         if (!t.step || !t.bias) continue;
+        const bool active = !(skip_zero && t.bias[2] == 0.0);
+        t.bias[2] = 0.0;                                   // the non-zero mark of acn_grad_sqnorm is consumed
+        t.bias[3] = active ? 1.0 : 0.0;
         double step = (double)*t.step;
-        if (!skip) { step += 1.0; *t.step = (float)step; }
+        if (!skip && active) { step += 1.0; *t.step = (float)step; }
         t.bias[0] = 1.0 - pow(beta1, step);
         t.bias[1] = sqrt(1.0 - pow(beta2, step));
     }
 }
 
 __global__ void __launch_bounds__(64) k_adam_advance(const __grid_constant__ AdamBatch b, const double* __restrict__ state,
-                                                     double beta1, double beta2)
+                                                     double beta1, double beta2, int skip_zero)
 {
-    adam_advance_tensors(b, state[2] != 0.0, beta1, beta2);
+    adam_advance_tensors(b, state[2] != 0.0, beta1, beta2, skip_zero != 0);
 }
 
 __global__ void __launch_bounds__(64) k_adam_prepare(double* __restrict__ acc, const float* __restrict__ grad_scale,
                                const float* __restrict__ found_inf_in, float max_norm, double beta1, double beta2,
                                double* __restrict__ state, float* __restrict__ found_inf_out,
-                               const __grid_constant__ AdamBatch b)
+                               const __grid_constant__ AdamBatch b, int skip_zero)
 {
     __shared__ int s_bad;
     if (threadIdx.x == 0) s_bad = (acc[1] > 0.0 || !isfinite(acc[0]) || (found_inf_in && *found_inf_in > 0.0f)) ? 1 : 0;
     __syncthreads();
-    adam_advance_tensors(b, s_bad != 0, beta1, beta2);
+    adam_advance_tensors(b, s_bad != 0, beta1, beta2, skip_zero != 0);
     if (threadIdx.x != 0) return;
     const double sq = acc[0];
     const bool bad = acc[1] > 0.0 || !isfinite(sq) || (found_inf_in && *found_inf_in > 0.0f);
@@ -264,6 +277,7 @@ __global__ void __launch_bounds__(256) k_adam_apply(const __grid_constant__ Adam
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
     for (int k = 0; k < b.count; ++k) {
         const acn_adam_tensor& t = b.t[k];
+        if (t.bias && t.bias[3] == 0.0) continue;                    // identically-zero gradient = "grad is None" (acn_adam_prepare)
         const double bc1 = t.bias ? t.bias[0] : state[3];           // per-tensor step (torch.optim.Adam) or the global one
         K.bc2_sqrt = (float)(t.bias ? t.bias[1] : state[4]);
         const float wd = (float)t.weight_decay, lr_wd = (float)(t.lr * t.weight_decay), step_size = (float)(t.lr / bc1);
@@ -338,7 +352,7 @@ extern "C" int acn_grad_sqnorm(acn_ctx* ctx, const acn_adam_tensor* tensors, int
 extern "C" int acn_adam_prepare(acn_ctx* ctx, double* acc2, const float* grad_scale_or_null,
                                 const float* found_inf_or_null, float max_norm, double beta1, double beta2,
                                 double* state8, float* found_inf_out_or_null, const acn_adam_tensor* tensors_or_null,
-                                int count, acn_stream stream)
+                                int count, int skip_zero_grads, acn_stream stream)
 {
     ACN_CHECK_CTX(ctx);
     ACN_REQUIRE(acc2 && state8, ACN_EINVAL, "acn_adam_prepare: null accumulator / state");
@@ -348,13 +362,13 @@ extern "C" int acn_adam_prepare(acn_ctx* ctx, double* acc2, const float* grad_sc
     int rc = fill_batch(b, tensors_or_null, tensors_or_null ? count : 0, false, "acn_adam_prepare");
     if (rc) return rc;
     k_adam_prepare<<<1, 64, 0, (cudaStream_t)stream>>>(acc2, grad_scale_or_null, found_inf_or_null, max_norm, beta1,
-                                                       beta2, state8, found_inf_out_or_null, b);
+                                                       beta2, state8, found_inf_out_or_null, b, skip_zero_grads);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }
 
 extern "C" int acn_adam_advance(acn_ctx* ctx, const acn_adam_tensor* tensors, int count, const double* state8,
-                                double beta1, double beta2, acn_stream stream)
+                                double beta1, double beta2, int skip_zero_grads, acn_stream stream)
 {
     ACN_CHECK_CTX(ctx);
     ACN_REQUIRE(state8 != nullptr, ACN_EINVAL, "acn_adam_advance: null state");
@@ -362,7 +376,7 @@ extern "C" int acn_adam_advance(acn_ctx* ctx, const acn_adam_tensor* tensors, in
     int rc = fill_batch(b, tensors, count, false, "acn_adam_advance");
     if (rc) return rc;
     if (count == 0) return ACN_OK;
-    k_adam_advance<<<1, 64, 0, (cudaStream_t)stream>>>(b, state8, beta1, beta2);
+    k_adam_advance<<<1, 64, 0, (cudaStream_t)stream>>>(b, state8, beta1, beta2, skip_zero_grads);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }

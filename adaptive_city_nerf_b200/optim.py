@@ -45,11 +45,17 @@ class FusedAdam(torch.optim.Optimizer):
     _step_supports_amp_scaling = True
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 adamw: bool = False, max_norm: Optional[float] = None, write_grads: bool = False):
+                 adamw: bool = False, max_norm: Optional[float] = None, write_grads: bool = False,
+                 skip_zero_grads: bool = False):
         if lr < 0.0 or eps < 0.0 or weight_decay < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
             raise ValueError(f"invalid Adam hyper-parameters lr={lr} betas={betas} eps={eps} weight_decay={weight_decay}")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self.adamw, self.max_norm, self.write_grads = bool(adamw), max_norm, bool(write_grads)
+        #: treat a parameter whose gradient is identically zero like torch treats `grad is None` (leave it and its step
+        #: count alone).  The container's sync-free routed path cannot return None for an expert that received no row
+        #: (it would have to read the row count back); it returns zeros, and this flag restores the reference's behaviour
+        #: (zero_grad(set_to_none=True) + experts without rays keep their Adam state).  `get_optimizer` sets it.
+        self.skip_zero_grads = bool(skip_zero_grads)
         self._dev: Optional[torch.device] = None
         self._state8 = self._acc2 = self._found_inf = None
         self._bias: Dict[torch.Tensor, torch.Tensor] = {}      # per parameter: [bias_correction1, sqrt(bias_correction2)] workspace
@@ -97,7 +103,7 @@ class FusedAdam(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 bias = self._bias.get(p)
                 if bias is None:
-                    bias = self._bias[p] = torch.zeros(2, dtype=torch.float64, device=p.device)
+                    bias = self._bias[p] = torch.zeros(4, dtype=torch.float64, device=p.device)
                 t = AdamTensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                                p.numel(), float(group["lr"]), float(group["weight_decay"]), st["step"].data_ptr(),
                                bias.data_ptr())
@@ -123,9 +129,10 @@ class FusedAdam(torch.optim.Optimizer):
             check(L.acn_grad_sqnorm(c, C.cast(arr, C.c_void_p), n, ptr(gs), ptr(self._acc2), s))
         check(L.acn_adam_prepare(c, ptr(self._acc2), ptr(gs), ptr(fi), float(max_norm) if max_norm else 0.0,
                                  float(betas[0]), float(betas[1]), ptr(self._state8), ptr(self._found_inf),
-                                 C.cast(chunks[0][0], C.c_void_p), chunks[0][1], s))
+                                 C.cast(chunks[0][0], C.c_void_p), chunks[0][1], int(self.skip_zero_grads), s))
         for arr, n in chunks[1:]:
-            check(L.acn_adam_advance(c, C.cast(arr, C.c_void_p), n, ptr(self._state8), float(betas[0]), float(betas[1]), s))
+            check(L.acn_adam_advance(c, C.cast(arr, C.c_void_p), n, ptr(self._state8), float(betas[0]), float(betas[1]),
+                                     int(self.skip_zero_grads), s))
         for arr, n in chunks:
             check(L.acn_adam_apply(c, C.cast(arr, C.c_void_p), n, ptr(self._state8), float(betas[0]), float(betas[1]),
                                    float(eps), int(self.adamw), int(self.write_grads), s))
@@ -207,4 +214,7 @@ def get_optimizer(P, model: torch.nn.Module) -> FusedAdam:
     opt_name = str(getattr(P, "optimizer", "adamw")).lower()
     if opt_name not in ("adam", "adamw"):
         raise ValueError(f"Unknown optimizer for the fused step: {opt_name} (adam | adamw; use torch.optim for sgd)")
-    return FusedAdam(groups, lr=base_lr, weight_decay=weight_decay, adamw=opt_name == "adamw")
+    # a container of several experts renders through the sync-free routed path: "no row for this expert" arrives as an
+    # all-zero gradient, which must behave like the reference's grad None (common/utils.py + torch.optim.Adam)
+    routed = len(getattr(model, "submodules", ())) > 1
+    return FusedAdam(groups, lr=base_lr, weight_decay=weight_decay, adamw=opt_name == "adamw", skip_zero_grads=routed)

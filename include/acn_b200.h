@@ -277,8 +277,10 @@ typedef struct {
     double weight_decay; /* the param group's weight decay */
     float* step;         /* device, 1 float: THIS tensor's step count, as torch.optim.Adam keeps it per parameter (a tensor
                           * that had no gradient on some steps lags behind the others); NULL = use the global count */
-    double* bias;        /* device, 2 doubles of workspace for this tensor: [bias_correction1, sqrt(bias_correction2)],
-                          * written by acn_adam_prepare / acn_adam_advance, read by acn_adam_apply; NULL with step == NULL */
+    double* bias;        /* device, 4 doubles of workspace for this tensor (zero before the first step):
+                          * [bias_correction1, sqrt(bias_correction2), gradient-has-a-non-zero mark, takes-part-in-this-step],
+                          * written by acn_grad_sqnorm / acn_adam_prepare / acn_adam_advance, read by acn_adam_apply;
+                          * NULL with step == NULL */
 } acn_adam_tensor;
 
 /* Optimizer tail of pipelines/offline_stage/meta_core.py:123-141 maml_meta_update (scaler.unscale_ ->
@@ -293,6 +295,8 @@ typedef struct {
  *                     tensors_or_null / count: the tensors taking part in THIS step (those with a gradient): unless
  *                     the step is skipped, each one's *step is incremented and its bias corrections are written to
  *                     *bias from ITS step (torch.optim.Adam: a parameter whose grad is None keeps its step).
+ *                     skip_zero_grads != 0: a tensor whose gradient is identically zero is left alone like one whose
+ *                     grad is None -- the sync-free routed path returns zeros, not None, for an expert without rows.
  *   acn_adam_advance: the per-tensor part of acn_adam_prepare for a further batch of tensors (more than
  *                     ACN_ADAM_MAX_TENSORS in one step); call after acn_adam_prepare.
  *   acn_adam_apply  : torch.optim.Adam (adamw = 0) / AdamW (adamw = 1) update of <= 48 tensors with the gradient
@@ -302,9 +306,9 @@ int acn_grad_sqnorm(acn_ctx*, const acn_adam_tensor* tensors, int count, const f
                     double* acc2, acn_stream);
 int acn_adam_prepare(acn_ctx*, double* acc2, const float* grad_scale_or_null, const float* found_inf_or_null,
                      float max_norm, double beta1, double beta2, double* state8, float* found_inf_out_or_null,
-                     const acn_adam_tensor* tensors_or_null, int count, acn_stream);
+                     const acn_adam_tensor* tensors_or_null, int count, int skip_zero_grads, acn_stream);
 int acn_adam_advance(acn_ctx*, const acn_adam_tensor* tensors, int count, const double* state8, double beta1,
-                     double beta2, acn_stream);
+                     double beta2, int skip_zero_grads, acn_stream);
 int acn_adam_apply(acn_ctx*, const acn_adam_tensor* tensors, int count, const double* state8, double beta1,
                    double beta2, double eps, int adamw, int write_grads, acn_stream);
 

@@ -139,7 +139,19 @@ for tail in ("torch", "fused"):
     res5[tail] = timed(step5, 8, warm=3)
     del opt
     torch.cuda.empty_cache()
+# the same step as ONE CUDA graph (nothing in it reads back to the host any more)
+import types
+from adaptive_city_nerf_b200.graphs import GraphedStep, graphed_adapt_step
+from adaptive_city_nerf_b200.optim import get_optimizer
+Pn = types.SimpleNamespace(lr=1e-3, encoding_lr=1e-2, sigma_lr=2e-3, color_lr=2e-3, bg_lr=1e-3, optimizer="adam", weight_decay=0.0,
+                           ray_samples=96, chunk_points=1 << 24, color_space="linear")
+opt = get_optimizer(Pn, m)
+scaler = torch.amp.GradScaler("cuda")
+gstep = GraphedStep(graphed_adapt_step(Pn, m, opt, scaler, grad_clip=1.0), [rays, gt])
+res5["graph"] = timed(lambda: gstep(rays, gt), 20, warm=3)
+m.check_route_overflow()
 ms = res5["fused"]
 print(json.dumps({"config": "cfg5: 8 experts, 4000 support rays x 96 samples, Adam + GradScaler + clip 1.0, whole container",
                   "ms_per_step": round(ms, 2), "rays_per_s": rays.shape[0] / (ms * 1e-3),
-                  "ms_per_step_with_pytorch_loss_and_optimizer": round(res5["torch"], 2)}))
+                  "ms_per_step_with_pytorch_loss_and_optimizer": round(res5["torch"], 2),
+                  "ms_per_step_cuda_graph": round(res5["graph"], 3), "rays_per_s_cuda_graph": rays.shape[0] / (res5["graph"] * 1e-3)}))
