@@ -737,6 +737,61 @@ extern "C" int acn_bucket_plan(acn_ctx* ctx, const int32_t* counts, int K, int64
     return ACN_OK;
 }
 
+// Expert sharding without a host read: from the all-gathered per-expert row counts of every rank (world x K, on the
+// device) every rank derives, identically, where each (source rank s, expert k) segment lies in the receive buffer of
+// k's owner (owner = k % world, buffer order: local expert e = k / world, then source rank) with every buffer clamped to
+// cap_peer rows, and takes its own part:
+//   seg_local (K+1)  this rank's local bucket layout (sel / w arrays, expert order), clamped to cap_local rows
+//   limit (K)        rows of expert k this rank may write (fits both the local arrays and the owner's buffer)
+//   row_off (K)      first row of (this rank, expert k) in the owner's buffer
+//   seg_recv (m+1)   row ranges of this rank's own experts in ITS buffer (all sources), m = K / world
+//   cursor (K) = 0;  *overflow = 1 when anything was cut
+__global__ void k_shard_plan(const int32_t* __restrict__ all_counts, int world, int K, int rank, int64_t cap_local, int64_t cap_peer,
+                             int32_t* __restrict__ seg_local, int32_t* __restrict__ limit, int32_t* __restrict__ row_off,
+                             int32_t* __restrict__ seg_recv, int32_t* __restrict__ cursor, int32_t* __restrict__ overflow) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int m = K / world;
+    bool cut = false;
+    for (int o = 0; o < world; ++o) {                      // every owner's buffer, filled in (local expert, source) order
+        int64_t run = 0;
+        for (int e = 0; e < m; ++e) {
+            const int k = e * world + o;
+            if (o == rank) seg_recv[e] = (int32_t)run;
+            for (int s_ = 0; s_ < world; ++s_) {
+                int64_t c = all_counts[s_ * K + k];
+                if (run + c > cap_peer) { c = cap_peer - run; cut = true; }
+                if (s_ == rank) { row_off[k] = (int32_t)run; limit[k] = (int32_t)c; }
+                run += c;
+            }
+        }
+        if (o == rank) seg_recv[m] = (int32_t)run;
+    }
+    int64_t run = 0;
+    seg_local[0] = 0;
+    for (int k = 0; k < K; ++k) {
+        int64_t c = limit[k];
+        if (run + c > cap_local) { c = cap_local - run; cut = true; }
+        limit[k] = (int32_t)c;
+        cursor[k] = 0;
+        run += c;
+        seg_local[k + 1] = (int32_t)run;
+    }
+    if (cut && overflow) *overflow = 1;
+}
+
+extern "C" int acn_shard_plan(acn_ctx* ctx, const int32_t* all_counts, int world, int K, int rank, int64_t cap_local, int64_t cap_peer,
+                              int32_t* seg_local, int32_t* limit, int32_t* row_off, int32_t* seg_recv, int32_t* cursor,
+                              int32_t* overflow_or_null, acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    ACN_REQUIRE(all_counts && seg_local && limit && row_off && seg_recv && cursor, ACN_EINVAL, "acn_shard_plan: null buffer");
+    ACN_REQUIRE(world >= 1 && K >= 1 && K % world == 0 && rank >= 0 && rank < world, ACN_EINVAL, "acn_shard_plan: K=%d experts over %d ranks (rank %d)", K, world, rank);
+    ACN_REQUIRE(cap_local >= 0 && cap_peer >= 0 && cap_local < ((int64_t)1 << 31) && cap_peer < ((int64_t)1 << 31), ACN_EINVAL, "acn_shard_plan: bad capacities");
+    k_shard_plan<<<1, 32, 0, (cudaStream_t)stream>>>(all_counts, world, K, rank, cap_local, cap_peer, seg_local, limit, row_off, seg_recv,
+                                                     cursor, overflow_or_null);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
+
 static int blend_grid(acn_ctx* ctx, int64_t M, bool ranged) {
     const int64_t blocks = (M + 255) / 256, cap = (int64_t)ctx->sm_count * 16;
     return (int)(blocks < 1 ? 1 : (ranged && blocks > cap ? cap : blocks));

@@ -182,6 +182,41 @@ class _PeerCombine(torch.autograd.Function):
         return px.dy[:M].clone(), None, None, None, None, None, None
 
 
+class _PeerCombineRanges(torch.autograd.Function):
+    """`_PeerCombine` without host-side sizes: out[sel] += w * y over all experts, every expert's rows read from its
+    owner's symmetric y buffer at the device-side offsets of `acn_shard_plan` (local range seg_local[k:k+2], owner rows
+    starting at row_off[k]); the backward stores w * dL/dout[sel] into the owners' dy buffers the same way and hands this
+    rank ITS dy buffer as the gradient of what it put into y.  Blending stays in expert order."""
+
+    @staticmethod
+    def forward(ctx, y_local: Tensor, px: "PeerExchange", K: int, world: int, seg_local: Tensor, row_off: Tensor, sel: Tensor,
+                wsel: Tensor, N: int):
+        px.h_y.barrier()                                     # every owner's y is complete and visible
+        dev = sel.device
+        out = torch.zeros(N, 4, dtype=torch.float32, device=dev)
+        L_, c, st = ops.lib(), ops.ctx(dev), ops.stream(dev)
+        for k in range(K):                                   # expert order, like the reference (meta_container.py:306-337)
+            ops.check(L_.acn_blend_add(c, ops.ptr(px.peer_y(k % world)), ops.ptr(wsel), ops.ptr(sel), sel.shape[0],
+                                       ops.ptr(seg_local[k:k + 2]), ops.ptr(row_off[k:k + 1]), ops.ptr(out), st))
+        ctx.px, ctx.K, ctx.world = px, K, world
+        ctx.save_for_backward(sel, wsel, seg_local, row_off)
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        px, K, world = ctx.px, ctx.K, ctx.world
+        sel, wsel, seg_local, row_off = ctx.saved_tensors
+        g = g.contiguous()
+        dev = g.device
+        L_, c, st = ops.lib(), ops.ctx(dev), ops.stream(dev)
+        px.h_dy.barrier()                                    # nobody is still reading dy from the previous use
+        for k in range(K):
+            ops.check(L_.acn_blend_bwd(c, ops.ptr(g), ops.ptr(wsel), ops.ptr(sel), sel.shape[0], ops.ptr(seg_local[k:k + 2]),
+                                       ops.ptr(row_off[k:k + 1]), ops.ptr(px.peer_dy(k % world)), st))
+        px.h_dy.barrier()                                    # every home rank's dL/dy has landed in my dy
+        return px.dy, None, None, None, None, None, None, None, None
+
+
 # --------------------------------------------------------------------------------------------- expert sharding
 class ExpertShardedContainer(torch.nn.Module):
     """A `MetaContainer` whose experts live on different ranks.  Built from a full container description; every
@@ -194,8 +229,10 @@ class ExpertShardedContainer(torch.nn.Module):
 
     def __init__(self, container, group=None, peer_rows: int = 0):
         """peer_rows > 0 switches the sample exchange from NCCL all-to-all to kernels that store to / load from peer
-        memory directly (`PeerExchange` with that many rows of capacity per rank; a step that would overflow it falls
-        back to NCCL on every rank alike)."""
+        memory directly (`PeerExchange` with that many rows of capacity per rank).  The render path (`forward_rays`)
+        then runs WITHOUT any host read: the per-expert counts of all ranks are all-gathered on the device,
+        `acn_shard_plan` lays the exchange out there, and the owners' kernels take device-side row ranges; rows that do
+        not fit the capacity are dropped and `check_route_overflow()` reports it."""
         super().__init__()
         self.inner = container
         self.group = group
@@ -264,7 +301,52 @@ class ExpertShardedContainer(torch.nn.Module):
                                                  row_base=row_base, row_off=row_off, **kw)
             return sel, wsel
 
+        if self._peer_rows > 0:
+            return self._forward_rays_peer_nosync(rays, t, counts, support, ray_major, params).view(N, S, -1)
         return self._exchange_and_blend(N * S, counts, params, bucket, dispatch).view(N, S, -1)
+
+    #: rows the local bucket arrays (sel, w) are allocated for, as a multiple of this rank's samples (soft routing)
+    route_capacity_factor = 2.0
+
+    def check_route_overflow(self) -> None:
+        """Raises if a routed step since the last check needed more rows than the local arrays (`route_capacity_factor`)
+        or an owner's peer buffer (`peer_rows`) hold.  Reads one device word: call it outside the timed steps."""
+        f = getattr(self, "_overflow", None)
+        if f is not None and int(f.item()) != 0:
+            f.zero_()
+            raise RuntimeError(f"sharded routed buckets overflowed (peer_rows={self._peer_rows}, "
+                               f"route_capacity_factor={self.route_capacity_factor}); the affected steps dropped samples")
+
+    def _forward_rays_peer_nosync(self, rays: Tensor, t: Tensor, counts: Tensor, support: Tensor, ray_major, params) -> Tensor:
+        """The routed step over peer memory with everything decided on the device (no .cpu(), no .tolist()):
+        all-gather of the counts -> acn_shard_plan -> dispatch straight into the owners' buffers -> barrier -> the owners'
+        experts on device-side row ranges of their buffer, writing y into their symmetric buffer -> barrier -> blend from
+        the peers' y in expert order.  The backward mirrors it through `_PeerCombineRanges` and `RoutedFieldFn`."""
+        c = self.inner
+        dev = rays.device
+        N, S = t.shape
+        P = N * S
+        W, K = self.world, self.K
+        if self._px is None:
+            self._px = PeerExchange(self._peer_rows, dev, self.group)
+            self._row_base = torch.tensor([self._px.rows_ptrs[k % W] for k in range(K)], dtype=torch.int64, device=dev)
+            self._overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        px = self._px
+        cap_local = P if c.boundary_margin <= 1.0 else int(min(float(K), float(self.route_capacity_factor)) * P)
+        with torch.no_grad():
+            all_counts = torch.empty(W, K, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(all_counts, counts.contiguous(), group=self.group)       # stays on the device
+            seg_local, limit, row_off, seg_recv, cursor = ops.shard_plan(all_counts, self.rank, cap_local, px.cap, self._overflow)
+            px.h_rows.barrier()                               # the owners are done with the previous contents of `rows`
+            sel, _, wsel = ops.route_bucket_rays(rays, t, c.centroids, 2 if c.cluster_2d else 3, c.boundary_margin, seg_local,
+                                                 cap_local, support=support, ray_major=ray_major, row_base=self._row_base,
+                                                 row_off=row_off, row_limit=limit, cursor=cursor)
+            px.h_rows.barrier()                               # every rank's rows have landed in every owner
+        # the owners' experts read their rows where they landed and write y where the peers will read it
+        y_local = c._evaluate_segments(px.rows, seg_recv, self.local_ids, c._sub_params(params), y_out=px.y)
+        if torch.is_grad_enabled() and not y_local.requires_grad:
+            y_local = y_local.detach().requires_grad_()       # the combine's backward is collective: every rank must run it
+        return _PeerCombineRanges.apply(y_local, px, K, W, seg_local, row_off, sel, wsel, P)
 
     def _exchange_and_blend(self, N: int, counts: Tensor, params, bucket, dispatch) -> Tensor:
         """counts (K,) rows per expert on this rank; bucket(offsets, total) -> (sel, xd, w) builds the local buckets,

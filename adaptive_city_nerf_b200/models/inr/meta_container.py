@@ -149,7 +149,8 @@ class MetaContainer(MetaModule):
         y = self._evaluate_segments(xd, seg, list(range(K)), self._sub_params(params))
         return ops.BlendRangesFn.apply(y, wsel, sel, seg, P).view(N, S, -1)
 
-    def _evaluate_segments(self, xd: torch.Tensor, seg: torch.Tensor, expert_ids: List[int], sub_params: List) -> torch.Tensor:
+    def _evaluate_segments(self, xd: torch.Tensor, seg: torch.Tensor, expert_ids: List[int], sub_params: List,
+                           y_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Experts `expert_ids` on the row ranges [seg[i], seg[i+1]) of xd (device-side ranges) -> (cap,4)."""
         from .meta_ngp import autocast_half
         subs = [self.submodules[k] for k in expert_ids]
@@ -162,7 +163,7 @@ class MetaContainer(MetaModule):
         for sub, k in zip(subs, expert_ids):
             flat.append(sub.xyz_encoder.hash_table)
             flat += sub.fused_weights(sub_params[k])
-        return ops.RoutedFieldFn.apply(xd, seg, half, experts, nodes, *flat)
+        return ops.RoutedFieldFn.apply(xd, seg, half, experts, nodes, y_out, *flat)
 
     def _routed(self, x: torch.Tensor, sub_params: List) -> torch.Tensor:
         N, K = x.shape[0], len(self.submodules)

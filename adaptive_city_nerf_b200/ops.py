@@ -537,6 +537,18 @@ def bucket_plan(counts: Tensor, cap: int, overflow: Optional[Tensor] = None):
     return seg, limit, cursor
 
 
+def shard_plan(all_counts: Tensor, rank: int, cap_local: int, cap_peer: int, overflow: Optional[Tensor] = None):
+    """acn_shard_plan: all_counts (world, K) int32 on the device -> seg_local (K+1,), limit (K,), row_off (K,), seg_recv
+    (K/world+1,), cursor (K,) -- the whole exchange layout of a sharded routed step, decided on the device."""
+    world, K = all_counts.shape
+    dev = all_counts.device
+    i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
+    seg_local, limit, row_off, seg_recv, cursor = i32(K + 1), i32(K), i32(K), i32(K // world + 1), i32(K)
+    check(lib().acn_shard_plan(ctx(dev), ptr(all_counts), world, K, int(rank), int(cap_local), int(cap_peer), ptr(seg_local), ptr(limit),
+                               ptr(row_off), ptr(seg_recv), ptr(cursor), ptr(overflow), stream(dev)))
+    return seg_local, limit, row_off, seg_recv, cursor
+
+
 def route_bucket_rays(rays: Tensor, t: Tensor, centroids: Tensor, dims: int, margin: float, offsets: Tensor, total: int,
                       support: Optional[Tensor] = None, ray_major=False, row_base: Optional[Tensor] = None,
                       row_off: Optional[Tensor] = None, row_limit: Optional[Tensor] = None, cursor: Optional[Tensor] = None):
@@ -589,10 +601,11 @@ class RoutedFieldFn(torch.autograd.Function):
     (models/inr/meta_container.py:306-337 without its K host syncs): xd (cap,>=6) [xyz, dir] rows, seg (n+1,) int32 device
     offsets -- expert i of `experts` evaluates rows [seg[i], seg[i+1]) -- -> y (cap,4) [rgb, sigma] (rows outside the
     ranges are never written nor read).  Every kernel takes the range as a device pointer; nothing is read back.
-    experts: list of (GridSpec, box6).  Flat tensor arguments: per expert its hash table, then its 14 MLP tensors."""
+    experts: list of (GridSpec, box6).  Flat tensor arguments: per expert its hash table, then its 14 MLP tensors.
+    y_out: optional (cap,4) fp32 buffer to write into (a peer-mapped buffer in the sharded container)."""
 
     @staticmethod
-    def forward(ctx_, xd, seg, half, experts, table_nodes, *tensors):
+    def forward(ctx_, xd, seg, half, experts, table_nodes, y_out, *tensors):
         n = len(experts)
         assert len(tensors) == 15 * n and seg.dtype == torch.int32 and seg.numel() == n + 1
         if xd.dtype != torch.float32 or not xd.is_contiguous():
@@ -602,7 +615,8 @@ class RoutedFieldFn(torch.autograd.Function):
         wss = [[dev_f32(w, "MLP weight") for w in tensors[15 * i + 1:15 * i + 15]] for i in range(n)]
         E = experts[0][0].L * experts[0][0].F
         enc = torch.empty(cap, E, dtype=torch.float16 if half else torch.float32, device=dev)
-        y = torch.empty(cap, 4, dtype=torch.float32, device=dev)
+        y = y_out if y_out is not None else torch.empty(cap, 4, dtype=torch.float32, device=dev)
+        assert y.shape == (cap, 4) and y.dtype == torch.float32 and y.is_contiguous()
         dirs = xd[:, 3:]
         L_ = lib()
         for i, (spec, box6) in enumerate(experts):
@@ -639,8 +653,8 @@ class RoutedFieldFn(torch.autograd.Function):
             spec, box6, ws = specs[i], boxes[i], wflat[14 * i:14 * i + 14]
             E, H, G, C = _field_dims(ws)
             rng = seg[i:i + 2]
-            need_table = ctx_.needs_input_grad[5 + 15 * i] and engine_wants(ctx_.table_nodes[i])
-            need_w = ctx_.needs_input_grad[6 + 15 * i:20 + 15 * i]
+            need_table = ctx_.needs_input_grad[6 + 15 * i] and engine_wants(ctx_.table_nodes[i])
+            need_w = ctx_.needs_input_grad[7 + 15 * i:21 + 15 * i]
             flat = torch.zeros(sum(w.numel() for w, nd in zip(ws, need_w) if nd), dtype=torch.float32, device=dev)
             grads, off = [], 0
             for w, nd in zip(ws, need_w):
@@ -661,7 +675,7 @@ class RoutedFieldFn(torch.autograd.Function):
                     check(L_.acn_hashgrid_bwd(ctx(dev), ptr(xd), cap, xd.stride(0), ptr(rng), ptr(box6), spec.L, spec.F, spec.log2T,
                                               ptr(_grid_res(spec, dev)), spec.interp, ptr(d_enc), F32, ptr(dtable), stream(dev)))
             out += [dtable, *grads]
-        return (None, None, None, None, None, *out)
+        return (None, None, None, None, None, None, *out)
 
 
 class BlendRangesFn(torch.autograd.Function):

@@ -253,6 +253,18 @@ int acn_route_bucket_rays(acn_ctx*, const float* rays8, const float* t_vals, int
 int acn_bucket_plan(acn_ctx*, const int32_t* counts, int K, int64_t cap, int32_t* seg, int32_t* limit,
                     int32_t* cursor, int32_t* overflow_or_null, acn_stream);
 
+/* The same for EXPERT SHARDING (expert k lives on rank k % world; no reference counterpart, the reference is single-GPU):
+ * from the all-gathered counts of every rank, all_counts (world, K) int32 on the device, every rank derives identically
+ * where each (source rank, expert) segment lies in the receive buffer of the expert's owner -- buffer order: local
+ * expert, then source rank; every buffer holds at most cap_peer rows -- and takes its part: seg_local (K+1) its local
+ * bucket layout (at most cap_local rows), limit (K) the rows of expert k it may write, row_off (K) where they start in
+ * the owner's buffer, seg_recv (K/world + 1) the row ranges of its OWN experts in its buffer; cursor (K) is zeroed;
+ * *overflow_or_null is set to 1 when anything was cut.  With these, acn_route_bucket_rays stores rows straight into peer
+ * memory and the owners' kernels take device-side row ranges: a routed step needs no host read. */
+int acn_shard_plan(acn_ctx*, const int32_t* all_counts, int world, int K, int rank, int64_t cap_local, int64_t cap_peer,
+                   int32_t* seg_local, int32_t* limit, int32_t* row_off, int32_t* seg_recv, int32_t* cursor,
+                   int32_t* overflow_or_null, acn_stream);
+
 /* ---- around the render: loss epilogue and optimizer tail --------------- */
 enum { ACN_COLOR_LINEAR = 0, ACN_COLOR_SRGB = 1, ACN_COLOR_IDENTITY = 2 };
 #define ACN_LOSS_PARTIALS 1024   /* doubles of workspace acn_color_mse may use */

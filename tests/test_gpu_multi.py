@@ -80,7 +80,12 @@ def _worker(rank, world, port, margin, peer_rows, ret):
             y_pts = model(ops.points(mine, t)).view(-1, S, 4)
             y_rays = model.forward_rays(mine, t, ray_major=True)
         perr = float((y_pts - y_rays).abs().max())
-        ret[rank] = (err, gerr, n_owned, float(total), ref_total, perr)
+        overflowed = False
+        try:
+            model.check_route_overflow()
+        except RuntimeError:
+            overflowed = True
+        ret[rank] = (err, gerr, n_owned, float(total), ref_total, perr, overflowed)
     finally:
         dist.destroy_process_group()
 
@@ -88,14 +93,19 @@ def _worker(rank, world, port, margin, peer_rows, ret):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("margin,peer_rows", [(1.05, 0), (1.0, 0), (1.05, 1 << 18), (1.0, 1 << 18), (1.05, 1000)])
 def test_expert_sharded_container_matches_single_process(margin, peer_rows):
-    """peer_rows = 0: NCCL all-to-all exchange; 2^18: kernels storing to / loading from peer memory over NVLink
-    (symmetric memory); 1000: a capacity the step overflows, i.e. the consistent fall-back to NCCL."""
+    """peer_rows = 0: NCCL all-to-all exchange (one host read per step); 2^18: kernels storing to / loading from peer memory
+    over NVLink (symmetric memory) with the whole exchange laid out on the device (acn_shard_plan: no host read);
+    1000: a capacity the step overflows -- the surplus rows are dropped on the device and check_route_overflow() reports it."""
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), margin, peer_rows, ret), nprocs=2, join=True)
     for rank in range(2):
-        err, gerr, n_owned, total, ref_total, perr = ret[rank]
+        err, gerr, n_owned, total, ref_total, perr, overflowed = ret[rank]
+        if peer_rows == 1000:
+            assert overflowed and np.isfinite(err)
+            continue
+        assert not overflowed
         assert perr == 0.0, (rank, perr)                    # points path == rays path (ray-major buckets), bit for bit
         assert err < 1e-5, (rank, err)                      # same kernels, same order of blending
         assert gerr < 1e-4, (rank, gerr)                    # float atomics reorder sums; nothing else differs
