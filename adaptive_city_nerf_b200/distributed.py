@@ -329,6 +329,7 @@ class ExpertShardedContainer(torch.nn.Module):
         W, K = self.world, self.K
         if self._px is None:
             self._px = PeerExchange(self._peer_rows, dev, self.group)
+        if getattr(self, "_row_base", None) is None:
             self._row_base = torch.tensor([self._px.rows_ptrs[k % W] for k in range(K)], dtype=torch.int64, device=dev)
             self._overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         px = self._px

@@ -46,7 +46,7 @@ class FusedAdam(torch.optim.Optimizer):
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                  adamw: bool = False, max_norm: Optional[float] = None, write_grads: bool = False,
-                 skip_zero_grads: bool = False):
+                 skip_zero_grads: bool = False, norm_group=None):
         if lr < 0.0 or eps < 0.0 or weight_decay < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
             raise ValueError(f"invalid Adam hyper-parameters lr={lr} betas={betas} eps={eps} weight_decay={weight_decay}")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
@@ -56,6 +56,10 @@ class FusedAdam(torch.optim.Optimizer):
         #: (it would have to read the row count back); it returns zeros, and this flag restores the reference's behaviour
         #: (zero_grad(set_to_none=True) + experts without rays keep their Adam state).  `get_optimizer` sets it.
         self.skip_zero_grads = bool(skip_zero_grads)
+        #: torch.distributed group over which the squared gradient norm (and the non-finite flag) is summed before the
+        #: step is decided: expert-sharded training, where every rank holds different parameters but the reference clips
+        #: ONE global norm (meta_core.py:181-190).  Two doubles per step, on the device.
+        self.norm_group = norm_group
         self._dev: Optional[torch.device] = None
         self._state8 = self._acc2 = self._found_inf = None
         self._bias: Dict[torch.Tensor, torch.Tensor] = {}      # per parameter: [bias_correction1, sqrt(bias_correction2)] workspace
@@ -127,6 +131,9 @@ class FusedAdam(torch.optim.Optimizer):
         fi = None if found_inf_in is None else found_inf_in.reshape(-1).to(device=dev, dtype=torch.float32)
         for arr, n in chunks:
             check(L.acn_grad_sqnorm(c, C.cast(arr, C.c_void_p), n, ptr(gs), ptr(self._acc2), s))
+        if self.norm_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self._acc2, group=self.norm_group)
         check(L.acn_adam_prepare(c, ptr(self._acc2), ptr(gs), ptr(fi), float(max_norm) if max_norm else 0.0,
                                  float(betas[0]), float(betas[1]), ptr(self._state8), ptr(self._found_inf),
                                  C.cast(chunks[0][0], C.c_void_p), chunks[0][1], int(self.skip_zero_grads), s))

@@ -41,11 +41,52 @@ ENC_BWD_BYTES = 2 * 1024 + 128                 # read-modify-write of the same 1
 FIELD_FWD_FLOP = 26880
 FIELD_BWD_FLOP = 2 * 26880                     # dgrad + wgrad (the recompute is not counted)
 COMPOSITE_BYTES = 24
-# DRAM bytes per launch at this workload (dram__bytes_read.sum + dram__bytes_write.sum, one `ncu --set full` capture:
-# profiles/r01_v1_stages_ncu_full_summary.csv).  The 64 MiB table is L2-resident, so the gather / scatter traffic that
-# the algorithmic byte count describes is served by L2, not HBM.
-NCU_DRAM_BYTES = {"acn_hashgrid_fwd_rays": 1.40e9, "acn_hashgrid_bwd_rays": 2.39e9, "acn_field_fwd": 1.33e9,
-                  "acn_field_bwd": 3.45e9, "acn_composite_fwd": 0.374e9, "acn_composite_bwd": 0.574e9}
+# fused backward (acn_render_expert_bwd = MLP backward + table scatter in one kernel): the 1024 B of table rows are
+# read-modify-written (2048 B), the fp16 encoding row (64 B) and dL/d[rgb,sigma] (16 B) are read; d_enc never exists
+FUSED_BWD_BYTES = 2 * 1024 + 64 + 16
+GRID_CORNERS = 16 * 8                          # (level, corner) table rows a sample gathers forward / updates backward
+# committed ncu captures (`--set full`, one launch of each kernel at this workload): kernel name in the capture per entry
+# point; `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of that launch is READ FROM THESE FILES
+NCU_FILES = ["profiles/r02_v3_fused_bwd_ncu_full_summary.csv", "profiles/r01_v3_stages_ncu_full_summary.csv"]
+NCU_KERNEL = {"acn_hashgrid_fwd_rays": "k_hashgrid_fwd<2, __half>", "acn_hashgrid_bwd_rays": "k_hashgrid_bwd_march<float>",
+              "acn_field_fwd": "k_field_fwd_mma<32, 0>", "acn_field_bwd": "k_field_bwd_mma<32, 0>",
+              "acn_render_expert_bwd": "k_field_bwd_mma<32, 0, 1>", "acn_composite_fwd": "k_composite_fwd",
+              "acn_composite_bwd": "k_composite_bwd"}
+
+
+def ncu_traffic():
+    """{entry point: (DRAM bytes per launch, file)} from the committed ncu summaries (first file that has the kernel)."""
+    import csv
+    out = {}
+    for f in NCU_FILES:
+        path = ROOT / f
+        if not path.exists():
+            continue
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        try:
+            ik, ir, iw = 0, [h.startswith("dram_rd") for h in hdr].index(True), [h.startswith("dram_wr") for h in hdr].index(True)
+        except ValueError:
+            continue
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        ur = next((v for k, v in scale.items() if k in hdr[ir]), 1e9)
+        uw = next((v for k, v in scale.items() if k in hdr[iw]), 1e9)
+        for r in rows[1:]:
+            for entry, kern in NCU_KERNEL.items():
+                if entry not in out and r[ik] == kern:
+                    out[entry] = (float(r[ir]) * ur + float(r[iw]) * uw, f)
+    return out
+
+
+def l2_peaks():
+    """Measured ceilings of the L2-resident table accesses (tools/l2_peak.py on this pool's B200): scattered 8-byte
+    gathers and red.global.add.v2/v4.f32 into a 64 MiB buffer, in accesses per second."""
+    f = ROOT / "profiles" / "r02_l2_peaks.json"
+    if not f.exists():
+        return None
+    rows = json.loads(f.read_text())["rows"]
+    pick = lambda op, b: next(r["g_accesses_per_s"] for r in rows if r["buffer_mib"] == 64 and r["op"] == op and r["bytes"] == b)
+    return {"gather_g_per_s": pick("gather", 8), "red_g_per_s": pick("red", 16), "source": "profiles/r02_l2_peaks.json"}
 
 
 def peaks():
@@ -199,6 +240,125 @@ def make_model(dev, box):
     return m
 
 
+def container_records(args, world, rank, dev):
+    """BASELINE configs 3 / 4 next to the headline: (a) `expert_sharded`: a routed training step of a K-expert container
+    (2x2 grid at N <= 4, 2x4 at N = 8; margin 1.05) with the experts sharded over the N ranks -- weak (2^18 rays per rank)
+    and fixed-total (2^18 rays in all) -- over the peer-memory exchange, nothing read back to the host; at N = 1 the same
+    container on one GPU is the baseline of the curve.  (b) `frame`: latency of one 1920x1080 frame, 8 experts with
+    boundary blending and the background head, pixel rows split over the ranks with the experts replicated (a single
+    view only touches the two or three experts under it, so sharding them cannot spread its work), image all-gathered."""
+    import torch
+    import torch.distributed as dist
+    import synth
+    from adaptive_city_nerf_b200.distributed import ExpertShardedContainer
+    from adaptive_city_nerf_b200.models.inr import MetaContainer
+    from adaptive_city_nerf_b200.nerfs.losses import mse_in_color_space
+    from adaptive_city_nerf_b200.nerfs.ray_rendering import render_rays
+    from adaptive_city_nerf_b200.nerfs.ray_sampling import clamp_rays_near_far, get_ray_directions, get_rays
+    from adaptive_city_nerf_b200.nerfs.scene_box import SceneBox
+    from adaptive_city_nerf_b200.optim import FusedAdam
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    conf = dict(levels=16, features_per_level=2, log2_hashmap_size=LOG2T, max_res=4096, min_res=16, interpolation="Linear")
+    box = SceneBox(T(synth.AABB_GLOBAL).to(dev))
+
+    def container(K, cen, use_bg):
+        torch.manual_seed(0)
+        return MetaContainer(num_submodules=K, centroids=T(cen), aabb=T(synth.AABB_GLOBAL), boundary_margin=1.05, cluster_2d=True,
+                             use_bg_nerf=use_bg, expert_box_list=[box] * K, hidden=64, sigma_depth=2, color_depth=2, color_hidden=64,
+                             dir_encoding="spherical", hash_enc_conf=conf, occ_conf={"use_occ": False}).to(dev)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n, warm=3):
+        for _ in range(warm):
+            fn()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    out = {}
+    # ---------------- (a) expert-sharded routed training step
+    K = 8 if world == 8 else 4
+    cen = synth.CENTROIDS_G24 if K == 8 else synth.CENTROIDS_G22
+    full = container(K, cen, False)
+    rays_all, _, _ = gpu_workload(dev, seed=100 + rank)        # 2^18 rays of 64 views spread over the scene, this rank's own
+    perm = torch.randperm(N_RAYS, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    rays_all = rays_all[perm].contiguous()
+    gt = torch.rand(N_RAYS, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(8))
+    if world > 1:
+        model = ExpertShardedContainer(full, peer_rows=int(2.5 * N_RAYS * SAMPLES)).shard_()
+        params = model.local_parameters()
+    else:
+        model, params = full, list(full.parameters())
+    model.train()
+    groups = {"encoding": [p for p in params if p.ndim == 2 and p.shape[1] == 2 and p.shape[0] > 4096],
+              "mlp": [p for p in params if not (p.ndim == 2 and p.shape[1] == 2 and p.shape[0] > 4096)]}
+    opt = FusedAdam([{"params": groups["encoding"], "lr": 1e-2}, {"params": groups["mlp"], "lr": 2e-3}], eps=1e-15,
+                    skip_zero_grads=True, norm_group=(dist.group.WORLD if world > 1 else None))
+    rec = {"experts": K, "grid": "2x4" if K == 8 else "2x2", "boundary_margin": 1.05,
+           "exchange": "peer memory over NVLink (kernels store rows into / load results from the owners' buffers; counts all-gathered "
+                       "and laid out on the device, no host read)" if world > 1 else "none (all experts on one GPU)",
+           "step": "render_rays(active_module=None) fp16 + colour-space MSE + backward + global-norm clip + Adam"}
+    for tag, n in (("weak", N_RAYS), ("fixed_total", N_RAYS // world)):
+        r, g = rays_all[:n], gt[:n]
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.float16):
+                rgb, *_ = render_rays(model, r, ray_samples=SAMPLES, active_module=None, chunk=1 << 30)
+            loss = mse_in_color_space(rgb, g, "linear")
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step(max_norm=1.0)
+
+        ms = timed(step, max(3, args.steps // 2))
+        rec[tag] = {"rays_per_rank": n, "rays_total": n * world, "ms_per_step": round(ms, 3), "rays_per_s": n * world / (ms * 1e-3)}
+    sync()
+    model.check_route_overflow()
+    out["expert_sharded"] = rec
+    del model, full, opt, params, groups
+    torch.cuda.empty_cache()
+    # ---------------- (b) 1080p frame, 8 experts replicated, pixel rows split over the ranks
+    full = container(8, synth.CENTROIDS_G24, True).eval()
+    H, W = 1080, 1920
+    cam = synth.nadir_rays(0, 1, H=H, W=W, f=1481.0 * W / 2048)[0]
+    dirs = get_ray_directions(H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"], True, dev)
+    rays = get_rays(dirs, T(cam["c2w"]).to(dev), scene_box=box).view(-1, 8)
+    rays, _ = clamp_rays_near_far(rays, (None, None))
+    rows = H // world
+    mine = rays[rank * rows * W:(rank + 1) * rows * W].contiguous() if rank < world - 1 else rays[rank * rows * W:].contiguous()
+    img = torch.empty(world, rows * W + (H - rows * world) * W, 3, device=dev) if world > 1 else None
+
+    def frame():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            rgb, *_ = render_rays(full, mine, ray_samples=SAMPLES, active_module=None, chunk=1 << 28)
+        if world > 1:
+            pad = torch.zeros(img.shape[1], 3, device=dev)
+            pad[:rgb.shape[0]] = rgb
+            dist.all_gather_into_tensor(img, pad)
+        return rgb
+
+    ms = timed(frame, max(3, args.steps // 2))
+    sync()
+    full.check_route_overflow()
+    out["frame"] = {"what": "one 1920x1080 frame, 2x4 grid (8 experts, margin 1.05, background head), 64 samples per ray, eval fp16; "
+                            "pixel rows split over the ranks, experts replicated, image all-gathered", "ms_per_frame": round(ms, 3),
+                    "samples_per_s": H * W * SAMPLES / (ms * 1e-3)}
+    del full
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -300,12 +460,17 @@ def run_ours(args):
         ms_render = float(t)
     model.train()
 
+    extra = container_records(args, world, rank, dev)          # expert sharding + frame latency (all ranks take part)
+
     if rank == 0:
         pk = peaks()
+        l2 = l2_peaks()
+        traffic = ncu_traffic()
         P = N_RAYS * SAMPLES
-        work = {  # kernel -> (bound, algorithmic units per launch, unit scale)
+        work = {  # kernel -> (bound, algorithmic units per launch)
             "acn_hashgrid_fwd_rays": ("hbm", ENC_FWD_BYTES * P), "acn_hashgrid_bwd_rays": ("hbm", ENC_BWD_BYTES * P),
             "acn_field_fwd": ("tensor", FIELD_FWD_FLOP * P), "acn_field_bwd": ("tensor", FIELD_BWD_FLOP * P),
+            "acn_render_expert_bwd": ("hbm", FUSED_BWD_BYTES * P),
             "acn_composite_fwd": ("hbm", COMPOSITE_BYTES * P), "acn_composite_bwd": ("hbm", (COMPOSITE_BYTES + 20) * P),
         }
         kernels = {}
@@ -317,12 +482,33 @@ def run_ours(args):
                 ach = units / (avg * 1e-3) / (1e9 if bound == "hbm" else 1e12)
                 ent.update(bound=bound, achieved=round(ach, 2), frac=round(ach / pk[bound], 4),
                            unit="GB/s" if bound == "hbm" else "TFLOP/s")
+            # the table is L2-resident: the honest ceilings of its accesses are the MEASURED L2 gather / atomic rates
+            if l2 and avg > 0 and k == "acn_hashgrid_fwd_rays":
+                g = GRID_CORNERS * P / (avg * 1e-3) / 1e9
+                ent["l2_gather"] = {"achieved_g_rows_per_s": round(g, 1), "peak_scattered_g_per_s": l2["gather_g_per_s"],
+                                    "frac": round(g / l2["gather_g_per_s"], 3),
+                                    "note": "algorithmic 8-byte corner gathers; > 1 because the coarse levels hit L1 (the peak is for scattered rows)"}
+            if l2 and avg > 0 and k in ("acn_render_expert_bwd", "acn_hashgrid_bwd_rays"):
+                g = GRID_CORNERS * P / (avg * 1e-3) / 1e9
+                ent["l2_red"] = {"achieved_g_corner_updates_per_s": round(g, 1), "peak_g_reds_per_s": l2["red_g_per_s"],
+                                 "frac": round(g / l2["red_g_per_s"], 3),
+                                 "note": "algorithmic corner updates; x-neighbours share a 16-byte RED and coarse-level runs are merged, so fewer REDs are issued (ncu: 1.08 G per launch)"}
+            if k == "acn_render_expert_bwd" and avg > 0:
+                tf = FIELD_BWD_FLOP * P / (avg * 1e-3) / 1e12
+                ent["tensor"] = {"achieved_tflops": round(tf, 1), "frac": round(tf / pk["tensor"], 4),
+                                 "note": "the MLP backward inside the fused kernel (dgrad + wgrad FLOPs only)"}
+            if k in traffic:
+                ent["ncu_dram_bytes_per_launch"] = traffic[k][0]
             kernels[k] = ent
         top = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches"])
         tk = kernels[top]
         roof = {"kernel": top, "bound": tk["bound"], "achieved": tk["achieved"], "peak": pk[tk["bound"]], "unit": tk["unit"],
-                "frac": tk["frac"], "traffic": NCU_DRAM_BYTES.get(top), "traffic_unit": "DRAM bytes per launch (ncu)",
+                "frac": tk["frac"], "traffic": traffic.get(top, (None, None))[0],
+                "traffic_source": f"dram__bytes_read.sum + dram__bytes_write.sum of one launch, read from {traffic[top][1]}" if top in traffic else None,
                 "algorithmic": work[top][1], "peak_source": pk["src"], "avg_ms": tk["avg_ms"]}
+        for alt in ("l2_red", "l2_gather", "tensor"):
+            if alt in tk:
+                roof[alt] = tk[alt]
         n_cpu, ts, cores = time_cpu(steps=2, warmup=1) if world == 1 else (0, [], 0)
         out = {
             "metric": "train rays/s", "value": world * N_RAYS * args.steps / (ms * 1e-3), "unit": "rays/s",
@@ -331,7 +517,8 @@ def run_ours(args):
             "config": {"workload": f"single Instant-NGP expert (L16 F2 T=2^{LOG2T}, 64-wide MLPs), 2^18 rays/batch x {SAMPLES} "
                                    "samples, training step = render_rays fwd + colour-space MSE + bwd + grad clip + Adam (configs[1])",
                        "rays_per_step_per_gpu": N_RAYS, "samples_per_ray": SAMPLES, "parallelism": f"dp{world}",
-                       "l2": "inputs > L2: 64 MiB table + 1 GiB fp16 encodings + 2 GiB fp32 dL/denc per step"},
+                       "l2": "inputs > L2: 64 MiB table + 1 GiB fp16 encodings (written forward, read by the fused backward) + 256 MiB "
+                             "rgb/sigma + 256 MiB of their gradients per step; d_enc is never materialised"},
             "samples_per_s": world * N_RAYS * SAMPLES * args.steps / (ms * 1e-3),
             "e2e": {"value": world * N_RAYS * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
                     "h2d_bytes_per_step": int(rays_h.numel() * 4 + gt_h.numel() * 4), "d2h_bytes_per_step": 4,
@@ -341,6 +528,7 @@ def run_ours(args):
                        "unit": "samples/s", "ms_per_batch": ms_render / args.steps,
                        "what": "render_rays forward only (eval, no_grad, autocast fp16), same expert and rays"},
         }
+        out.update(extra)
         if ts:
             out["cpu_baseline"] = {"value": n_cpu / min(ts), "unit": "rays/s", "cores": cores, "kind": "port",
                                    "sample": f"{n_cpu} rays x {SAMPLES} samples fwd+bwd (configs[0] shape, T=2^{LOG2T}), "
