@@ -323,6 +323,15 @@ def container_records(args, world, rank, dev):
 
         ms = timed(step, max(3, args.steps // 2))
         rec[tag] = {"rays_per_rank": n, "rays_total": n * world, "ms_per_step": round(ms, 3), "rays_per_s": n * world / (ms * 1e-3)}
+        if args.graph:       # the same step as ONE CUDA graph per rank: nothing in it reads back to the host (all-gather of the
+            try:             # counts, the device-side barriers and the peer-memory kernels are captured with the rest)
+                from adaptive_city_nerf_b200.graphs import GraphedStep
+                gs = GraphedStep(lambda a, b: step(), [r, g], warmup=2)
+                msg = timed(lambda: gs(r, g), max(3, args.steps // 2), warm=2)
+                rec[tag].update(ms_per_step_cuda_graph=round(msg, 3), rays_per_s_cuda_graph=n * world / (msg * 1e-3))
+                del gs
+            except Exception as e:     # noqa: BLE001 -- recorded, not fatal: the eager number stands
+                rec[tag]["cuda_graph_error"] = f"{type(e).__name__}: {str(e)[:200]}"
     sync()
     model.check_route_overflow()
     out["expert_sharded"] = rec
@@ -544,6 +553,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--graph", action="store_true", help="also time the expert-sharded step as one CUDA graph per rank")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
