@@ -174,10 +174,20 @@ class MetaNGP(MetaModule):
         nerf_runner.py:41-42).  TF32 and fp16 carry the same 10-bit mantissa, the accumulators are fp32 either way, and
         the backward scales its gradient tiles into fp16 range, so this is the precision the reference's own GPU path
         has with that flag; without it the strict fp32 SIMT kernels run (40x / 14x slower forward / backward).  Only for
-        the encoding widths the tensor-core backward is built for (16 or 32 = L*F)."""
+        the encoding widths the tensor-core backward is built for (16 or 32 = L*F).
+
+        RANGE LIMIT of the TF32 stand-in: fp16 has TF32's mantissa but a 5-bit exponent -- an encoding, weight or hidden
+        activation beyond +-65504 becomes inf where TF32 (8-bit exponent) would not, and magnitudes below 6e-8 flush to
+        zero.  Hash features and the weights of a 64-wide ReLU MLP are O(1) (reference init: table U(+-1e-3), Linear
+        default), so neither bound is near in practice; a caller who cannot rule it out sets
+        `MetaNGP.tf32_on_tensor_cores = False` (class or instance) and gets the strict fp32 kernels for non-autocast
+        calls.  Under autocast(float16) the reference itself has the fp16 range."""
         if self.xyz_encoder.out_dim not in (16, 32) or device.type != "cuda":
             return False
-        return autocast_half(device) or bool(torch.backends.cuda.matmul.allow_tf32)
+        return autocast_half(device) or (self.tf32_on_tensor_cores and bool(torch.backends.cuda.matmul.allow_tf32))
+
+    #: serve non-autocast calls with the tcgen05 kernels (fp16 operands) when the caller allowed TF32 matmuls; see _use_half
+    tf32_on_tensor_cores = True
 
     def forward(self, x_d: Tensor, params=None) -> Tensor:
         """(...,>=6) [xyz, dir] -> (...,4) [rgb, sigma] (reference :226-241), fused."""

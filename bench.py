@@ -289,54 +289,62 @@ def container_records(args, world, rank, dev):
 
     out = {}
     # ---------------- (a) expert-sharded routed training step
-    K = 8 if world == 8 else 4
-    cen = synth.CENTROIDS_G24 if K == 8 else synth.CENTROIDS_G22
-    full = container(K, cen, False)
     rays_all, _, _ = gpu_workload(dev, seed=100 + rank)        # 2^18 rays of 64 views spread over the scene, this rank's own
     perm = torch.randperm(N_RAYS, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
     rays_all = rays_all[perm].contiguous()
     gt = torch.rand(N_RAYS, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(8))
-    if world > 1:
-        model = ExpertShardedContainer(full, peer_rows=int(2.5 * N_RAYS * SAMPLES)).shard_()
-        params = model.local_parameters()
-    else:
-        model, params = full, list(full.parameters())
-    model.train()
-    groups = {"encoding": [p for p in params if p.ndim == 2 and p.shape[1] == 2 and p.shape[0] > 4096],
-              "mlp": [p for p in params if not (p.ndim == 2 and p.shape[1] == 2 and p.shape[0] > 4096)]}
-    opt = FusedAdam([{"params": groups["encoding"], "lr": 1e-2}, {"params": groups["mlp"], "lr": 2e-3}], eps=1e-15,
-                    skip_zero_grads=True, norm_group=(dist.group.WORLD if world > 1 else None))
-    rec = {"experts": K, "grid": "2x4" if K == 8 else "2x2", "boundary_margin": 1.05,
-           "exchange": "peer memory over NVLink (kernels store rows into / load results from the owners' buffers; counts all-gathered "
-                       "and laid out on the device, no host read)" if world > 1 else "none (all experts on one GPU)",
-           "step": "render_rays(active_module=None) fp16 + colour-space MSE + backward + global-norm clip + Adam"}
-    for tag, n in (("weak", N_RAYS), ("fixed_total", N_RAYS // world)):
-        r, g = rays_all[:n], gt[:n]
 
-        def step():
-            with torch.autocast("cuda", dtype=torch.float16):
-                rgb, *_ = render_rays(model, r, ray_samples=SAMPLES, active_module=None, chunk=1 << 30)
-            loss = mse_in_color_space(rgb, g, "linear")
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            opt.step(max_norm=1.0)
+    def sharded_record(K):
+        cen = synth.CENTROIDS_G24 if K == 8 else synth.CENTROIDS_G22
+        full = container(K, cen, False)
+        if world > 1:
+            model = ExpertShardedContainer(full, peer_rows=int(2.5 * N_RAYS * SAMPLES)).shard_()
+            params = model.local_parameters()
+        else:
+            model, params = full, list(full.parameters())
+        model.train()
+        is_table = lambda p: p.ndim == 2 and p.shape[1] == 2 and p.shape[0] > 4096
+        opt = FusedAdam([{"params": [p for p in params if is_table(p)], "lr": 1e-2},
+                         {"params": [p for p in params if not is_table(p)], "lr": 2e-3}], eps=1e-15,
+                        skip_zero_grads=True, norm_group=(dist.group.WORLD if world > 1 else None))
+        rec = {"experts": K, "grid": "2x4" if K == 8 else "2x2", "boundary_margin": 1.05,
+               "exchange": "peer memory over NVLink (kernels store rows into / load results from the owners' buffers; counts all-gathered "
+                           "and laid out on the device, no host read)" if world > 1 else "none (all experts on one GPU)",
+               "step": "render_rays(active_module=None) fp16 + colour-space MSE + backward + global-norm clip + Adam"}
+        for tag, n in (("weak", N_RAYS), ("fixed_total", N_RAYS // world)):
+            if world == 1 and tag == "fixed_total":
+                rec[tag] = dict(rec["weak"])                   # the same step at N = 1
+                continue
+            r, g = rays_all[:n], gt[:n]
 
-        ms = timed(step, max(3, args.steps // 2))
-        rec[tag] = {"rays_per_rank": n, "rays_total": n * world, "ms_per_step": round(ms, 3), "rays_per_s": n * world / (ms * 1e-3)}
-        if args.graph:       # the same step as ONE CUDA graph per rank: nothing in it reads back to the host (all-gather of the
-            try:             # counts, the device-side barriers and the peer-memory kernels are captured with the rest)
-                from adaptive_city_nerf_b200.graphs import GraphedStep
-                gs = GraphedStep(lambda a, b: step(), [r, g], warmup=2)
-                msg = timed(lambda: gs(r, g), max(3, args.steps // 2), warm=2)
-                rec[tag].update(ms_per_step_cuda_graph=round(msg, 3), rays_per_s_cuda_graph=n * world / (msg * 1e-3))
-                del gs
-            except Exception as e:     # noqa: BLE001 -- recorded, not fatal: the eager number stands
-                rec[tag]["cuda_graph_error"] = f"{type(e).__name__}: {str(e)[:200]}"
-    sync()
-    model.check_route_overflow()
-    out["expert_sharded"] = rec
-    del model, full, opt, params, groups
-    torch.cuda.empty_cache()
+            def step():
+                with torch.autocast("cuda", dtype=torch.float16):
+                    rgb, *_ = render_rays(model, r, ray_samples=SAMPLES, active_module=None, chunk=1 << 30)
+                loss = mse_in_color_space(rgb, g, "linear")
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step(max_norm=1.0)
+
+            ms = timed(step, max(3, args.steps // 2))
+            rec[tag] = {"rays_per_rank": n, "rays_total": n * world, "ms_per_step": round(ms, 3), "rays_per_s": n * world / (ms * 1e-3)}
+            if args.graph:   # the same step as ONE CUDA graph per rank: nothing in it reads back to the host (the all-gather of
+                try:         # the counts, the device-side barriers and the peer-memory kernels are captured with the rest)
+                    from adaptive_city_nerf_b200.graphs import GraphedStep
+                    gs = GraphedStep(lambda a, b: step(), [r, g], warmup=2)
+                    msg = timed(lambda: gs(r, g), max(3, args.steps // 2), warm=2)
+                    rec[tag].update(ms_per_step_cuda_graph=round(msg, 3), rays_per_s_cuda_graph=n * world / (msg * 1e-3))
+                    del gs
+                except Exception as e:     # noqa: BLE001 -- recorded, not fatal: the eager number stands
+                    rec[tag]["cuda_graph_error"] = f"{type(e).__name__}: {str(e)[:200]}"
+        sync()
+        model.check_route_overflow()
+        del model, full, opt, params
+        torch.cuda.empty_cache()
+        return rec
+
+    out["expert_sharded"] = sharded_record(8 if world == 8 else 4)
+    if world == 1:                                             # the one-GPU baseline of the 8-expert curve as well
+        out["expert_sharded_8_experts"] = sharded_record(8)
     # ---------------- (b) 1080p frame, 8 experts replicated, pixel rows split over the ranks
     full = container(8, synth.CENTROIDS_G24, True).eval()
     H, W = 1080, 1920
