@@ -906,6 +906,32 @@ def gen_scene_boxes():
     save("scene_boxes.npz", **out)
 
 
+from make_golden_items import ram_rays_items  # noqa: E402
+
+
+def gen_ram_rays():
+    """data/ram_rays_dataset.py RamRaysDataset (single-process mode) on the items above."""
+    import types as _t
+    from data.ram_rays_dataset import RamRaysDataset
+    items = ram_rays_items()
+    mds = []
+    for it in items:
+        md = _t.SimpleNamespace(H=it["H"], W=it["W"], intrinsics=it["intrinsics"], c2w=T(it["c2w"]), image_index=it["image_index"], is_val=False)
+        md.load_image = (lambda a=it["image"]: T(a))
+        md.load_mask = (lambda m=it["mask"]: None if m is None else T(m))
+        mds.append(md)
+    box = SceneBox(aabb=T(synth.AABB_GLOBAL))
+    out = {}
+    for tag, nf in (("none", None), ("nf", (0.02, 0.5))):
+        import contextlib, io as _io
+        with contextlib.redirect_stdout(_io.StringIO()), contextlib.redirect_stderr(_io.StringIO()):
+            ds = RamRaysDataset(mds, center_pixels=True, val_balancing=False, ray_gen_kwargs={"scene_box": box, "near_far_override": nf}, num_workers=1)
+        out[f"{tag}.rgbs"], out[f"{tag}.rays"], out[f"{tag}.idx"] = ds._rgbs.numpy(), ds._rays.numpy(), ds._img_indices.numpy()
+        out[f"{tag}.num_images"] = np.int32(ds._num_images)
+        print(f"  ram_rays[{tag}]: {len(ds)} rays from {ds._num_images} images")
+    save("ram_rays.npz", **out)
+
+
 if __name__ == "__main__":
     which = set(sys.argv[1:])
     cc = None
@@ -930,3 +956,4 @@ if __name__ == "__main__":
     if want("hashgrid_t19"): gen_hashgrid_t19()
     if want("field_half"): gen_field_half()
     if want("scene_boxes"): gen_scene_boxes()
+    if want("ram_rays"): gen_ram_rays()

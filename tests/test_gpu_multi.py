@@ -111,3 +111,81 @@ def test_expert_sharded_container_matches_single_process(margin, peer_rows):
         assert gerr < 1e-4, (rank, gerr)                    # float atomics reorder sums; nothing else differs
         assert n_owned == 2 * 15                            # two experts' 14 MLP tensors + table each (experts r and r + 2)
         assert abs(total - ref_total) / ref_total < 1e-4    # the sharded global norm is the global norm
+
+
+def _worker_modes(rank, world, port, ret):
+    """SURVEY 8e rows 1 and 4 on two GPUs: per-expert meta-training (each rank trains ITS expert; the reference clips ONE
+    global gradient norm over all experts, pipelines/offline_stage/meta_core.py:181-190) and rank-strided Voronoi mask
+    generation with the box / count reduction of scripts/create_clusters.py:928-932."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from adaptive_city_nerf_b200.data.cluster_masks import finalize_expert_boxes, new_expert_boxes, voronoi_masks_and_boxes
+        from adaptive_city_nerf_b200.distributed import reduce_expert_aabbs
+        from adaptive_city_nerf_b200.nerfs.ray_rendering import render_rays
+        from adaptive_city_nerf_b200.optim import FusedAdam
+        K, S = 2, 24
+        cen = synth.CENTROIDS_G22[[0, 3]]
+        boxes = synth.EXPERT_BOXES_G22[[0, 3]]
+
+        def fresh():
+            return make_container(K, cen, boxes, 1.0, False, seed0=400, device=dev).train()
+
+        def expert_loss(m, k):
+            rr = _rays(10 + k, dev, n=2000)
+            jit = torch.rand(rr.shape[0], S, device=dev, generator=torch.Generator(device=dev).manual_seed(k))
+            with torch.autocast("cuda", dtype=torch.float16):
+                rgb, *_ = render_rays(m, rr, ray_samples=S, active_module=k, jitter=jit)
+            return ((rgb - 0.25 * (k + 1)) ** 2).mean() * 50.0          # large enough for the clip to bite
+
+        # one process, both experts, one optimizer, one global clip: what the reference's meta update does
+        ref = fresh()
+        opt = FusedAdam(ref.parameters(), lr=1e-2, eps=1e-15)
+        for _ in range(3):
+            opt.zero_grad(set_to_none=True)
+            (expert_loss(ref, 0) + expert_loss(ref, 1)).backward()
+            opt.step(max_norm=1.0)
+        ref_norm = float(opt.last_norm)
+        # sharded: this rank only ever touches expert `rank`; the clip still sees the global norm
+        mine = fresh()
+        own = list(mine.submodules[rank].parameters())
+        opt2 = FusedAdam(own, lr=1e-2, eps=1e-15, norm_group=dist.group.WORLD)
+        for _ in range(3):
+            opt2.zero_grad(set_to_none=True)
+            expert_loss(mine, rank).backward()
+            opt2.step(max_norm=1.0)
+        err = max(float((a - b).abs().max() / (b.abs().max() + 1e-12)) for a, b in zip(own, ref.submodules[rank].parameters()))
+        untouched = all(torch.equal(a, b) for a, b in zip(mine.submodules[1 - rank].parameters(), fresh().submodules[1 - rank].parameters()))
+        norm_err = abs(float(opt2.last_norm) - ref_norm) / ref_norm
+        assert ref_norm > 1.0                                              # the clip was active
+        # rank-strided mask generation + reduction
+        g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "scene_boxes.npz")))
+        images = [dict(H=int(g["HW"][i, 0]) // 4, W=int(g["HW"][i, 1]) // 4, intrinsics=g["intrinsics"][i] / 4.0, c2w=g["c2w"][i])
+                  for i in (0, 50, 120, 200)]
+        cen4, aabb = torch.from_numpy(g["centroids"]).to(dev), torch.from_numpy(g["aabb_global"]).to(dev)
+        kw = dict(ray_samples=64, boundary_margin=float(g["margin"]), cluster_2d=True)
+        full = voronoi_masks_and_boxes(images, cen4, aabb, **kw)
+        part = voronoi_masks_and_boxes(images[rank::world], cen4, aabb, **kw)
+        red = reduce_expert_aabbs(*part)
+        same = all(torch.equal(a, b) for a, b in zip(red, full))
+        fin = finalize_expert_boxes(*red, cen4, aabb)
+        ret[rank] = (err, untouched, norm_err, same, bool(torch.isfinite(fin[0]).all() and (fin[1] >= fin[0]).all()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_per_expert_training_and_mask_generation_shard_across_gpus():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_modes, args=(2, _free_port(), ret), nprocs=2, join=True)
+    for rank in range(2):
+        err, untouched, norm_err, same, finite = ret[rank]
+        assert err < 2e-5, (rank, err)              # the rank's expert after 3 globally-clipped Adam steps = the one-process run
+        assert untouched                            # the other expert's replica is never written
+        assert norm_err < 1e-5                      # sharded global norm = global norm
+        assert same and finite                      # MIN / MAX / SUM reduction of the strided images = all images on one rank
