@@ -89,7 +89,9 @@ class RamRaysDataset(Dataset):
                 if not bool(valid.any()):
                     continue
                 image_rays = image_rays[valid]
-                img = img[valid].to(torch.float32).div_(255.0)
+                # a TENSOR divisor: torch's CUDA div-by-Python-scalar multiplies by the rounded reciprocal (1 ulp off the
+                # reference's CPU `/ 255.0`, data/ram_rays_dataset.py:211); tensor / tensor is an IEEE division
+                img = img[valid].to(torch.float32) / torch.full((), 255.0, dtype=torch.float32, device=device)
                 rgbs.append(img.contiguous())
                 rays.append(image_rays.contiguous())
                 indices.append(torch.full((img.shape[0],), int(md.image_index), dtype=torch.int32, device=device))
