@@ -117,6 +117,7 @@ class HashGridEncoder(nn.Module):
         lv = torch.arange(L, dtype=torch.float32)
         res = torch.floor(self.min_res * (self.growth_factor ** lv)).to(torch.int32)
         self.register_buffer("level_resolutions", res, persistent=False)
+        self._res_host = [int(r) for r in res.tolist()]      # host copy made while the buffer is still on the CPU
         self.register_buffer("level_offsets", torch.arange(L, dtype=torch.int64) * self.hash_table_size,
                              persistent=False)
         self.register_buffer("hash_primes", torch.tensor([1, 2654435761, 805459861], dtype=torch.int64),
@@ -146,7 +147,7 @@ class HashGridEncoder(nn.Module):
         s = self._spec
         if s is None or s.interp != mode or s.res.device != self.level_resolutions.device:
             s = ops.GridSpec(self.levels, self.features_per_level, self.log2_hashmap_size,
-                             self.level_resolutions.to(torch.int32).contiguous(), mode)
+                             self.level_resolutions.to(torch.int32).contiguous(), mode, res_host=self._res_host)
             self._spec = s
         return s
 

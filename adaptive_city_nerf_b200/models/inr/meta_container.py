@@ -73,7 +73,7 @@ class MetaContainer(MetaModule):
                 raise NotImplementedError("bg_encoding: only 'spherical' is supported")
             self.bg_dir_enc = SHEncoder(levels=4, implementation="tcnn")
             self.bg_hidden_dim = int(bg_hidden)
-            # per-RAY head (N x 16 -> 32 -> 3): tiny, stays as torch layers (SURVEY 8b "Autograd")
+            # per-RAY head (N x 16 -> 32 -> 3): nn layers for the state dict; evaluated by acn_background_fwd/_bwd
             self.bg_mlp = nn.Sequential(
                 nn.Linear(self.bg_dir_enc.out_dim, self.bg_hidden_dim, bias=True), nn.ReLU(),
                 nn.Linear(self.bg_hidden_dim, 3, bias=True), nn.Sigmoid())
@@ -163,7 +163,7 @@ class MetaContainer(MetaModule):
         for sub, k in zip(subs, expert_ids):
             flat.append(sub.xyz_encoder.hash_table)
             flat += sub.fused_weights(sub_params[k])
-        return ops.RoutedFieldFn.apply(xd, seg, half, experts, nodes, y_out, *flat)
+        return ops.RoutedFieldFn.apply(xd, seg, half, experts, (nodes, torch.is_grad_enabled()), y_out, *flat)
 
     def _routed(self, x: torch.Tensor, sub_params: List) -> torch.Tensor:
         N, K = x.shape[0], len(self.submodules)
@@ -212,8 +212,16 @@ class MetaContainer(MetaModule):
             raise RuntimeError("background_color called but use_bg_nerf=False")
         if d.dim() not in (2, 3):
             raise ValueError(f"background_color expects (N,3) or (B,N,3), got {tuple(d.shape)}")
+        lin, out = self.bg_mlp[0], self.bg_mlp[2]
+        if (d.is_cuda and lin.weight.is_cuda and getattr(self.bg_dir_enc, "levels", 0) == 4 and lin.in_features == 16
+                and lin.out_features <= 64 and out.out_features == 3):
+            # one kernel: normalise, SH16, both layers, sigmoid (csrc/background.cu); fp16 result under autocast as the
+            # reference's autocast Linear gives
+            from .meta_ngp import autocast_half
+            d2 = d.reshape(-1, d.shape[-1])
+            rgb = ops.BackgroundFn.apply(d2, lin.weight, lin.bias, out.weight, out.bias, autocast_half(d.device))
+            return rgb.view(*d.shape[:-1], 3)
         dn = F.normalize(d, dim=-1).reshape(-1, 3)
-        lin = self.bg_mlp[0]
         enc = self.bg_dir_enc(dn).to(dtype=lin.weight.dtype, device=lin.weight.device)
         return self.bg_mlp(enc).view(*d.shape[:-1], 3)
 

@@ -196,7 +196,7 @@ class MetaNGP(MetaModule):
         x2 = x_d.reshape(-1, x_d.shape[-1])
         table = self.xyz_encoder.hash_table
         out = ops.ExpertFieldFn.apply(x2, None, None, table, self.xyz_encoder.grid_spec(),
-                                      self.box6(), self._use_half(x2.device), False, ops.grad_node_of(table),
+                                      self.box6(), self._use_half(x2.device), False, ops.grad_ctx(table),
                                       *self.fused_weights(params))
         return out.view(*x_d.shape[:-1], 4)
 
@@ -208,7 +208,7 @@ class MetaNGP(MetaModule):
         self._check_fused()
         table = self.xyz_encoder.hash_table
         out = ops.ExpertFieldFn.apply(None, rays, t_vals, table, self.xyz_encoder.grid_spec(),
-                                      self.box6(), self._use_half(rays.device), ray_major, ops.grad_node_of(table),
+                                      self.box6(), self._use_half(rays.device), ray_major, ops.grad_ctx(table),
                                       *self.fused_weights(params))
         return out.view(t_vals.shape[0], t_vals.shape[1], 4)
 

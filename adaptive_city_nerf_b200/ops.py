@@ -5,6 +5,7 @@ current CUDA stream.  Nothing here computes on the CPU."""
 from __future__ import annotations
 
 import ctypes as C_
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -130,8 +131,11 @@ def _ray_major_args(ray_major):
 class GridSpec:
     """Static description of one hash grid (device-resident resolution table)."""
 
-    def __init__(self, L: int, F: int, log2T: int, res: Tensor, interp: int):
+    def __init__(self, L: int, F: int, log2T: int, res: Tensor, interp: int, res_host: Optional[Sequence[int]] = None):
         self.L, self.F, self.log2T, self.res, self.interp = L, F, log2T, res, interp
+        #: the same resolutions as plain host ints (known at construction, so no device read): lets the fused forward
+        #: size the shared-memory lattices of the coarsest levels
+        self.res_host = (C_.c_int32 * len(res_host))(*[int(r) for r in res_host]) if res_host is not None else None
 
     @property
     def rows(self) -> int:
@@ -270,6 +274,46 @@ def field_bwd(enc: Tensor, dirs: Tensor, dirs_stride: int, dirs_group: int, ws: 
     return grads, d_enc
 
 
+#: set False to run the two-kernel forward (hash encode -> fp16 encoding in HBM -> MLP); tests cross-check the two
+FUSED_EXPERT_FWD = os.environ.get("ACN_FUSED_FWD", "1") != "0"
+#: stage the coarsest hash levels as dense lattices in shared memory inside the fused forward.  OFF: measured 7.2 ms vs
+#: 3.76 ms per 2^24 samples -- the 150 KB of lattices come out of the unified L1/shared-memory array, and the L1 that is
+#: left no longer holds the mid levels' rows
+STAGE_COARSE_LEVELS = os.environ.get("ACN_STAGE_COARSE", "0") != "0"
+
+
+def fused_fwd_ok(spec: "GridSpec", ws: Sequence[Tensor], half: bool) -> bool:
+    E, H, G, C = _field_dims(ws)
+    return (FUSED_EXPERT_FWD and half and spec.F == 2 and spec.L in (8, 16) and spec.interp != 0 and H == 64 and C == 64
+            and 1 <= G <= 15 and E == spec.L * spec.F)
+
+
+def render_expert_fwd(pos: Sequence[Tensor], table: Tensor, spec: "GridSpec", box6: Optional[Tensor], dirs: Tensor,
+                      dirs_stride: int, dirs_group: int, ws: Sequence[Tensor], want_enc: bool, ray_major=False,
+                      rng: Optional[Tensor] = None, enc: Optional[Tensor] = None, out: Optional[Tensor] = None):
+    """Fused hash encode + tcgen05 MLPs (acn_render_expert_fwd) -> (rgb_sigma (P,4) fp32, enc (P,E) fp16 or None).
+    pos: (rays (N,8), t (N,S)) or (x (P,>=3),); rng: device int32 [first, end) row range (buckets)."""
+    _, H, G, C = _field_dims(ws)
+    if len(pos) == 2:
+        rays, t = pos
+        x, xs, S, P = None, 3, t.shape[1], t.shape[0] * t.shape[1]
+    else:
+        x, xs, rays, t, S, P = pos[0], pos[0].stride(0), None, None, 1, pos[0].shape[0]
+    dev = dirs.device
+    if want_enc and enc is None:
+        enc = torch.empty(P, spec.L * spec.F, dtype=torch.float16, device=dev)
+    if out is None:
+        out = torch.empty(P, 4, dtype=torch.float32, device=dev)
+    rm, rm_dev = _ray_major_args(ray_major)
+    st = pack_weights(ws)
+    res_host = spec.res_host if (STAGE_COARSE_LEVELS and P >= 65536) else None
+    check(lib().acn_render_expert_fwd(ctx(dev), ptr(x), xs, ptr(rays), ptr(t), P, S, rm, rm_dev, ptr(rng), ptr(box6), ptr(table),
+                                      spec.L, spec.F, spec.log2T, ptr(_grid_res(spec, dev)), res_host, spec.interp, ptr(dirs),
+                                      dirs_stride, dirs_group, H, G, C, C_.byref(st), ptr(enc) if want_enc else None, ptr(out),
+                                      stream(dev)))
+    return out, (enc if want_enc else None)
+
+
 def render_expert_bwd(enc: Tensor, pos: Sequence[Tensor], dirs: Tensor, dirs_stride: int, dirs_group: int, ws: Sequence[Tensor],
                       d_rgb_sigma: Tensor, need: Sequence[bool], spec: "GridSpec", box6: Optional[Tensor], dtable: Tensor):
     """Fused MLP backward + table scatter (acn_render_expert_bwd): -> the 14 weight gradients; dtable is accumulated into."""
@@ -311,19 +355,30 @@ class ExpertFieldFn(torch.autograd.Function):
         ws = [dev_f32(w, "MLP weight") for w in ws]
         table_c = dev_f32(table, "hash_table")
         enc_dtype = torch.float16 if half else torch.float32
+        fused = fused_fwd_ok(spec, ws, half)
+        # grad mode is off inside forward(): the caller's mode rides in with the node (grad_ctx)
+        table_node, grad_on = table_node if isinstance(table_node, tuple) else (table_node, True)
+        want_enc = grad_on and any(ctx_.needs_input_grad)          # inference never materialises the encoding
         if rays is not None:
             rays = dev_f32(rays, "rays")
             t = dev_f32(t, "t_vals")
-            enc = hashgrid_fwd_rays(rays, t, table_c, spec, box6, enc_dtype, ray_major)
             dirs, dstride, dgroup = rays[:, 3:], 8, t.shape[1]
             pos = (rays, t)
+            if not fused:
+                enc = hashgrid_fwd_rays(rays, t, table_c, spec, box6, enc_dtype, ray_major)
         else:
             if x6.dtype != torch.float32 or not x6.is_contiguous():
                 x6 = x6.float().contiguous()
-            enc = hashgrid_fwd(x6, table_c, spec, box6, enc_dtype)
             dirs, dstride, dgroup = x6[:, 3:], x6.stride(0), 1
             pos = (x6,)
-        out = field_fwd(enc, dirs, dstride, dgroup, ws, half)
+            if not fused:
+                enc = hashgrid_fwd(x6, table_c, spec, box6, enc_dtype)
+        if fused:
+            out, enc = render_expert_fwd(pos, table_c, spec, box6, dirs, dstride, dgroup, ws, want_enc, ray_major)
+            if enc is None:
+                enc = out.new_empty(0)
+        else:
+            out = field_fwd(enc, dirs, dstride, dgroup, ws, half)
         ctx_.save_for_backward(enc, *pos, *(t_ for t_ in (box6,) if t_ is not None), *ws)
         ctx_.meta = (spec, half, len(pos), box6 is not None, dstride, dgroup, table.shape)
         ctx_.table_node = table_node
@@ -368,6 +423,13 @@ def grad_node_of(t: Optional[Tensor]):
     return t.grad_fn if t.grad_fn is not None else t.view_as(t).grad_fn.next_functions[0][0]
 
 
+def grad_ctx(t: Optional[Tensor]):
+    """(grad_node_of(t), is grad mode on) -- what ExpertFieldFn / RoutedFieldFn take as `table_node(s)`: grad mode is
+    always off inside an autograd.Function's forward, and a forward that will never be differentiated need not write
+    the encoding."""
+    return grad_node_of(t), torch.is_grad_enabled()
+
+
 def engine_wants(node) -> bool:
     """Inside a backward: will the running autograd pass deliver a gradient to `node`?  (True when unknown.)"""
     if node is None:
@@ -376,6 +438,41 @@ def engine_wants(node) -> bool:
         return bool(torch._C._will_engine_execute_node(node))
     except Exception:
         return True
+
+
+class BackgroundFn(torch.autograd.Function):
+    """Background head (models/inr/meta_container.py:347-382): d (N,>=3) -> rgb (N,3); differentiable w.r.t. the four
+    bg_mlp tensors (directions come from rays built under no_grad)."""
+
+    @staticmethod
+    def forward(ctx_, d, w1, b1, w2, b2, out_half):
+        if not d.is_cuda:
+            raise RuntimeError("background head needs CUDA tensors; there is no CPU path")
+        if d.dtype != torch.float32 or d.stride(1) != 1:
+            d = d.float().contiguous()                  # a (N,3) view of packed rays is read in place (row stride)
+        ws = [dev_f32(w, "bg_mlp weight") for w in (w1, b1, w2, b2)]
+        N, dev, Hb = d.shape[0], d.device, ws[0].shape[0]
+        out = torch.empty(N, 3, dtype=torch.float16 if out_half else torch.float32, device=dev)
+        check(lib().acn_background_fwd(ctx(dev), ptr(d), N, d.stride(0) if N else 3, *[ptr(w) for w in ws], Hb, ptr(out), _dt(out),
+                                       stream(dev)))
+        ctx_.save_for_backward(d, *ws)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx_, g):
+        d, *ws = ctx_.saved_tensors
+        N, dev, Hb = d.shape[0], d.device, ws[0].shape[0]
+        need = ctx_.needs_input_grad[1:5]
+        flat = torch.zeros(sum(w.numel() for w, n in zip(ws, need) if n), dtype=torch.float32, device=dev)
+        grads, off = [], 0
+        for w, n in zip(ws, need):
+            grads.append(flat[off:off + w.numel()].view(w.shape) if n else None)
+            off += w.numel() if n else 0
+        g = g.contiguous().float()
+        check(lib().acn_background_bwd(ctx(dev), ptr(d), N, d.stride(0) if N else 3, *[ptr(w) for w in ws], Hb, ptr(g),
+                                       *[ptr(x) for x in grads], stream(dev)))
+        return (None, *grads, None)
 
 
 # ------------------------------------------------------------------------------------------ stage 4
@@ -614,13 +711,20 @@ class RoutedFieldFn(torch.autograd.Function):
         tables = [dev_f32(tensors[15 * i], "hash_table") for i in range(n)]
         wss = [[dev_f32(w, "MLP weight") for w in tensors[15 * i + 1:15 * i + 15]] for i in range(n)]
         E = experts[0][0].L * experts[0][0].F
-        enc = torch.empty(cap, E, dtype=torch.float16 if half else torch.float32, device=dev)
+        fused = [fused_fwd_ok(spec, wss[i], half) for i, (spec, _) in enumerate(experts)]
+        table_nodes, grad_on = table_nodes if isinstance(table_nodes, tuple) else (table_nodes, True)
+        want_enc = grad_on and any(ctx_.needs_input_grad)   # inference with every expert fused never materialises the encoding
+        enc = (torch.empty(cap, E, dtype=torch.float16 if half else torch.float32, device=dev) if (want_enc or not all(fused))
+               else xd.new_empty(0))
         y = y_out if y_out is not None else torch.empty(cap, 4, dtype=torch.float32, device=dev)
         assert y.shape == (cap, 4) and y.dtype == torch.float32 and y.is_contiguous()
         dirs = xd[:, 3:]
         L_ = lib()
         for i, (spec, box6) in enumerate(experts):
             rng = seg[i:i + 2]
+            if fused[i]:
+                render_expert_fwd((xd,), tables[i], spec, box6, dirs, xd.stride(0), 1, wss[i], want_enc, rng=rng, enc=enc, out=y)
+                continue
             _, H, G, C = _field_dims(wss[i])
             check(L_.acn_hashgrid_fwd(ctx(dev), ptr(xd), cap, xd.stride(0), ptr(rng), ptr(box6), ptr(tables[i]), spec.L, spec.F,
                                       spec.log2T, ptr(_grid_res(spec, dev)), spec.interp, ptr(enc), _dt(enc), None, stream(dev)))

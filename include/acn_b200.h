@@ -148,6 +148,23 @@ int acn_field_bwd(acn_ctx*, const void* enc, int enc_dtype, const float* dirs, i
                   const acn_field_weights* w, int precision, const float* d_rgb_sigma,
                   const acn_field_grads* g, void* d_enc_or_null, int d_enc_dtype, acn_stream);
 
+/* Fused per-expert forward for the `active_module` / routed-bucket render path (SURVEY 8b acn_render_expert_fwd; replaces
+ * nerfs/ray_rendering.py:317-325 -> models/inr/meta_ngp.py:226-241 -> models/encodings.py:293-381 under autocast):
+ * world->unit, hash-grid encode and the tcgen05 field MLPs in ONE persistent, warp-specialised kernel -- producer warps
+ * write each point's fp16 encoding row into shared memory as the A operand of the first trunk layer; the encoding is
+ * never read back from HBM.  Positions / directions / row range as in acn_render_expert_bwd; ray_major as in
+ * acn_hashgrid_fwd_rays.  enc_f16_out_or_null (P, L*F): when given, the encoding is also written for the backward
+ * (bit-identical to acn_hashgrid_fwd's fp16 rows).  res_host_or_null: the same (L) resolutions in HOST memory; when
+ * given (and box6 is), the coarsest levels that fit are staged as dense lattices in shared memory.  F = 2, L in {8,16},
+ * Linear / Smoothstep, H = C = 64.  -> rgb_sigma (P,4) fp32, equal to acn_hashgrid_fwd(f16) + acn_field_fwd(ACN_F16). */
+int acn_render_expert_fwd(acn_ctx*, const float* x_or_null, int x_stride, const float* rays8_or_null,
+                          const float* t_vals_or_null, int64_t P, int S, int ray_major,
+                          const int32_t* ray_major_dev_or_null, const int32_t* range_or_null,
+                          const float* box6_or_null, const float* table, int L, int F, int log2T,
+                          const int32_t* res, const int32_t* res_host_or_null, int interp, const float* dirs,
+                          int dirs_stride, int dirs_group, int H, int G, int C, const acn_field_weights* w,
+                          void* enc_f16_out_or_null, float* rgb_sigma, acn_stream);
+
 /* Fused per-expert backward for the `active_module` / routed-bucket render path (SURVEY 8b acn_render_expert_bwd;
  * replaces autograd through nerfs/ray_rendering.py:317-325 -> models/inr/meta_ngp.py:226-241 ->
  * models/encodings.py:331-381): the tcgen05 MLP backward of acn_field_bwd(ACN_F16) and the hash-table gradient scatter
@@ -161,6 +178,17 @@ int acn_render_expert_bwd(acn_ctx*, const float* x_or_null, int x_stride, const 
                           int log2T, const int32_t* res, int interp, const void* enc_f16, const float* dirs,
                           int dirs_stride, int dirs_group, int H, int G, int C, const acn_field_weights* w,
                           const float* d_rgb_sigma, const acn_field_grads* g, float* dtable, acn_stream);
+
+/* Background head of the container (models/inr/meta_container.py:79-93 bg_dir_enc + bg_mlp, :347-382
+ * background_color): per ray direction F.normalize -> SH16 -> Linear(16,hidden) -> ReLU -> Linear(hidden,3) -> Sigmoid,
+ * one kernel forward, one backward.  dirs (N,>=3) rows of `stride` floats; w1 (hidden,16), b1 (hidden), w2 (3,hidden),
+ * b2 (3) fp32 nn.Linear layout; hidden <= 64.  rgb (N,3) fp32 or fp16.  The backward takes d_rgb (N,3) fp32 and
+ * ACCUMULATES the four weight gradients (each may be NULL); directions carry no gradient (rays are built under no_grad). */
+int acn_background_fwd(acn_ctx*, const float* dirs, int64_t N, int stride, const float* w1, const float* b1,
+                       const float* w2, const float* b2, int hidden, void* rgb, int rgb_dtype, acn_stream);
+int acn_background_bwd(acn_ctx*, const float* dirs, int64_t N, int stride, const float* w1, const float* b1,
+                       const float* w2, const float* b2, int hidden, const float* d_rgb, float* g_w1, float* g_b1,
+                       float* g_w2, float* g_b2, acn_stream);
 
 /* ---- stage 4: alpha compositing (nerfs/ray_rendering.py:114-165 volume_render) -------------- */
 int acn_composite_fwd(acn_ctx*, const float* rgb_sigma, const float* t_vals,
