@@ -14,6 +14,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libacn_b200.so"
 LIB_DEBUG = PKG / "libacn_b200_debug.so"
+LIB_COMM = PKG / "libacn_b200_comm.so"       # include/acn_b200_comm.h: NCCL-backed exchange entries for non-PyTorch hosts
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -31,10 +32,10 @@ def debug_sources():
 
 
 def needs_build() -> bool:
-    if not LIB.exists() or not LIB_DEBUG.exists():
+    if not LIB.exists() or not LIB_DEBUG.exists() or not LIB_COMM.exists():
         return True
-    t = min(LIB.stat().st_mtime, LIB_DEBUG.stat().st_mtime)
-    deps = list(CSRC.rglob("*.cu")) + list(CSRC.rglob("*.cuh")) + list((PKG.parent / "include").glob("*.h"))
+    t = min(LIB.stat().st_mtime, LIB_DEBUG.stat().st_mtime, LIB_COMM.stat().st_mtime)
+    deps = list(CSRC.rglob("*.cu")) + list(CSRC.rglob("*.cuh")) + list(CSRC.rglob("*.cpp")) + list((PKG.parent / "include").glob("*.h"))
     return any(d.stat().st_mtime > t for d in deps)
 
 
@@ -70,7 +71,18 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         objs = [str(o) for t, _, o, _ in jobs if t == tag]
         subprocess.run([nvcc, "-shared", "-o", str(lib), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
                         "-Xcompiler", "-fPIC"], check=True)
+    build_comm()
     return LIB
+
+
+def build_comm() -> Path:
+    """g++ (host code only): links libnccl + libcudart.  In a PyTorch process the loader resolves libnccl.so.2 to the
+    copy torch has already loaded."""
+    cuda = Path(os.environ.get("CUDA_HOME", "/usr/local/cuda"))
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-I", str(cuda / "include"),
+           str(CSRC / "comm" / "comm.cpp"), "-o", str(LIB_COMM), "-L", str(cuda / "lib64"), "-lcudart", "-lnccl"]
+    subprocess.run(cmd, check=True)
+    return LIB_COMM
 
 
 if __name__ == "__main__":

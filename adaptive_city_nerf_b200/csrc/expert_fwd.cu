@@ -22,19 +22,22 @@
 // Row order.  Sample-major (explicit points, buckets, shuffled training rays): tile g holds points [128 g, 128 g + 128).
 // Ray-major (frames, acn_rays_coherent): tile g = (ray block, sample group) holds 4 consecutive samples of 32 adjacent
 // rays, one sample per producer warp, so the lanes of a warp share cells up to the mid levels (hashgrid.cu).
-#include <stdlib.h>
 #include "field_mma.cuh"
 
 namespace {
 
 constexpr int XNC = 2;                       // consumer warpgroups
-constexpr int XNP = 16;                      // producer warps
-constexpr int XTHREADS = XNC * 128 + XNP * 32;
-constexpr int XST = 4;                       // tile stages: one per production slot (the slots stagger themselves after the first round)
-constexpr int XSLOTS = XNP / 4;              // tiles in production at a time
 constexpr uint32_t XTMEM_COLS = XNC * 128;
+// NP producer warps: NP / 4 tiles in production at a time, one tile stage per production slot (the slots stagger
+// themselves after the first round).  16 producer + 8 consumer warps = 768 threads leave every thread 80 registers.
+template <int NP> struct XCfg {
+    static constexpr int threads = XNC * 128 + NP * 32;
+    static constexpr int slots = NP / 4;
+    static constexpr int stages = NP / 4;
+};
+constexpr int XNP = 16;
 
-template <int E> struct XMap {
+template <int E, int XST> struct XMap {
     static constexpr uint32_t w = 0;
     static constexpr uint32_t stages = (wmap(E).end + 1023u) & ~1023u;
     static constexpr uint32_t tile_bytes = TM * E * 2;
@@ -51,7 +54,6 @@ struct XArgs {
     int ray_major; const int32_t* ray_major_dev;
     const float* box6;
     const float* table; int L; int log2T; const int32_t* res; int interp;
-    int pair_mode;                                    // 1: per-lane paired 16-byte gathers; 0: only when the whole warp agrees
     int staged_levels; uint32_t lattice_off[2];       // levels [0, staged_levels) live in shared memory at these byte offsets
 };
 
@@ -82,34 +84,17 @@ __device__ __forceinline__ float2 blend8(const float2* f, const GridCell& g) {
     return o;
 }
 
-// x-neighbours of an even x0 are rows r and r^1 (the hash is x ^ y*p1 ^ z*p2): ONE aligned 16-byte load fetches both.
-// Every lane loads the pair that holds its x0 corner; only the lanes whose x0 is odd load a second pair for x0 + 1
-// (predicated, no divergence).  A scattered 16-byte and a scattered 8-byte load cost the L1 the same wavefront, so a
-// level costs 4 + 4/2 = 6 wavefronts per lane on average instead of 8 (profiles/r02_l2_peaks.json: the gather rate is
-// per request, not per byte).  Same table values, hence the same features.
-__device__ __forceinline__ float2 level_from_table(const float* __restrict__ lt, const GridCell& g, uint32_t mask, int pair_mode) {
+// One level from the table: eight 8-byte gathers; the x-neighbours of an even x0 are rows r and r^1 (the hash is
+// x ^ y*p1 ^ z*p2), so when the WHOLE warp sits on even x0 (frames; hashgrid.cu) four aligned 16-byte loads fetch them.
+// Measured and dropped (profiles/r02_v5_fused_fwd_variants.txt): per-lane pairs with the second load predicated on an odd
+// x0 (6 instead of 8 requests per lane and level, but 3.91 vs 3.76 ms: four more registers per load in flight), and 24
+// producer warps at 48 registers with setmaxnreg (4.19 ms) -- the gathers are bound in the L1 data pipe, not by latency.
+__device__ __forceinline__ float2 level_from_table(const float* __restrict__ lt, const GridCell& g, uint32_t mask) {
     float2 f[8];
-    const float4* lt4 = reinterpret_cast<const float4*>(lt);
-    const uint32_t yp0 = g.y0 * 2654435761u, yp1 = yp0 + 2654435761u;
-    const uint32_t zp0 = g.z0 * 805459861u, zp1 = zp0 + 805459861u;
-    const bool xodd = (g.x0 & 1u) != 0u;
-    if (pair_mode == 1) {
-#pragma unroll
-        for (int yz = 0; yz < 4; ++yz) {
-            const uint32_t h = ((yz & 2) ? yp1 : yp0) ^ ((yz & 1) ? zp1 : zp0);
-            const uint32_t ra = (g.x0 ^ h) & mask;
-            const float4 va = __ldg(lt4 + (ra >> 1));
-            const bool aodd = ra & 1u;
-            f[yz] = aodd ? make_float2(va.z, va.w) : make_float2(va.x, va.y);
-            float2 fb = aodd ? make_float2(va.x, va.y) : make_float2(va.z, va.w);      // row ra ^ 1 = the x0 + 1 corner when x0 is even
-            if (xodd) {
-                const uint32_t rb = ((g.x0 + 1u) ^ h) & mask;
-                const float4 vb = __ldg(lt4 + (rb >> 1));
-                fb = (rb & 1u) ? make_float2(vb.z, vb.w) : make_float2(vb.x, vb.y);
-            }
-            f[4 + yz] = fb;
-        }
-    } else if (__all_sync(0xffffffffu, !xodd)) {      // whole warp on even x0 (frames; hashgrid.cu)
+    if (__all_sync(0xffffffffu, !(g.x0 & 1u))) {
+        const float4* lt4 = reinterpret_cast<const float4*>(lt);
+        const uint32_t yp0 = g.y0 * 2654435761u, yp1 = yp0 + 2654435761u;
+        const uint32_t zp0 = g.z0 * 805459861u, zp1 = zp0 + 805459861u;
 #pragma unroll
         for (int yz = 0; yz < 4; ++yz) {
             const uint32_t h = ((yz & 2) ? yp1 : yp0) ^ ((yz & 1) ? zp1 : zp0);
@@ -139,8 +124,8 @@ __device__ __forceinline__ float2 level_from_lattice(uint32_t base, int R1, cons
     return blend8(f, g);
 }
 
-template <int E>
-__global__ void __launch_bounds__(XTHREADS, 1) k_expert_fwd(
+template <int E, int NP>
+__global__ void __launch_bounds__(XCfg<NP>::threads, 1) k_expert_fwd(
     XArgs a, const float* __restrict__ dirs, int dstride, int dgroup, int64_t P, int G, acn_field_weights w,
     __half* __restrict__ enc_out, float4* __restrict__ rgb_sigma, const int32_t* __restrict__ range)
 {
@@ -151,7 +136,9 @@ __global__ void __launch_bounds__(XTHREADS, 1) k_expert_fwd(
         a.x += r0 * a.xs; dirs += r0 * dstride; rgb_sigma += r0;
         if (enc_out) enc_out += r0 * E;
     }
-    using M = XMap<E>;
+    using CF = XCfg<NP>;
+    constexpr int XST = CF::stages, XSLOTS = CF::slots, XTHREADS = CF::threads;
+    using M = XMap<E, XST>;
     constexpr WMap wm = wmap(E);
     constexpr int EC = E / 8;
     const uint32_t sb = umma::smem_u32(smem_raw);
@@ -248,7 +235,7 @@ __global__ void __launch_bounds__(XTHREADS, 1) k_expert_fwd(
                     const GridCell g = grid_cell(u0, u1, u2, umma::lds_f32(sb + M::res + 4u * l), a.interp);
                     float2 o;
                     if (l < a.staged_levels) o = level_from_lattice(sb + M::lattice + a.lattice_off[l & 1], (int)umma::lds_f32(sb + M::res + 4u * l) + 1, g);
-                    else o = level_from_table(a.table + (((size_t)l << a.log2T) << 1), g, hmask, a.pair_mode);
+                    else o = level_from_table(a.table + (((size_t)l << a.log2T) << 1), g, hmask);
                     const __half2 hv = __floats2half2_rn(o.x, o.y);
                     h[j] = *reinterpret_cast<const uint32_t*>(&hv);
                 }
@@ -370,9 +357,10 @@ __global__ void __launch_bounds__(XTHREADS, 1) k_expert_fwd(
 
 template <int E>
 int launch_expert_fwd(acn_ctx* ctx, XArgs a, const float* dirs, int dstride, int dgroup, int64_t P, int G,
-                      const acn_field_weights* w, void* enc_out, float* rgb_sigma, const int32_t* range,
-                      const int32_t* res_host_or_null, cudaStream_t st) {
-    using M = XMap<E>;
+                          const acn_field_weights* w, void* enc_out, float* rgb_sigma, const int32_t* range,
+                          const int32_t* res_host_or_null, cudaStream_t st) {
+    constexpr int NP = XNP;
+    using M = XMap<E, XCfg<NP>::stages>;
     // coarse levels staged in shared memory: as many of levels 0, 1 as fit beside the weights and the tile ring
     uint32_t lat_bytes = 0;
     a.staged_levels = 0;
@@ -387,16 +375,15 @@ int launch_expert_fwd(acn_ctx* ctx, XArgs a, const float* dirs, int dstride, int
         }
     }
     uint32_t smem = M::lattice + lat_bytes;
-    if (const char* e = getenv("ACN_DEBUG_EXTRA_SMEM")) smem += (uint32_t)atoi(e);      // A/B knob: L1 capacity sensitivity
-    if (const char* e = getenv("ACN_FWD_PAIR")) a.pair_mode = atoi(e);
     ACN_REQUIRE((int)smem <= ctx->max_smem_optin, ACN_EUNSUPPORTED, "acn_render_expert_fwd: needs %u B shared memory", smem);
     const int64_t tiles_a = (P + TM - 1) / TM;
     const int64_t tiles_b = a.rays ? ((a.N + 31) / 32) * ((a.S + 3) / 4) : 0;
     int64_t grid = tiles_a > tiles_b ? tiles_a : tiles_b;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
     if (grid < 1) grid = 1;
-    ACN_CUDA(cudaFuncSetAttribute(k_expert_fwd<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_expert_fwd<E><<<(int)grid, XTHREADS, smem, st>>>(a, dirs, dstride, dgroup, P, G, *w, (__half*)enc_out, (float4*)rgb_sigma, range);
+    ACN_CUDA(cudaFuncSetAttribute(k_expert_fwd<E, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_expert_fwd<E, NP><<<(int)grid, XCfg<NP>::threads, smem, st>>>(a, dirs, dstride, dgroup, P, G, *w, (__half*)enc_out,
+                                                                             (float4*)rgb_sigma, range);
     ACN_CHECK_LAUNCH();
     return ACN_OK;
 }
@@ -433,7 +420,6 @@ extern "C" int acn_render_expert_fwd(acn_ctx* ctx, const float* x_or_null, int x
     a.x = from_rays ? nullptr : x_or_null; a.xs = x_stride;
     a.rays = rays8_or_null; a.t = t_vals_or_null; a.S = from_rays ? S : 1; a.N = from_rays ? P / S : 0;
     a.ray_major = ray_major; a.ray_major_dev = ray_major_dev_or_null;
-    a.pair_mode = 1;
     a.box6 = box6_or_null; a.table = table; a.L = L; a.log2T = log2T; a.res = res; a.interp = interp;
     cudaStream_t st = (cudaStream_t)stream;
     if (L == 8) return launch_expert_fwd<16>(ctx, a, dirs, dirs_stride, dirs_group, P, G, w, enc_f16_out_or_null, rgb_sigma, range_or_null, res_host_or_null, st);

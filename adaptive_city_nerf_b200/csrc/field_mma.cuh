@@ -305,5 +305,112 @@ __device__ __forceinline__ void epi_hidden_tmem(uint32_t acc) {
     umma::wait_st();
 }
 
-}  // namespace
+// ======================================================================================================
+// backward: 2 slots x 1 tile, 256 threads per slot (two threads per row)
+// ======================================================================================================
+constexpr int BNS = 2;
+// TMEM columns: per-slot D windows, then the persistent weight-gradient accumulators.  Bias gradients ride inside
+// them (see "ones" below) except for the first trunk layer, which keeps a separate G^T 1 accumulator (8 columns).
+constexpr uint32_t COL_ACC0 = 128;
+constexpr uint32_t COL_WC1 = 128, COL_WT1 = 208, COL_WC0 = 288, COL_WT0 = 320, COL_WC2T = 384, COL_WHDT = 400, COL_BT0 = 416;
+constexpr uint32_t COL_ACC1 = 432;
+constexpr uint32_t BWD_TMEM_COLS = 512;
+constexpr int HW = 72;   // hidden activation tiles are 72 columns wide: 64 units + a chunk [1,0,0,0,0,0,0,0]
 
+// Per-slot tiles (byte offsets inside the slot block).  The four hidden tiles carry a constant ONES column (col 64):
+// as the B operand of a weight-gradient MMA (N = 72) it makes column 64 of dW the bias gradient, as the A operand
+// of a transposed one (M = 128) it makes lane 64 the bias gradient -- no separate G^T 1 MMAs (48 of 140 per tile).
+// The colour-MLP input has a free column (31) that plays the same role.  `dg` holds d rgb_raw (forward end) and
+// later the heads gradient: their lifetimes are disjoint.  MN-major M=128 views read up to 2 KB past a tile into
+// whatever follows, which must be mapped shared memory.
+template <int E> struct SlotMap {
+    static constexpr uint32_t dg = 0, c2 = 4096, c1 = c2 + TM * HW * 2, h2 = c1 + TM * HW * 2, h1 = h2 + TM * HW * 2;
+    static constexpr uint32_t xe = h1 + TM * HW * 2, cin = xe + TM * E * 2, bytes = cin + TM * 32 * 2;
+};
+template <int E> struct BwdMap {
+    static constexpr uint32_t slots = 0;
+    static constexpr uint32_t w = BNS * SlotMap<E>::bytes;
+    static constexpr uint32_t bars = (w + wmap(E).end + 127u) & ~127u;     // per slot: done_d, done_w
+    static constexpr uint32_t tmem_ptr = bars + BNS * 2 * 8u;
+    static constexpr uint32_t res = tmem_ptr + 16u;                         // fused scatter: float resolution per level (16)
+    static constexpr uint32_t bytes = res + 64u;
+};
+
+// Fused table scatter (acn_render_expert_bwd): instead of storing d_enc, the thread that holds 16 columns (8 levels) of
+// a point's encoding gradient forms the point's cell at each of those levels and adds w_corner * g to the 8 corner rows
+// of the table gradient -- models/encodings.py:331-381 differentiated w.r.t. the table, the same arithmetic as
+// k_hashgrid_bwd.  The 2 GiB (P,E) fp32 d_enc round trip through HBM disappears and the REDs (bound by the per-SM
+// atomic issue rate, not by anything the MMAs use) overlap the tensor-core work of the tiles in flight.
+struct ScatterArgs {
+    const float* x; int xs;                           // explicit positions (P,>=3), or
+    const float* rays; const float* t; int S;         // rays (N,8) + t (N,S): p = o + d*t (nerfs/ray_rendering.py:317)
+    const float* box6;                                // [min, extent] (world -> unit) or null
+    float* dtable; int L; int log2T; const int32_t* res; int interp;
+};
+
+// power-of-two loss scale from max |dL/dy|: max * scale in [2^9, 2^10)
+__device__ __forceinline__ float grad_scale_from_max(float mx) {
+    if (!(mx > 0.0f) || !(mx < 3.0e38f)) return 1.0f;
+    int e;
+    frexpf(mx, &e);                       // mx = m * 2^e, m in [0.5, 1)
+    e = 10 - e;
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    return ldexpf(1.0f, e);
+}
+
+__global__ void __launch_bounds__(256) k_absmax(const float4* __restrict__ x, int64_t n4, unsigned int* __restrict__ out,
+                                                const int32_t* __restrict__ range) {
+    if (range) { const int64_t r0 = __ldg(range); x += r0; n4 = __ldg(range + 1) - r0; }
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = ld_stream_f4(x + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));   // fmaxf drops NaNs
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
+}
+
+// backward epilogue, part 1: 32 columns of D -> fp16 -> * [act > 0] in registers (the act tile is only read)
+__device__ __forceinline__ void epi_mask32_load(uint32_t tmem_d, int col0, const Tile& act, int row, uint4* o) {
+    float v[32];
+    ld32(tmem_d + col0, v);
+    uint4 a[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[q] = lds128(chunk_addr(act, row, col0 / 8 + q));
+    umma::wait_ld();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        o[q].x = hmask2(pack_h2(v[8 * q + 0], v[8 * q + 1]), a[q].x);
+        o[q].y = hmask2(pack_h2(v[8 * q + 2], v[8 * q + 3]), a[q].y);
+        o[q].z = hmask2(pack_h2(v[8 * q + 4], v[8 * q + 5]), a[q].z);
+        o[q].w = hmask2(pack_h2(v[8 * q + 6], v[8 * q + 7]), a[q].w);
+    }
+}
+// part 2 (after the weight-gradient MMAs that read the act tile have completed): overwrite it in place
+__device__ __forceinline__ void epi_mask32_store(const Tile& act, int row, int col0, const uint4* o) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sts128(chunk_addr(act, row, col0 / 8 + q), o[q]);
+}
+
+int check_dims(const char* fn, int enc_dtype, int E, int H, int G, int C, const void* enc) {
+    ACN_REQUIRE(enc_dtype == ACN_F16, ACN_EUNSUPPORTED, "%s(f16): the tensor-core path takes fp16 encodings (cast in the caller)", fn);
+    ACN_REQUIRE(H == 64 && C == 64, ACN_EUNSUPPORTED, "%s(f16): hidden widths must be 64 (got H=%d, C=%d)", fn, H, C);
+    ACN_REQUIRE(E == 16 || E == 32 || E == 48 || E == 64, ACN_EUNSUPPORTED, "%s(f16): encoding width %d not in {16,32,48,64}", fn, E);
+    ACN_REQUIRE(G >= 1 && G <= 15, ACN_EUNSUPPORTED, "%s(f16): geo_feat_dim %d outside [1,15]", fn, G);
+    ACN_REQUIRE(((uintptr_t)enc & 15) == 0, ACN_EINVAL, "%s(f16): enc must be 16-byte aligned", fn);
+    return ACN_OK;
+}
+
+
+int absmax_word(acn_ctx* ctx, const char* fn, const float* d_rgb_sigma, int64_t P, const int32_t* range, cudaStream_t st, unsigned int** out) {
+    unsigned int* slot = acn_scratch_word(ctx);
+    ACN_REQUIRE(slot != nullptr, ACN_ECUDA, "%s(f16): no context scratch", fn);
+    ACN_CUDA(cudaMemsetAsync(slot, 0, sizeof(unsigned int), st));
+    k_absmax<<<acn_grid_1d(P, 256 * 8, (int64_t)ctx->sm_count * 8), 256, 0, st>>>((const float4*)d_rgb_sigma, P, slot, range);
+    ACN_CHECK_LAUNCH();
+    *out = slot;
+    return ACN_OK;
+}
+
+}  // namespace

@@ -50,6 +50,20 @@ def test_debug_library_is_separate_and_complete(built_lib):
     assert d.acn_version() == 200
 
 
+def test_comm_library_exports_its_header(built_lib):
+    """libacn_b200_comm.so (NCCL-backed exchange entries for non-PyTorch hosts) exports exactly what
+    include/acn_b200_comm.h declares and binds through ctypes; no collective is called here (no GPU)."""
+    from adaptive_city_nerf_b200 import build, comm
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "acn_b200_comm.h").read_text(), flags=re.S)
+    want = sorted(set(re.findall(r"\b(acn_[a-z0-9_]+)\s*\(", text)))
+    out = subprocess.run(["nm", "-D", "--defined-only", str(build.LIB_COMM)], capture_output=True, text=True, check=True).stdout
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("acn_"))
+    assert exported == want and len(want) == 8
+    l = comm.comm_lib()
+    assert l.acn_comm_rank(None, None, None) != 0 and b"null communicator" in l.acn_comm_last_error()
+    assert len(l.acn_alltoall_samples.argtypes) == 7
+
+
 def test_ctypes_table_matches_header(built_lib):
     from adaptive_city_nerf_b200 import _lib
     assert sorted(_lib.SIGNATURES) == header_symbols()
@@ -233,7 +247,7 @@ def test_integration_md_ctypes_example_matches_the_header():
     """The argument counts of the calls shown in INTEGRATION.md section 2 are the header's."""
     from adaptive_city_nerf_b200 import _lib
     text = (ROOT / "INTEGRATION.md").read_text()
-    for name in ("acn_hashgrid_fwd_rays", "acn_field_fwd", "acn_composite_fwd"):
+    for name in ("acn_hashgrid_fwd_rays", "acn_field_fwd", "acn_render_expert_fwd", "acn_composite_fwd"):
         m = re.search(r"lib\." + name + r"\((.*?)\)\s*(?:#|\n[a-z#`])", text, flags=re.S)
         assert m, name
         args = re.sub(r"\([^()]*\)", "", m.group(1))              # drop nested calls such as C.c_int64(N)

@@ -118,8 +118,8 @@ def test_render_rays_same_image_and_gradients_with_either_forward():
             torch.manual_seed(5)
             with torch.autocast("cuda", dtype=torch.float16):
                 tr = render_rays(m, rays, ray_samples=32, active_module=0)
-            (tr["rgb"].float().square().mean() + tr["depth"].float().mean() * 0.1).backward()
-            res[fused] = (ev["rgb"].float(), ev["depth"].float(), tr["rgb"].float(),
+            (tr[0].float().square().mean() + tr[1].float().mean() * 0.1).backward()
+            res[fused] = (ev[0].float(), ev[1].float(), tr[0].float().detach(),
                           {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
         finally:
             ops.FUSED_EXPERT_FWD = True

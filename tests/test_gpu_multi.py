@@ -189,3 +189,53 @@ def test_per_expert_training_and_mask_generation_shard_across_gpus():
         assert untouched                            # the other expert's replica is never written
         assert norm_err < 1e-5                      # sharded global norm = global norm
         assert same and finite                      # MIN / MAX / SUM reduction of the strided images = all images on one rank
+
+
+def _worker_comm(rank, world, port, ret):
+    """The C-ABI communicator (libacn_b200_comm.so, include/acn_b200_comm.h) driven with raw pointers as a C host would:
+    the rendezvous id travels over a host channel (here a TCP store), then all-reduce, all-gather and the variable-size
+    all-to-all of routed sample rows."""
+    from torch.distributed import TCPStore
+    from adaptive_city_nerf_b200 import comm
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    store = TCPStore("127.0.0.1", port, world, is_master=(rank == 0))
+    if rank == 0:
+        store.set("uid", comm.unique_id())
+    c = comm.Communicator(dev, store.get("uid"), rank, world)
+    try:
+        x = torch.arange(1000, dtype=torch.float32, device=dev) * (rank + 1)
+        c.allreduce_(x)
+        ok = bool(torch.equal(x, torch.arange(1000, dtype=torch.float32, device=dev) * sum(r + 1 for r in range(world))))
+        h = torch.full((7,), float(rank + 1), dtype=torch.float16, device=dev)
+        c.allreduce_(h, comm.OP_MAX)
+        ok &= bool((h == world).all())
+        counts = torch.tensor([10 * rank + 3, rank + 1], dtype=torch.int32, device=dev)      # rows this rank sends to rank 0, 1
+        allc = c.allgather(counts)                                                             # (world, world)
+        ok &= allc.tolist() == [[10 * r + 3, r + 1] for r in range(world)]
+        send_counts = counts.tolist()
+        recv_counts = [int(allc[r, rank]) for r in range(world)]
+        rows = torch.empty(sum(send_counts), 6, device=dev)
+        off = 0
+        for dst, n in enumerate(send_counts):           # row value encodes (source, destination, index)
+            rows[off:off + n] = (100 * rank + 10 * dst) + torch.arange(n, device=dev, dtype=torch.float32)[:, None] / 64
+            off += n
+        got = c.alltoall_samples(rows, send_counts, recv_counts)
+        off = 0
+        for src, n in enumerate(recv_counts):
+            want = (100 * src + 10 * rank) + torch.arange(n, device=dev, dtype=torch.float32)[:, None] / 64
+            ok &= bool(torch.equal(got[off:off + n], want.expand(n, 6)))
+            off += n
+        torch.cuda.synchronize()
+        ret[rank] = ok
+    finally:
+        c.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_c_abi_communicator_two_gpus():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_comm, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
