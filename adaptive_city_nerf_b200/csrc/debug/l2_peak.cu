@@ -56,7 +56,38 @@ __global__ void __launch_bounds__(256) k_l2_red(uint8_t* __restrict__ buf, uint3
     }
 }
 
+// RED rate as a function of the warps an SM has and of how full their RED instructions are: `active_lanes` of every
+// warp issue the 16-byte REDs, the others skip them (predicated), `work` dependent integer operations separate two REDs
+// of a thread.  What the fused backward can get out of its 16 resident warps is read off this, not off the
+// full-occupancy peak.
+__global__ void k_red_probe(uint8_t* __restrict__ buf, uint32_t mask, int iters, int active_lanes, int work) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = (int)(threadIdx.x & 31) < active_lanes;
+    uint32_t s = mix(tid * 2654435761u + 7u);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s = s * 1664525u + 1013904223u;
+            for (int k = 0; k < work; ++k) s = s * 1664525u + 1013904223u + (uint32_t)k;
+            const uint32_t off = mix(s) & mask & ~15u;
+            if (on) atomicAdd(reinterpret_cast<float4*>(buf + off), make_float4(1.0f, 1.0f, 1.0f, 1.0f));
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int acn_debug_red_probe(acn_ctx* ctx, void* buf, int64_t buf_bytes, int iters, int grid, int block, int active_lanes,
+                                   int work, acn_stream stream) {
+    ACN_CHECK_CTX(ctx);
+    ACN_REQUIRE(buf && buf_bytes >= 4096 && (buf_bytes & (buf_bytes - 1)) == 0 && buf_bytes <= ((int64_t)1 << 32), ACN_EINVAL,
+                "acn_debug_red_probe: buf_bytes must be a power of two in [4 KiB, 4 GiB]");
+    ACN_REQUIRE(iters >= 1 && grid >= 1 && block >= 32 && block <= 1024 && block % 32 == 0 && active_lanes >= 1 && active_lanes <= 32 && work >= 0,
+                ACN_EINVAL, "acn_debug_red_probe: bad arguments");
+    k_red_probe<<<grid, block, 0, (cudaStream_t)stream>>>((uint8_t*)buf, (uint32_t)(buf_bytes - 1), iters, active_lanes, work);
+    ACN_CHECK_LAUNCH();
+    return ACN_OK;
+}
 
 extern "C" int acn_debug_l2_probe(acn_ctx* ctx, int mode, int bytes_per_access, void* buf, int64_t buf_bytes, int iters,
                                   int grid, float* sink, acn_stream stream) {

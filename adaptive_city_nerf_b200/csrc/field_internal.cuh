@@ -14,7 +14,3 @@ int acn_field_fwd_tc(acn_ctx* ctx, const void* enc, int enc_dtype, const float* 
 int acn_field_bwd_tc(acn_ctx* ctx, const void* enc, int enc_dtype, const float* dirs, int dirs_stride, int dirs_group,
                      int64_t P, int E, int H, int G, int C, const acn_field_weights* w, const float* d_rgb_sigma,
                      const acn_field_grads* g, float* d_enc, const int32_t* range, cudaStream_t st);
-// warp-specialised fused backward (expert_bwd.cu); scatter_args points at field_mma.cuh's ScatterArgs
-int acn_expert_bwd_ws(acn_ctx* ctx, int E, const void* enc, const float* dirs, int dirs_stride, int dirs_group, int64_t P, int G,
-                      const acn_field_weights* w, const float* d_rgb_sigma, const unsigned int* absmax, const acn_field_grads* g,
-                      const void* scatter_args, const int32_t* range, cudaStream_t st);

@@ -35,7 +35,6 @@
 // +2*RG per K step); an MN-major A view wider than its tile reads on into the following shared memory and leaves
 // garbage in the TMEM lanes beyond the tile's columns, which are never read; an M = 64 accumulator keeps row m in lane
 // (m >> 4) * 32 + (m & 15); a TMEM A operand holds row r in lane r, two consecutive K elements per 32-bit column.
-#include <stdlib.h>
 #include "field_mma.cuh"
 
 namespace {
@@ -718,10 +717,6 @@ extern "C" int acn_render_expert_bwd(acn_ctx* ctx, const float* x_or_null, int x
     rc = absmax_word(ctx, fn, d_rgb_sigma, P, range_or_null, st, &slot);
     if (rc) return rc;
     const ScatterArgs sc{ from_rays ? nullptr : x_or_null, x_stride, rays8_or_null, t_vals_or_null, S, box6_or_null, dtable, L, log2T, res, interp };
-    // default: the warp-specialised kernel (expert_bwd.cu).  ACN_BWD_WS=0 selects the single-role kernel below (every MLP
-    // thread scatters its own columns between its epilogues), kept as the cross-check of tests/test_gpu_tc.py.
-    static const bool ws = []() { const char* e = getenv("ACN_BWD_WS"); return !(e && e[0] == '0'); }();
-    if (ws) return acn_expert_bwd_ws(ctx, E, enc_f16, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, &sc, range_or_null, st);
     if (E == 16) return launch_bwd<16>(ctx, enc_f16, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, nullptr, &sc, range_or_null, st);
     return launch_bwd<32>(ctx, enc_f16, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, nullptr, &sc, range_or_null, st);
 }

@@ -52,6 +52,13 @@ int acn_debug_field_trace(acn_ctx*, long long* trace_or_null);
 int acn_debug_l2_probe(acn_ctx*, int mode, int bytes_per_access, void* buf, int64_t buf_bytes, int iters, int grid,
                        float* sink, acn_stream);
 
+/* 16-byte scattered REDs from `grid` CTAs of `block` threads in which only `active_lanes` lanes of every warp issue
+ * them, with `work` dependent integer operations between two REDs of a thread (tools/red_probe.py): the RED rate an SM
+ * reaches with few resident warps and partly filled RED instructions.  REDs per launch = grid * block / 32 * active_lanes
+ * * iters * 8. */
+int acn_debug_red_probe(acn_ctx*, void* buf, int64_t buf_bytes, int iters, int grid, int block, int active_lanes, int work,
+                        acn_stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
