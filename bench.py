@@ -47,10 +47,11 @@ FUSED_BWD_BYTES = 2 * 1024 + 64 + 16
 GRID_CORNERS = 16 * 8                          # (level, corner) table rows a sample gathers forward / updates backward
 # committed ncu captures (`--set full`, one launch of each kernel at this workload): kernel name in the capture per entry
 # point; `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of that launch is READ FROM THESE FILES
-NCU_FILES = ["profiles/r02_v3_fused_bwd_ncu_full_summary.csv", "profiles/r01_v3_stages_ncu_full_summary.csv"]
+NCU_FILES = ["profiles/r02_v5_stages_ncu_full_summary.csv", "profiles/r02_v3_fused_bwd_ncu_full_summary.csv",
+             "profiles/r01_v3_stages_ncu_full_summary.csv"]
 NCU_KERNEL = {"acn_hashgrid_fwd_rays": "k_hashgrid_fwd<2, __half>", "acn_hashgrid_bwd_rays": "k_hashgrid_bwd_march<float>",
               "acn_field_fwd": "k_field_fwd_mma<32, 0>", "acn_field_bwd": "k_field_bwd_mma<32, 0>",
-              "acn_render_expert_bwd": "k_field_bwd_mma<32, 0, 1>", "acn_render_expert_fwd": "k_expert_fwd<32>", "acn_composite_fwd": "k_composite_fwd",
+              "acn_render_expert_bwd": "k_field_bwd_mma<32, 0, 1>", "acn_render_expert_fwd": "k_expert_fwd<32, 16>", "acn_composite_fwd": "k_composite_fwd",
               "acn_composite_bwd": "k_composite_bwd"}
 
 
@@ -327,6 +328,16 @@ def container_records(args, world, rank, dev):
 
             ms = timed(step, max(3, args.steps // 2))
             rec[tag] = {"rays_per_rank": n, "rays_total": n * world, "ms_per_step": round(ms, 3), "rays_per_s": n * world / (ms * 1e-3)}
+            # what bounds a sharded step from above: the routed rows each OWNER evaluates (all ranks' rays, outside the timed region)
+            with torch.no_grad():
+                from adaptive_city_nerf_b200 import ops as _ops
+                tt = _ops.sample_stratified(r, SAMPLES, None)
+                cnt = _ops.route_count_rays(r, tt, full.centroids, 2, 1.05).to(torch.float64)
+                if world > 1:
+                    dist.all_reduce(cnt)
+                per_owner = torch.zeros(world, dtype=torch.float64, device=dev).index_add_(0, torch.arange(K, device=dev) % world, cnt)
+                rec[tag]["routed_rows_per_owner"] = {"max": int(per_owner.max()), "mean": float(per_owner.mean()),
+                                                     "max_over_mean": round(float(per_owner.max() / per_owner.mean()), 3)}
             if args.graph:   # the same step as ONE CUDA graph per rank: nothing in it reads back to the host (the all-gather of
                 try:         # the counts, the device-side barriers and the peer-memory kernels are captured with the rest)
                     from adaptive_city_nerf_b200.graphs import GraphedStep
