@@ -454,14 +454,45 @@ def run_ours(args):
     # ---- end to end through the public API with HOST buffers ----
     rays_h = rays.cpu().pin_memory()
     gt_h = gt.cpu().pin_memory()
-    for _ in range(2):
-        float(step(rays_h.to(dev, non_blocking=True), gt_h.to(dev, non_blocking=True)))
+    # Every step's inputs are copied from pinned host memory and every step's loss is read back, all inside the timed
+    # region -- pipelined the way a training loop with an asynchronous loader is: the copy of step i+1's inputs runs on a
+    # copy stream while step i computes, and the loss of step i is read (4 bytes into pinned memory) once step i+1 has
+    # been launched, so the host never waits for the GPU with nothing queued behind it.
+    copy_stream = torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream(dev)
+    loss_h = torch.zeros(2, dtype=torch.float32).pin_memory()
+
+    def fetch():
+        with torch.cuda.stream(copy_stream):
+            r, g = rays_h.to(dev, non_blocking=True), gt_h.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return r, g, ev
+
+    def run_e2e(n):
+        pending = None
+        nxt = fetch()
+        for i in range(n):
+            r, g, ev = nxt
+            main.wait_event(ev)
+            r.record_stream(main); g.record_stream(main)
+            nxt = fetch() if i + 1 < n else None
+            loss = step(r, g)
+            loss_h[i & 1].copy_(loss.detach(), non_blocking=True)          # D2H read of the step's result
+            done = torch.cuda.Event()
+            done.record(main)
+            if pending is not None:
+                pending[0].synchronize()                                    # the previous step's loss has landed
+                _ = float(loss_h[pending[1]])
+            pending = (done, i & 1)
+        pending[0].synchronize()
+        return float(loss_h[pending[1]])
+
+    run_e2e(2)
     sync()
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        loss = step(rays_h.to(dev, non_blocking=True), gt_h.to(dev, non_blocking=True))
-        loss_val = float(loss)                      # D2H read of the step's result
+    loss_val = run_e2e(args.steps)
     e1.record()
     sync()
     ms_e2e = e0.elapsed_time(e1)
