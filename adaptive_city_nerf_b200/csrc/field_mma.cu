@@ -622,15 +622,18 @@ int launch_bwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride
     int64_t grid = (ntiles + BNS - 1) / BNS;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
     const ScatterArgs none{};
+#ifdef ACN_DEBUG_BUILD
     if (sc) {
-        if constexpr (E <= 32) {             // the fused table scatter: E = 2 L, L <= 16
+        if constexpr (E <= 32) {             // the single-role fused table scatter (debug library): E = 2 L, L <= 16
             ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<E, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_field_bwd_mma<E, false, true><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
                                                                                  (const float4*)d_rgb_sigma, absmax, *g, nullptr, nullptr, *sc, range);
         } else {
             ACN_REQUIRE(false, ACN_EUNSUPPORTED, "acn_render_expert_bwd: encoding width %d > 32", E);
         }
-    } else if (kTraceBuild && g_field_trace && E == 32) {          // the timeline build of the kernel (tools/field_trace.py --bwd)
+    } else
+#endif
+    if (kTraceBuild && g_field_trace && E == 32) {          // the timeline build of the kernel (tools/field_trace.py --bwd)
         ACN_CUDA(cudaFuncSetAttribute(k_field_bwd_mma<32, kTraceBuild, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_field_bwd_mma<32, kTraceBuild, false><<<(int)grid, BNS * 256, smem, st>>>((const __half*)enc, dirs, dirs_stride, dirs_group, P, G, *w,
                                                                               (const float4*)d_rgb_sigma, absmax, *g, d_enc, g_field_trace, none, range);
@@ -643,8 +646,6 @@ int launch_bwd(acn_ctx* ctx, const void* enc, const float* dirs, int dirs_stride
     return ACN_OK;
 }
 
-// loss scale: max |dL/dy| over the batch -> one word of context scratch (a ring, so calls in flight on different
-// streams do not share a word)
 }  // namespace
 
 #ifdef ACN_DEBUG_BUILD
@@ -685,16 +686,18 @@ int acn_field_bwd_tc(acn_ctx* ctx, const void* enc, int enc_dtype, const float* 
     }
 }
 
-// Fully fused backward of one expert on a batch of points (SURVEY 8b acn_render_expert_bwd): fused MLP backward +
-// hash-table gradient scatter in ONE kernel; d_enc never exists in HBM.
-extern "C" int acn_render_expert_bwd(acn_ctx* ctx, const float* x_or_null, int x_stride, const float* rays8_or_null,
+// The SINGLE-ROLE fused backward (k_field_bwd_mma<.., SCAT>: every MLP thread scatters its own d enc columns between its
+// epilogues), superseded by the warp-specialised kernel of expert_bwd.cu (8.9 vs 10.0 ms).  Debug library only: the
+// cross-check / A-B partner of acn_render_expert_bwd (tools/prof_fused_bwd.py, tests/test_gpu_tc.py); same arguments.
+#ifdef ACN_DEBUG_BUILD
+extern "C" int acn_debug_render_expert_bwd_single(acn_ctx* ctx, const float* x_or_null, int x_stride, const float* rays8_or_null,
                                      const float* t_vals_or_null, int64_t P, int S, const int32_t* range_or_null,
                                      const float* box6_or_null, int L, int F,
                                      int log2T, const int32_t* res, int interp, const void* enc_f16, const float* dirs,
                                      int dirs_stride, int dirs_group, int H, int G, int C, const acn_field_weights* w,
                                      const float* d_rgb_sigma, const acn_field_grads* g, float* dtable, acn_stream stream) {
     ACN_CHECK_CTX(ctx);
-    const char* fn = "acn_render_expert_bwd";
+    const char* fn = "acn_debug_render_expert_bwd_single";
     ACN_REQUIRE(P >= 0, ACN_EINVAL, "%s: negative P", fn);
     ACN_REQUIRE(F == 2 && (L == 8 || L == 16), ACN_EUNSUPPORTED, "%s: built for F = 2 and 8 or 16 levels (got L=%d, F=%d)", fn, L, F);
     ACN_REQUIRE(log2T >= 1 && log2T <= 24 && res, ACN_EINVAL, "%s: bad table size / res table", fn);
@@ -720,3 +723,4 @@ extern "C" int acn_render_expert_bwd(acn_ctx* ctx, const float* x_or_null, int x
     if (E == 16) return launch_bwd<16>(ctx, enc_f16, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, nullptr, &sc, range_or_null, st);
     return launch_bwd<32>(ctx, enc_f16, dirs, dirs_stride, dirs_group, P, G, w, d_rgb_sigma, slot, g, nullptr, &sc, range_or_null, st);
 }
+#endif

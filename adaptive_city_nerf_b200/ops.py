@@ -338,6 +338,33 @@ def render_expert_bwd(enc: Tensor, pos: Sequence[Tensor], dirs: Tensor, dirs_str
     return grads
 
 
+def debug_render_expert_bwd_single(enc: Tensor, pos: Sequence[Tensor], dirs: Tensor, dirs_stride: int, dirs_group: int,
+                                   ws: Sequence[Tensor], d_rgb_sigma: Tensor, need: Sequence[bool], spec: "GridSpec",
+                                   box6: Optional[Tensor], dtable: Tensor):
+    """The single-role fused backward of the debug library (acn_debug_render_expert_bwd_single): cross-check / A-B partner
+    of render_expert_bwd; same arguments and results."""
+    l, chk, dctx = _dbg()
+    P = enc.shape[0]
+    E, H, G, C = _field_dims(ws)
+    dev = enc.device
+    flat = torch.zeros(sum(w.numel() for w, n in zip(ws, need) if n), dtype=torch.float32, device=dev)
+    grads: List[Optional[Tensor]] = []
+    off = 0
+    for w, n in zip(ws, need):
+        grads.append(flat[off:off + w.numel()].view(w.shape) if n else None)
+        off += w.numel() if n else 0
+    wst, gst = pack_weights(ws), pack_weights(grads)
+    if len(pos) == 2:
+        rays, t = pos
+        x, xs, S = None, 3, t.shape[1]
+    else:
+        x, xs, rays, t, S = pos[0], pos[0].stride(0), None, None, 1
+    chk(l.acn_debug_render_expert_bwd_single(dctx(dev), ptr(x), xs, ptr(rays), ptr(t), P, S, None, ptr(box6), spec.L, spec.F, spec.log2T,
+                                             ptr(_grid_res(spec, dev)), spec.interp, ptr(enc), ptr(dirs), dirs_stride, dirs_group,
+                                             H, G, C, C_.byref(wst), ptr(d_rgb_sigma), C_.byref(gst), ptr(dtable), stream(dev)))
+    return grads
+
+
 #: set False to run the two-kernel backward (MLP backward -> d_enc in HBM -> scatter); tests cross-check the two
 FUSED_EXPERT_BWD = True
 

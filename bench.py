@@ -47,11 +47,11 @@ FUSED_BWD_BYTES = 2 * 1024 + 64 + 16
 GRID_CORNERS = 16 * 8                          # (level, corner) table rows a sample gathers forward / updates backward
 # committed ncu captures (`--set full`, one launch of each kernel at this workload): kernel name in the capture per entry
 # point; `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of that launch is READ FROM THESE FILES
-NCU_FILES = ["profiles/r02_v5_stages_ncu_full_summary.csv", "profiles/r02_v3_fused_bwd_ncu_full_summary.csv",
+NCU_FILES = ["profiles/r02_v6_stages_ncu_full_summary.csv", "profiles/r02_v5_stages_ncu_full_summary.csv", "profiles/r02_v3_fused_bwd_ncu_full_summary.csv",
              "profiles/r01_v3_stages_ncu_full_summary.csv"]
 NCU_KERNEL = {"acn_hashgrid_fwd_rays": "k_hashgrid_fwd<2, __half>", "acn_hashgrid_bwd_rays": "k_hashgrid_bwd_march<float>",
               "acn_field_fwd": "k_field_fwd_mma<32, 0>", "acn_field_bwd": "k_field_bwd_mma<32, 0>",
-              "acn_render_expert_bwd": "k_field_bwd_mma<32, 0, 1>", "acn_render_expert_fwd": "k_expert_fwd<32, 16>", "acn_composite_fwd": "k_composite_fwd",
+              "acn_render_expert_bwd": "k_expert_bwd<32>", "acn_render_expert_fwd": "k_expert_fwd<32, 16>", "acn_composite_fwd": "k_composite_fwd",
               "acn_composite_bwd": "k_composite_bwd"}
 
 

@@ -52,6 +52,16 @@ int acn_debug_field_trace(acn_ctx*, long long* trace_or_null);
 int acn_debug_l2_probe(acn_ctx*, int mode, int bytes_per_access, void* buf, int64_t buf_bytes, int iters, int grid,
                        float* sink, acn_stream);
 
+/* The single-role fused backward (every MLP thread scatters its own d enc columns between its epilogues), superseded in
+ * the product by the warp-specialised acn_render_expert_bwd: same arguments, same results to fp32 summation order.  The
+ * A/B partner of tools/prof_fused_bwd.py and the cross-check of tests/test_gpu_tc.py. */
+int acn_debug_render_expert_bwd_single(acn_ctx*, const float* x_or_null, int x_stride, const float* rays8_or_null,
+                                       const float* t_vals_or_null, int64_t P, int S, const int32_t* range_or_null,
+                                       const float* box6_or_null, int L, int F,
+                                       int log2T, const int32_t* res, int interp, const void* enc_f16, const float* dirs,
+                                       int dirs_stride, int dirs_group, int H, int G, int C, const acn_field_weights* w,
+                                       const float* d_rgb_sigma, const acn_field_grads* g, float* dtable, acn_stream);
+
 /* 16-byte scattered REDs from `grid` CTAs of `block` threads in which only `active_lanes` lanes of every warp issue
  * them, with `work` dependent integer operations between two REDs of a thread (tools/red_probe.py): the RED rate an SM
  * reaches with few resident warps and partly filled RED instructions.  REDs per launch = grid * block / 32 * active_lanes

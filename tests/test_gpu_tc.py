@@ -224,7 +224,7 @@ def test_field_fp16_other_widths_and_ray_mode(E, G, mode):
 
 @pytest.mark.parametrize("mode,L,log2T,interp", [("rays", 16, 14, "Linear"), ("points", 16, 12, "Smoothstep"), ("rays", 8, 10, "Linear")])
 def test_fused_expert_backward_matches_two_kernel_path(mode, L, log2T, interp):
-    """acn_render_expert_bwd (MLP backward + table scatter in one kernel, d_enc never in HBM) against acn_field_bwd ->
+    """acn_render_expert_bwd (MLP backward + table scatter in one warp-specialised kernel, d_enc never in HBM) against acn_field_bwd ->
     d_enc -> acn_hashgrid_bwd[_rays]: the MLP arithmetic is the same kernel code, so the weight gradients agree to the
     order of the atomics and the table gradient to fp32 summation order (2e-5 relative L2; 1e-6 of the largest entry)."""
     from adaptive_city_nerf_b200 import ops, _lib
@@ -265,6 +265,12 @@ def test_fused_expert_backward_matches_two_kernel_path(mode, L, log2T, interp):
     assert float(dt2.abs().max()) > 0
     assert _rel_l2(dt1, dt2) < 2e-5, _rel_l2(dt1, dt2)
     assert float((dt1 - dt2).abs().max()) < 1e-6 * float(dt2.abs().max()) + 1e-30
+    # the single-role fused kernel of the debug library (the shipped kernel's predecessor and A/B partner): same results
+    dt5 = torch.zeros_like(table)
+    g5 = ops.debug_render_expert_bwd_single(enc, pos, dirs, ds, dg, wt, dy, [True] * 14, spec, box6, dt5)
+    for key, a, b in zip(synth.EXPERT_KEYS, g1, g5):
+        assert _rel_l2(a, b) < 1e-5, (key, _rel_l2(a, b))
+    assert _rel_l2(dt1, dt5) < 2e-5, _rel_l2(dt1, dt5)
     # a ragged tail (P not a multiple of the 128-point tile) and only some weight gradients requested
     Pq = P - 37 * S if mode == "rays" else P - 1777
     need = [i % 3 != 0 for i in range(14)]

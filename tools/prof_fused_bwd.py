@@ -44,6 +44,10 @@ def fused(dt):
     return ops.render_expert_bwd(enc, (rays, t), rays[:, 3:], 8, S, ws, d_rs, need, spec, box6, dt)
 
 
+def fused_single(dt):        # the single-role kernel of the debug library (the shipped kernel's predecessor)
+    return ops.debug_render_expert_bwd_single(enc, (rays, t), rays[:, 3:], 8, S, ws, d_rs, need, spec, box6, dt)
+
+
 def timed(fn, reps):
     dt = torch.zeros_like(table)
     for _ in range(2):
@@ -71,5 +75,5 @@ else:
     rel = float((d1 - d2).double().norm() / d2.double().norm())
     relw = max(float((a - b).double().norm() / (b.double().norm() + 1e-300)) for a, b in zip(g1, g2))
     out = {"rays": N, "samples": S, "two_kernel_ms": timed(two_kernel, 10), "fused_ms": timed(fused, 10),
-           "table_grad_rel_l2": rel, "weight_grad_rel_l2_max": relw}
+           "fused_single_role_ms": timed(fused_single, 10), "table_grad_rel_l2": rel, "weight_grad_rel_l2_max": relw}
     print(json.dumps(out))
