@@ -33,7 +33,9 @@ constexpr uint32_t XTMEM_COLS = XNC * 128;
 template <int NP> struct XCfg {
     static constexpr int threads = XNC * 128 + NP * 32;
     static constexpr int slots = NP / 4;
-    static constexpr int stages = NP / 4;
+    // a stage's tiles must all go to the SAME consumer warpgroup (an mbarrier waiter may be at most one phase behind):
+    // the stage count is kept a multiple of the XNC consumer warpgroups
+    static constexpr int stages = (NP / 4) % XNC == 0 ? NP / 4 : XNC * (NP / 4);
 };
 constexpr int XNP = 16;
 

@@ -9,7 +9,4 @@ d=json.loads(sys.stdin.read())
 print('ms/step',round(d['ms_per_step'],3),'fwd',d['kernels']['acn_render_expert_fwd']['avg_ms'],'render',round(d['render']['ms_per_batch'],3))
 " || tail -20 gpurun_out/bench_$name.log
 }
-run nostream A=1
-run stream3 ACN_DEBUG_STREAM_CHUNK=3
-run stream2 ACN_DEBUG_STREAM_CHUNK=2
-run stream1 ACN_DEBUG_STREAM_CHUNK=1
+run np12 A=1
