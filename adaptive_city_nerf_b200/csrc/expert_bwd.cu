@@ -10,7 +10,7 @@
 //   * 8 SCATTER warps (2 per TMEM lane quarter; warp = 32 consecutive points) wait for that MMA's commit, read their
 //     columns of the window (tcgen05.ld), release it, and add w_corner * g to the 8 corner rows of the table gradient at
 //     each of their levels -- the arithmetic of k_hashgrid_bwd, with its pair REDs and the run-merging of the coarse
-//     levels.  Levels are dealt round-robin (part p: p, p + 2, ...) so both parts carry two of the costlier coarse levels.
+//     levels.  Levels are dealt round-robin (part p: p, p + 2, ...) so both parts carry one of the costlier run-merged coarse levels.
 //
 // Measured on the bench batch (2^24 samples, profiles/r02_v6_fused_bwd_variants.txt): 8.9 ms, against 10.0 ms for the
 // single-role kernel (k_field_bwd_mma<.., SCAT>: every MLP thread scatters its own columns between its epilogues, whose
@@ -28,7 +28,7 @@ constexpr int YSW = 8;                       // scatter warps
 constexpr int YPARTS = YSW / 4;              // ... per TMEM lane quarter: each takes every YPARTS-th level
 constexpr int YTHREADS = (YCW + YSW) * 32;   // 512 threads x 128 registers = the whole register file
 constexpr uint32_t COL_DENC = 448;           // per-slot 32-column window the last dgrad writes d_enc into (448 .. 511)
-constexpr int DEDUP_LEVELS = 4;
+constexpr int DEDUP_LEVELS = 2;           // run-merged coarse levels: 2 measured best (8.71 ms; 3: 8.71, 4: 8.81), one per scatter part
 
 template <int E> struct YMap {
     static constexpr uint32_t slots = 0;
