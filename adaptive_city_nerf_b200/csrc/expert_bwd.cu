@@ -30,6 +30,8 @@ constexpr int YTHREADS = (YCW + YSW) * 32;   // 512 threads x 128 registers = th
 constexpr uint32_t COL_DENC = 448;           // per-slot 32-column window the last dgrad writes d_enc into (448 .. 511)
 constexpr int DEDUP_LEVELS = 2;           // run-merged coarse levels: 2 measured best (8.71 ms; 3: 8.71, 4: 8.81), one per scatter part
 
+static_assert(DEDUP_LEVELS % YPARTS == 0, "every scatter part takes the same number of run-merged levels");
+
 template <int E> struct YMap {
     static constexpr uint32_t slots = 0;
     static constexpr uint32_t w = BNS * SlotMap<E>::bytes;
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(YTHREADS, 1) k_expert_bwd(
                     const int l = part + j * YPARTS;
                     const float gx = v[2 * j] * inv_scale, gy = v[2 * j + 1] * inv_scale;
                     const bool act = son && !(gx == 0.0f && gy == 0.0f);      // fully occluded samples scatter nothing
-                    const bool dedup = l < DEDUP_LEVELS;                       // warp-uniform
+                    const bool dedup = j * YPARTS < DEDUP_LEVELS;              // = (l < DEDUP_LEVELS), a constant once the loop is unrolled
                     if (!dedup && !act) continue;
                     const GridCell c = grid_cell(upos[0], upos[1], upos[2], umma::lds_f32(sb + M::res + 4u * l), sc.interp);
                     const float wx[2] = { 1.0f - c.wx, c.wx }, wy[2] = { 1.0f - c.wy, c.wy }, wz[2] = { 1.0f - c.wz, c.wz };
