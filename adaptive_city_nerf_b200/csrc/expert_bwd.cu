@@ -150,13 +150,11 @@ __global__ void __launch_bounds__(YTHREADS, 1) k_expert_bwd(
                 umma::wait_ld();
                 umma::fence_before_sync();
                 mbar_arrive_a(bfree);          // the chain issuer may overwrite the window with the slot's next tile
-#pragma unroll
-                for (int j = 0; j < LPP; ++j) {
-                    const int l = part + j * YPARTS;
-                    const float gx = v[2 * j] * inv_scale, gy = v[2 * j + 1] * inv_scale;
+                // j = 0: this part's run-merged coarse level; j >= 1: fine levels, one ROLLED loop (the unrolled form was 7 copies of
+                // the cell arithmetic and its REDs: instruction-cache footprint matters with two roles running different code)
+                auto one_level = [&](int l, float gx, float gy, bool dedup) {
                     const bool act = son && !(gx == 0.0f && gy == 0.0f);      // fully occluded samples scatter nothing
-                    const bool dedup = j * YPARTS < DEDUP_LEVELS;              // = (l < DEDUP_LEVELS), a constant once the loop is unrolled
-                    if (!dedup && !act) continue;
+                    if (!dedup && !act) return;
                     const GridCell c = grid_cell(upos[0], upos[1], upos[2], umma::lds_f32(sb + M::res + 4u * l), sc.interp);
                     const float wx[2] = { 1.0f - c.wx, c.wx }, wy[2] = { 1.0f - c.wy, c.wy }, wz[2] = { 1.0f - c.wz, c.wz };
                     float2 acc[8];
@@ -190,6 +188,15 @@ __global__ void __launch_bounds__(YTHREADS, 1) k_expert_bwd(
                     } else {
                         scatter_cell_f2(lt, c.x0, c.y0, c.z0, hmask, acc);
                     }
+                };
+                static_assert(DEDUP_LEVELS == YPARTS, "one run-merged level per part: j = 0");
+                one_level(part, v[0] * inv_scale, v[1] * inv_scale, true);
+#pragma unroll 1
+                for (int j = 1; j < LPP; ++j) {
+                    float gx = v[2], gy = v[3];                 // v[2j], v[2j+1] by a select chain: v stays in registers
+#pragma unroll
+                    for (int q = 2; q < LPP; ++q) { gx = j == q ? v[2 * q] : gx; gy = j == q ? v[2 * q + 1] : gy; }
+                    one_level(part + j * YPARTS, gx * inv_scale, gy * inv_scale, false);
                 }
             }
             if (!any) break;
