@@ -94,21 +94,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// Bounded wait: a descriptor bug must surface as a trap (CUDA error), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-#pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        if (ok) return;
-    }
-    __trap();
-}
+// Bounded wait (wall time, see mbar_wait_a below): a descriptor bug must surface as a trap (CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
 
 // ---- address-based variants (32-bit shared-space addresses keep every access STS/LDS and every MMA operand in
 // uniform registers; generic pointers into dynamic shared memory made ptxas emit generic LD/ST) -------------
@@ -118,11 +106,21 @@ __device__ __forceinline__ void mbar_init_a(uint32_t addr, uint32_t count) {
 __device__ __forceinline__ void commit_a(uint32_t addr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(addr) : "memory");
 }
-// (the spin loop is kept ROLLED: unrolled four times at ~40 wait sites it was half of the fused backward's code, and the two roles
-// of the warp-specialised kernels run different code at the same time -- 8.51 -> 8.18 ms from this pragma alone)
+// Bounded wait: a protocol bug must surface as a trap (CUDA error), never as a hung GPU.  The bound is WALL TIME (4 s of
+// %globaltimer, checked every 2^14 polls), not a poll count: how long one mbarrier.try_wait takes before it reports "not
+// yet" is implementation-defined, and a poll-count bound that is safe for one code shape is not for another -- with the loop
+// below kept rolled (it must be: unrolled four times at ~40 wait sites it was half of the fused backward's code, and the two
+// roles of the warp-specialised kernels run different code at the same time: 8.51 -> 8.18 ms from the pragma alone) 2^22
+// polls elapsed in legitimate waits about once in 10^2 training steps queued back to back.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+    unsigned long long t0 = 0;
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    for (uint32_t spin = 0;; ++spin) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -130,8 +128,12 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
         if (ok) return;
+        if ((spin & 0x3FFFu) == 0x3FFFu) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
     }
-    __trap();
 }
 // true in exactly one lane of a converged warp; the form ptxas recognises as "single thread" for tcgen05 issue
 __device__ __forceinline__ bool elect_one() {
