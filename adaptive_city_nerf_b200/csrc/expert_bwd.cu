@@ -12,7 +12,7 @@
 //     each of their levels -- the arithmetic of k_hashgrid_bwd, with its pair REDs and the run-merging of the coarse
 //     levels.  Levels are dealt round-robin (part p: p, p + 2, ...) so both parts carry one of the costlier run-merged coarse levels.
 //
-// Measured on the bench batch (2^24 samples, profiles/r02_v6_fused_bwd_variants.txt): 8.9 ms, against 10.0 ms for the
+// Measured on the bench batch (2^24 samples, profiles/r02_v6_fused_bwd_variants.txt): 8.2 - 8.4 ms, against 10.0 ms for the
 // single-role kernel (k_field_bwd_mma<.., SCAT>: every MLP thread scatters its own columns between its epilogues, whose
 // chain time and RED time add up) and 9.8 / 9.9 ms with 16 / 12 scatter warps at 64 / 80 registers: a RED holds its
 // payload and address registers until the memory system has taken it, so what counts is registers per scatter warp

@@ -100,17 +100,19 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md).  nvidia-smi needs a few hundred
+    milliseconds before its first line, longer than the timed region itself, so it is started before the warm-up and only
+    the lines that arrive between begin() and end() -- the timed region -- are summarised."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -119,20 +121,38 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *a):
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
+    def stop(self):
         if self.proc:
             self.proc.terminate()
             self.t.join(timeout=2)
 
+    def __enter__(self):
+        self.begin()
+        return self
+
+    def __exit__(self, *a):
+        self.end()
+
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        inside = [r for ts, r in self.rows if self.t0 is not None and self.t0 <= ts <= (self.t1 or ts)]
+        where = "timed region"
+        if not inside and self.rows and self.t0 is not None:       # region shorter than the sampling period: the line closest to it
+            inside = [min(self.rows, key=lambda tr: abs(tr[0] - 0.5 * (self.t0 + (self.t1 or self.t0))))[1]]
+            where = "nearest sample to the timed region (under the same load)"
+        sm = [float(r[0]) for r in inside if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in inside if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in inside if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "where": where}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -432,17 +452,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local).start()          # nvidia-smi is up and sampling by the time the timed region starts
     for _ in range(max(args.warmup, 3)):
         step(rays, gt)
     # ---- device-resident throughput (`value`): EXACTLY K steps between two events, nothing else on the stream ----
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    with clk:
         e0.record()
         for _ in range(args.steps):
             step(rays, gt)
         e1.record()
         sync()
+    clk.stop()
     ms = e0.elapsed_time(e1)
     # ---- the same K steps once more with a CUDA-event pair around every C-ABI call (per-kernel table, launch count);
     # the ~20 extra event records per step cost ~0.1 ms, which is why this pass is not the one `value` is taken from

@@ -159,3 +159,30 @@ def test_background_head_kernel_matches_the_torch_layers(N, Hb):
         assert float((p.grad - gr).norm()) <= 1e-5 * float(gr.norm()) + 1e-7
     half = ops.BackgroundFn.apply(d, mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias, True)
     assert half.dtype == torch.float16 and float((half.float() - ref).abs().max()) < 6e-4
+
+
+def test_many_training_steps_queued_back_to_back_do_not_fault():
+    """120 training steps launched without a host sync in between (what bench.py and a real training loop do): the
+    warp-specialised kernels' mbarrier waits are bounded by wall time, not by a poll count -- a poll-count bound faulted about
+    once per hundred queued steps (never with a sync after every step).  Loss finite and decreasing at the end."""
+    import bench
+    from adaptive_city_nerf_b200.nerfs.losses import mse_in_color_space
+    from adaptive_city_nerf_b200.nerfs.ray_rendering import render_rays
+    from adaptive_city_nerf_b200.optim import FusedAdam
+    dev = torch.device("cuda")
+    rays, gt, box = bench.gpu_workload(dev, 100)
+    rays, gt = rays[: 1 << 16].contiguous(), gt[: 1 << 16].contiguous()
+    model = bench.make_model(dev, box)
+    opt = FusedAdam([{"params": list(model.parameters()), "lr": 2e-3}], eps=1e-15)
+    losses = []
+    for _ in range(120):
+        with torch.autocast("cuda", dtype=torch.float16):
+            rgb, *_ = render_rays(model, rays, ray_samples=bench.SAMPLES, active_module=0, chunk=1 << 30)
+        loss = mse_in_color_space(rgb, gt, "linear")
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step(max_norm=1.0)
+        losses.append(loss.detach())
+    torch.cuda.synchronize()
+    ls = torch.stack(losses).cpu()
+    assert bool(torch.isfinite(ls).all()) and float(ls[-10:].mean()) < float(ls[:10].mean())
