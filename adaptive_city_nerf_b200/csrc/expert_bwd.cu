@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(YTHREADS, 1) k_expert_bwd(
         enc += r0 * E; dirs += r0 * dstride; d_rgb_sigma += r0;
         if (sc.x) sc.x += r0 * sc.xs;
     }
+    if (P <= 0) return;     // an empty bucket (the host never reads the counts): leave before staging weights / allocating TMEM
     using M = YMap<E>;
     using SM = SlotMap<E>;
     constexpr WMap wm = wmap(E);

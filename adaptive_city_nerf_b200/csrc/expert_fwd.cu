@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(XCfg<NP>::threads, 1) k_expert_fwd(
         a.x += r0 * a.xs; dirs += r0 * dstride; rgb_sigma += r0;
         if (enc_out) enc_out += r0 * E;
     }
+    if (P <= 0) return;     // an empty bucket (the host never reads the counts): leave before staging weights / allocating TMEM
     using CF = XCfg<NP>;
     constexpr int XST = CF::stages, XSLOTS = CF::slots, XTHREADS = CF::threads;
     using M = XMap<E, XST>;

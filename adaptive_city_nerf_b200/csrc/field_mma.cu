@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(FWG * 128, 1) k_field_fwd_mma(
         P = __ldg(range + 1) - r0;
         enc += r0 * E; dirs += r0 * dstride; rgb_sigma += r0;
     }
+    if (P <= 0) return;     // an empty bucket: leave before staging weights / allocating TMEM
     using M = FwdMap<E>;
     constexpr WMap wm = wmap(E);
     constexpr int EC = E / 8;
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(BNS * 256, 1) k_field_bwd_mma(
         if (d_enc) d_enc += r0 * E;
         if (sc.x) sc.x += r0 * sc.xs;
     }
+    if (P <= 0) return;     // an empty bucket: leave before staging weights / allocating TMEM
     using M = BwdMap<E>;
     using SM = SlotMap<E>;
     constexpr WMap wm = wmap(E);
