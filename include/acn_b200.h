@@ -168,7 +168,8 @@ int acn_render_expert_fwd(acn_ctx*, const float* x_or_null, int x_stride, const 
 /* Fused per-expert backward for the `active_module` / routed-bucket render path (SURVEY 8b acn_render_expert_bwd;
  * replaces autograd through nerfs/ray_rendering.py:317-325 -> models/inr/meta_ngp.py:226-241 ->
  * models/encodings.py:331-381): the tcgen05 MLP backward of acn_field_bwd(ACN_F16) and the hash-table gradient scatter
- * of acn_hashgrid_bwd in ONE kernel -- the (P, L*F) gradient of the encoding never exists in HBM.
+ * of acn_hashgrid_bwd in ONE warp-specialised kernel (csrc/expert_bwd.cu: chain warps run the MLP backward, scatter warps take
+ * each tile's encoding gradient out of a TMEM window and issue the REDs) -- the (P, L*F) gradient of the encoding never exists in HBM.
  * Positions: x_or_null (P,>=3) rows of stride x_stride, or rays8 (N,8) + t_vals (N,S) with P = N*S (p = o + d*t).
  * enc_f16 (P, L*F): the fp16 encoding the forward saved.  F = 2, L in {8,16}, Linear / Smoothstep.  Weight gradients
  * are accumulated into g, the table gradient into dtable (L*2^log2T, 2) fp32. */
